@@ -1,0 +1,866 @@
+// mqi_capi.cu -- the C ABI of include/mqi_b200.h on top of the sm_100a kernels.
+//
+// Host-side responsibilities only: device buffers, the calibration LUT (HU -> density -> RSP /
+// radiation-length coefficients), launch configuration, downloads.  No transport arithmetic runs on
+// the host and there is no CPU fallback: without a usable CUDA device every compute entry point
+// returns MQI_ENODEVICE.
+#include "../../include/mqi_b200.h"
+#include "mqi_device.cuh"
+#include "mqi_kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace mqib;
+
+namespace
+{
+#include "mqi_tables_data.inc"   // generated from moquimc_b200/data/mqi_tables_v1.bin by build.py
+
+thread_local std::string g_err;
+
+int
+fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(MQI_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));               \
+    } while (0)
+
+struct HostScorer {
+    int         kind = 0;
+    std::string name;
+    uint64_t    capacity = 0;
+    double*     d_dense  = nullptr;
+    bool        external = false;
+    DijSlot*    d_table  = nullptr;
+};
+
+const float* table_ptr(int t) { return reinterpret_cast<const float*>(k_tables_blob + 16) + 600 * t; }
+const float* correction_ptr() { return reinterpret_cast<const float*>(k_tables_blob + 16) + 3600; }
+
+// ---- calibration on the host side, only to fill the LUT -----------------------------------------
+// patient_material_t::hu_to_density  materials/mqi_patient_materials.hpp:514-542
+float
+host_hu_to_density(int hu) {
+    hu = hu < -1000 ? -1000 : (hu > 2995 ? 2995 : hu);
+    float rho_mass;
+    if (hu < -98) rho_mass = 0.00121 + 0.001029700665188 * (1000.0 + hu);
+    else if (hu < 15) rho_mass = 1.018 + 0.000893 * hu;
+    else if (hu < 23) rho_mass = 1.03;
+    else if (hu < 101) rho_mass = 1.003 + 0.001169 * hu;
+    else if (hu < 2001) rho_mass = 1.017 + 0.000592 * hu;
+    else if (hu < 2995) rho_mass = 2.201 + 0.0005 * (-2000.0 + hu);
+    else rho_mass = 4.54;
+    rho_mass *= correction_ptr()[hu + 1000];
+    rho_mass /= 1000.0;
+    return rho_mass;
+}
+
+inline float
+lerp_ref(float x, float x0, float x1, float y0, float y1) {
+    return (x1 == x0) ? y0 : y0 + (x - x0) * (y1 - y0) / (x1 - x0);
+}
+
+// spr_default / radiation_length_default (:414-473) folded into per-density coefficients
+MatEntry
+make_mat_entry(float rho, int variant) {
+    MatEntry m;
+    std::memset(&m, 0, sizeof(m));
+    m.rho     = rho;
+    m.inv_rho = rho > 0.f ? 1.0f / rho : 0.f;
+    const float d = rho * 1000.0;
+    const bool  water_shortcut = (variant == MQI_PHYSICS_DEBUG) && std::fabs(d - 1.0) < 1e-3;
+    if (water_shortcut) {
+        m.a = 1.0f;
+    } else if (d <= 0.26f) {
+        m.a = d < 0.0012f ? 0.0f : lerp_ref(d, 0.0012f, 0.26f, 0.8815f, 0.9925f);
+    } else {
+        const float P = (float) ((double) powf(d, -0.7f) - 1.0);
+        if (d >= 0.9f) {
+            m.b = 1.0f;
+            m.c = P;
+        } else {
+            const float w = (d - 0.26f) / (0.9f - 0.26f);
+            m.a = 0.9925f - 0.9925f * w;
+            m.b = w;
+            m.c = w * P;
+        }
+    }
+    // radiation length
+    float x0;
+    if (water_shortcut) {
+        x0 = 360.863f;
+    } else {
+        float f = 0.f;
+        if (d <= 0.26f) f = 0.9857 + 0.0085 * d;
+        else if (d <= 0.9f) f = 1.0446 - 0.2180 * d;
+        else f = 1.19 + 0.44 * std::log((double) d - 0.44);
+        x0 = (0.001f * 360.863f) / (d * 0.001 * f);
+    }
+    m.pad    = x0;
+    m.inv_x0 = 1.0f / x0;
+    // rsp(rho, Ek = 0) for the zero-energy delta daughter of the debug variant
+    float rsp0;
+    if (m.c != 0.f) rsp0 = INFINITY;   // Ek^-0.3421 -> inf
+    else rsp0 = m.a + m.b * 1.0123f;
+    m.inv_rsp0 = (std::isfinite(rsp0) && rsp0 > 0.f) ? 1.0f / rsp0 : 0.f;
+    return m;
+}
+
+float
+dedx_term0() {   // physics_constants::two_pi_re2_mc2_h2o  base/mqi_physics_constants.hpp:30-33
+    const float cm3            = 10.0f * 10.0f * 10.0f;
+    const float re             = 2.8179403262e-12;
+    const float re_sq          = re * re;
+    const float two_pi_re2_mc2 = 2.0 * M_PI * re_sq * 0.510998928f;
+    return two_pi_re2_mc2 * 3.3428e+23 / cm3;
+}
+}   // namespace
+
+struct mqi_handle {
+    int          device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+    int          sm_count = 148;
+    int          variant  = MQI_PHYSICS_RELEASE;
+    uint32_t     quirks   = 0;
+    int          accum    = MQI_ACCUM_ATOMIC;
+    int          count_steps = 0;
+    int          blocks_per_sm_override = 0;
+    // physics tables
+    float4* d_tab_a = nullptr;
+    float4* d_tab_b = nullptr;
+    float*  d_correction = nullptr;
+    // grid
+    bool      has_grid = false;
+    int       nx = 0, ny = 0, nz = 0;
+    float*    d_edges = nullptr;
+    uint16_t* d_mat   = nullptr;
+    MatEntry* d_lut   = nullptr;
+    int       lut_size = 0;
+    float     rot[9]   = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    float     trans[3] = { 0, 0, 0 };
+    int       identity = 1;
+    // source
+    BeamletDev*         d_beamlets = nullptr;
+    unsigned long long* d_cum      = nullptr;
+    uint32_t            n_spots    = 0;
+    uint64_t            total_histories = 0;
+    VertexDev*          d_vertices = nullptr;
+    uint32_t*           d_spot_ids = nullptr;
+    uint64_t            n_vertices = 0;
+    // scorers
+    std::vector<HostScorer> scorers;
+    unsigned long long*     d_counters = nullptr;
+    mqi_run_stats           stats {};
+};
+
+namespace
+{
+size_t nvox(const mqi_handle* h) { return (size_t) h->nx * h->ny * h->nz; }
+
+int
+activate(mqi_handle* h) {
+    if (!h) return fail(MQI_EINVAL, "null handle");
+    CU(cudaSetDevice(h->device));
+    return MQI_OK;
+}
+
+void
+free_grid(mqi_handle* h) {
+    cudaFree(h->d_edges);
+    cudaFree(h->d_mat);
+    cudaFree(h->d_lut);
+    h->d_edges = nullptr;
+    h->d_mat   = nullptr;
+    h->d_lut   = nullptr;
+    h->has_grid = false;
+}
+
+int
+set_grid_common(mqi_handle* h, const float* xe, int n_xe, const float* ye, int n_ye, const float* ze, int n_ze,
+                const float* rot, const float* trans) {
+    if (!xe || !ye || !ze || n_xe < 2 || n_ye < 2 || n_ze < 2) return fail(MQI_EINVAL, "bad grid edges");
+    const size_t nv = (size_t) (n_xe - 1) * (n_ye - 1) * (n_ze - 1);
+    if (nv >= 0x7fffffffull) return fail(MQI_EINVAL, "grid has more than 2^31-1 voxels (scorer keys are 32-bit, B6)");
+    for (int i = 1; i < n_xe; ++i) if (!(xe[i] > xe[i - 1])) return fail(MQI_EINVAL, "x edges must increase");
+    for (int i = 1; i < n_ye; ++i) if (!(ye[i] > ye[i - 1])) return fail(MQI_EINVAL, "y edges must increase");
+    for (int i = 1; i < n_ze; ++i) if (!(ze[i] > ze[i - 1])) return fail(MQI_EINVAL, "z edges must increase");
+    if (transport_smem_bytes(n_xe - 1, n_ye - 1, n_ze - 1) > 200 * 1024) return fail(MQI_EINVAL, "too many grid edges for shared memory");
+    // scorers are sized by the grid: drop dense accumulators of a previous grid
+    for (auto& s : h->scorers) {
+        if (s.d_dense && !s.external) cudaFree(s.d_dense);
+        if (!s.external) s.d_dense = nullptr;
+    }
+    free_grid(h);
+    h->nx = n_xe - 1; h->ny = n_ye - 1; h->nz = n_ze - 1;
+    std::vector<float> e;
+    e.insert(e.end(), xe, xe + n_xe);
+    e.insert(e.end(), ye, ye + n_ye);
+    e.insert(e.end(), ze, ze + n_ze);
+    CU(cudaMalloc(&h->d_edges, e.size() * sizeof(float)));
+    CU(cudaMemcpyAsync(h->d_edges, e.data(), e.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const float I[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    std::memcpy(h->rot, rot ? rot : I, sizeof(I));
+    h->trans[0] = trans ? trans[0] : 0.f; h->trans[1] = trans ? trans[1] : 0.f; h->trans[2] = trans ? trans[2] : 0.f;
+    h->identity = (std::memcmp(h->rot, I, sizeof(I)) == 0 && h->trans[0] == 0.f && h->trans[1] == 0.f && h->trans[2] == 0.f) ? 1 : 0;
+    return MQI_OK;
+}
+
+int
+upload_hu_lut(mqi_handle* h, float density_scale) {
+    std::vector<MatEntry> lut(3996);
+    for (int i = 0; i < 3996; ++i) {
+        float rho = host_hu_to_density(i - 1000);
+        if (density_scale != 1.0f) rho *= density_scale;
+        lut[i] = make_mat_entry(rho, h->variant);
+    }
+    CU(cudaMalloc(&h->d_lut, lut.size() * sizeof(MatEntry)));
+    CU(cudaMemcpyAsync(h->d_lut, lut.data(), lut.size() * sizeof(MatEntry), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->lut_size = (int) lut.size();
+    return MQI_OK;
+}
+
+int
+ensure_scorer_buffers(mqi_handle* h) {
+    for (auto& s : h->scorers) {
+        if (s.kind == MQI_SCORER_DIJ) {
+            if (!s.d_table) {
+                CU(cudaMalloc(&s.d_table, s.capacity * sizeof(DijSlot)));
+                CU(launch_dij_clear(s.d_table, s.capacity, h->stream));
+            }
+        } else if (!s.d_dense) {
+            CU(cudaMalloc(&s.d_dense, nvox(h) * sizeof(double)));
+            CU(cudaMemsetAsync(s.d_dense, 0, nvox(h) * sizeof(double), h->stream));
+        }
+    }
+    return MQI_OK;
+}
+
+void
+fill_params(const mqi_handle* h, Params& p) {
+    std::memset(&p, 0, sizeof(p));
+    p.g.nx = h->nx; p.g.ny = h->ny; p.g.nz = h->nz;
+    p.g.edges = h->d_edges;
+    p.g.mat   = h->d_mat;
+    p.g.lut   = h->d_lut;
+    p.g.lut_size = h->lut_size;
+    p.g.identity = h->identity;
+    std::memcpy(p.g.rot_fwd, h->rot, sizeof(h->rot));
+    std::memcpy(p.g.trans, h->trans, sizeof(h->trans));
+    p.src.beamlets = h->d_beamlets;
+    p.src.cum      = h->d_cum;
+    p.src.n_spots  = h->n_spots;
+    p.src.vertices = h->d_vertices;
+    p.src.spot_ids = h->d_spot_ids;
+    p.n_scorers = (int) h->scorers.size();
+    for (int i = 0; i < p.n_scorers; ++i) {
+        p.sc[i].kind     = h->scorers[i].kind;
+        p.sc[i].dense    = h->scorers[i].d_dense;
+        p.sc[i].table    = h->scorers[i].d_table;
+        p.sc[i].capacity = h->scorers[i].capacity;
+    }
+    p.quirks      = h->quirks;
+    p.accum_mode  = h->accum;
+    p.count_steps = h->count_steps;
+    p.dedx_term0  = dedx_term0();
+    p.tab_a       = h->d_tab_a;
+    p.tab_b       = h->d_tab_b;
+    p.counters    = h->d_counters;
+}
+
+template<typename T>
+struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+};
+}   // namespace
+
+extern "C" {
+
+const char* mqi_last_error(void) { return g_err.c_str(); }
+const char* mqi_version(void) { return "moquimc_b200 0.1 (sm_100a)"; }
+
+int
+mqi_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int
+mqi_create(int device_id, mqi_handle** out) {
+    if (!out) return fail(MQI_EINVAL, "out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(MQI_ENODEVICE, "no usable CUDA device (this library has no CPU fallback)");
+    }
+    if (device_id < 0 || device_id >= n) return fail(MQI_EINVAL, "device id out of range");
+    if (std::memcmp(k_tables_blob, "MQITBL1", 7) != 0) return fail(MQI_ESTATE, "embedded physics tables are corrupt");
+    mqi_handle* h = new mqi_handle;
+    h->device     = device_id;
+    CU(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device_id));
+    h->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    // physics tables -> interleaved float4 arrays (one 16-byte shared-memory load per grid point)
+    std::vector<float4> a(kTableN), b(kTableN);
+    for (int i = 0; i < kTableN; ++i) {
+        a[i] = make_float4(table_ptr(0)[i], table_ptr(1)[i], table_ptr(2)[i], 0.f);
+        b[i] = make_float4(table_ptr(3)[i], table_ptr(4)[i], table_ptr(5)[i], 0.f);
+    }
+    CU(cudaMalloc(&h->d_tab_a, kTableN * sizeof(float4)));
+    CU(cudaMalloc(&h->d_tab_b, kTableN * sizeof(float4)));
+    CU(cudaMalloc(&h->d_correction, 3996 * sizeof(float)));
+    CU(cudaMalloc(&h->d_counters, C_COUNT * sizeof(unsigned long long)));
+    CU(cudaMemcpy(h->d_tab_a, a.data(), kTableN * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_tab_b, b.data(), kTableN * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_correction, correction_ptr(), 3996 * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemset(h->d_counters, 0, C_COUNT * sizeof(unsigned long long)));
+    *out = h;
+    return MQI_OK;
+}
+
+int
+mqi_destroy(mqi_handle* h) {
+    if (!h) return MQI_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_grid(h);
+    for (auto& s : h->scorers) {
+        if (s.d_dense && !s.external) cudaFree(s.d_dense);
+        cudaFree(s.d_table);
+    }
+    cudaFree(h->d_tab_a); cudaFree(h->d_tab_b); cudaFree(h->d_correction); cudaFree(h->d_counters);
+    cudaFree(h->d_beamlets); cudaFree(h->d_cum); cudaFree(h->d_vertices); cudaFree(h->d_spot_ids);
+    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return MQI_OK;
+}
+
+int
+mqi_set_physics(mqi_handle* h, int variant, uint32_t quirks) {
+    if (!h) return fail(MQI_EINVAL, "null handle");
+    if (variant != MQI_PHYSICS_RELEASE && variant != MQI_PHYSICS_DEBUG) return fail(MQI_EINVAL, "unknown physics variant");
+    if (h->has_grid && variant != h->variant) return fail(MQI_ESTATE, "set the physics variant before the grid (the calibration LUT depends on it)");
+    h->variant = variant;
+    h->quirks  = quirks;
+    return MQI_OK;
+}
+
+static int
+set_grid_hu_impl(mqi_handle* h, const float* xe, int n_xe, const float* ye, int n_ye, const float* ze, int n_ze,
+                 const void* hu, bool on_device, float density_scale, const float* rot, const float* trans) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (!hu) return fail(MQI_EINVAL, "hu is null");
+    rc = set_grid_common(h, xe, n_xe, ye, n_ye, ze, n_ze, rot, trans);
+    if (rc) return rc;
+    const size_t nv = nvox(h);
+    CU(cudaMalloc(&h->d_mat, nv * sizeof(uint16_t)));
+    if (on_device) {
+        CU(launch_hu_to_material(static_cast<const int16_t*>(hu), h->d_mat, nv, h->stream));
+    } else {
+        DevBuf<int16_t> tmp;
+        CU(tmp.alloc(nv));
+        CU(cudaMemcpyAsync(tmp.p, hu, nv * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream));
+        CU(launch_hu_to_material(tmp.p, h->d_mat, nv, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    rc = upload_hu_lut(h, density_scale);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    h->has_grid = true;
+    return MQI_OK;
+}
+
+int
+mqi_set_grid_hu(mqi_handle* h, const float* xe, int n_xe, const float* ye, int n_ye, const float* ze, int n_ze,
+                const int16_t* hu, float density_scale, const float* rot, const float* trans) {
+    return set_grid_hu_impl(h, xe, n_xe, ye, n_ye, ze, n_ze, hu, false, density_scale, rot, trans);
+}
+
+int
+mqi_set_grid_hu_device(mqi_handle* h, const float* xe, int n_xe, const float* ye, int n_ye, const float* ze,
+                       int n_ze, const void* d_hu, float density_scale, const float* rot, const float* trans) {
+    return set_grid_hu_impl(h, xe, n_xe, ye, n_ye, ze, n_ze, d_hu, true, density_scale, rot, trans);
+}
+
+int
+mqi_set_grid_density(mqi_handle* h, const float* xe, int n_xe, const float* ye, int n_ye, const float* ze, int n_ze,
+                     const float* rho, const float* rot, const float* trans) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (!rho) return fail(MQI_EINVAL, "rho is null");
+    rc = set_grid_common(h, xe, n_xe, ye, n_ye, ze, n_ze, rot, trans);
+    if (rc) return rc;
+    const size_t nv = nvox(h);
+    // dictionary of distinct densities (bit patterns) -> 16-bit material index
+    std::map<uint32_t, uint16_t> dict;
+    std::vector<uint16_t>        mat(nv);
+    std::vector<MatEntry>        lut;
+    for (size_t i = 0; i < nv; ++i) {
+        uint32_t bits;
+        std::memcpy(&bits, &rho[i], 4);
+        auto it = dict.find(bits);
+        if (it == dict.end()) {
+            if (lut.size() >= 65536) return fail(MQI_EINVAL, "more than 65536 distinct densities; pass HU instead");
+            it = dict.emplace(bits, (uint16_t) lut.size()).first;
+            lut.push_back(make_mat_entry(rho[i], h->variant));
+        }
+        mat[i] = it->second;
+    }
+    CU(cudaMalloc(&h->d_mat, nv * sizeof(uint16_t)));
+    CU(cudaMalloc(&h->d_lut, lut.size() * sizeof(MatEntry)));
+    CU(cudaMemcpyAsync(h->d_mat, mat.data(), nv * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_lut, lut.data(), lut.size() * sizeof(MatEntry), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->lut_size = (int) lut.size();
+    h->has_grid = true;
+    return MQI_OK;
+}
+
+int
+mqi_add_scorer(mqi_handle* h, int kind, const char* name, uint64_t capacity) {
+    if (!h) return fail(MQI_EINVAL, "null handle");
+    if (kind < MQI_SCORER_DOSE || kind > MQI_SCORER_DIJ) return fail(MQI_EINVAL, "unknown scorer kind");
+    if ((int) h->scorers.size() >= kMaxScorers) return fail(MQI_EINVAL, "too many scorers");
+    if (kind == MQI_SCORER_DIJ && capacity == 0) return fail(MQI_EINVAL, "Dij scorer needs a capacity");
+    HostScorer s;
+    s.kind     = kind;
+    s.name     = name ? name : "";
+    s.capacity = capacity;
+    h->scorers.push_back(s);
+    return (int) h->scorers.size() - 1;
+}
+
+int
+mqi_bind_scorer_buffer(mqi_handle* h, int scorer, void* d_buffer) {
+    if (!h || scorer < 0 || scorer >= (int) h->scorers.size()) return fail(MQI_EINVAL, "bad scorer index");
+    HostScorer& s = h->scorers[scorer];
+    if (s.kind == MQI_SCORER_DIJ) return fail(MQI_EINVAL, "Dij scorers own their table");
+    if (s.d_dense && !s.external) cudaFree(s.d_dense);
+    s.d_dense  = static_cast<double*>(d_buffer);
+    s.external = d_buffer != nullptr;
+    return MQI_OK;
+}
+
+int
+mqi_clear_scorers(mqi_handle* h) {
+    int rc = activate(h);
+    if (rc) return rc;
+    for (auto& s : h->scorers) {
+        if (s.d_table) CU(launch_dij_clear(s.d_table, s.capacity, h->stream));
+        if (s.d_dense) CU(cudaMemsetAsync(s.d_dense, 0, nvox(h) * sizeof(double), h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return MQI_OK;
+}
+
+int
+mqi_set_accumulation(mqi_handle* h, int mode) {
+    if (!h) return fail(MQI_EINVAL, "null handle");
+    if (mode != MQI_ACCUM_ATOMIC && mode != MQI_ACCUM_WARP_MATCH) return fail(MQI_EINVAL, "unknown accumulation mode");
+    h->accum = mode;
+    return MQI_OK;
+}
+
+int
+mqi_set_option(mqi_handle* h, const char* key, int64_t value) {
+    if (!h || !key) return fail(MQI_EINVAL, "null argument");
+    const std::string k(key);
+    if (k == "count_steps") h->count_steps = value != 0;
+    else if (k == "blocks_per_sm") h->blocks_per_sm_override = (int) value;
+    else return fail(MQI_EINVAL, "unknown option " + k);
+    return MQI_OK;
+}
+
+int
+mqi_set_beamlets(mqi_handle* h, const mqi_beamlet* beamlets, uint32_t n_spots, const uint64_t* histories_per_spot) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (!beamlets || !histories_per_spot || n_spots == 0) return fail(MQI_EINVAL, "empty beam source");
+    static_assert(sizeof(mqi_beamlet) == sizeof(BeamletDev), "beamlet layout");
+    std::vector<unsigned long long> cum(n_spots);
+    unsigned long long              acc = 0;
+    for (uint32_t i = 0; i < n_spots; ++i) {
+        acc += histories_per_spot[i];
+        cum[i] = acc;
+    }
+    cudaFree(h->d_beamlets); cudaFree(h->d_cum);
+    h->d_beamlets = nullptr; h->d_cum = nullptr;
+    cudaFree(h->d_vertices); cudaFree(h->d_spot_ids);
+    h->d_vertices = nullptr; h->d_spot_ids = nullptr; h->n_vertices = 0;
+    CU(cudaMalloc(&h->d_beamlets, n_spots * sizeof(BeamletDev)));
+    CU(cudaMalloc(&h->d_cum, n_spots * sizeof(unsigned long long)));
+    CU(cudaMemcpyAsync(h->d_beamlets, beamlets, n_spots * sizeof(BeamletDev), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_cum, cum.data(), n_spots * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->n_spots         = n_spots;
+    h->total_histories = acc;
+    return MQI_OK;
+}
+
+int
+mqi_set_vertices(mqi_handle* h, const mqi_vertex* vertices, uint64_t n, const uint32_t* spot_ids) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (!vertices || n == 0) return fail(MQI_EINVAL, "empty vertex list");
+    static_assert(sizeof(mqi_vertex) == sizeof(VertexDev), "vertex layout");
+    cudaFree(h->d_vertices); cudaFree(h->d_spot_ids);
+    h->d_vertices = nullptr; h->d_spot_ids = nullptr;
+    CU(cudaMalloc(&h->d_vertices, n * sizeof(VertexDev)));
+    CU(cudaMemcpyAsync(h->d_vertices, vertices, n * sizeof(VertexDev), cudaMemcpyHostToDevice, h->stream));
+    if (spot_ids) {
+        CU(cudaMalloc(&h->d_spot_ids, n * sizeof(uint32_t)));
+        CU(cudaMemcpyAsync(h->d_spot_ids, spot_ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    h->n_vertices = n;
+    return MQI_OK;
+}
+
+int
+mqi_run(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t count, int per_spot) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (!h->has_grid) return fail(MQI_ESTATE, "no grid set");
+    if (h->scorers.empty()) return fail(MQI_ESTATE, "no scorer added");
+    if (h->d_vertices) {
+        if (first_history + count > h->n_vertices) return fail(MQI_EINVAL, "history range exceeds the vertex list");
+    } else {
+        if (!h->d_beamlets) return fail(MQI_ESTATE, "no beam source set");
+        if (first_history + count > h->total_histories) return fail(MQI_EINVAL, "history range exceeds the beam source");
+    }
+    rc = ensure_scorer_buffers(h);
+    if (rc) return rc;
+    std::memset(&h->stats, 0, sizeof(h->stats));
+    if (count == 0) return MQI_OK;
+    Params p;
+    fill_params(h, p);
+    p.seed     = seed;
+    p.first    = first_history;
+    p.count    = count;
+    p.per_spot = per_spot;
+    if (h->d_vertices) {   // explicit vertices are addressed relative to the launch
+        p.src.vertices = h->d_vertices + first_history;
+        p.src.spot_ids = h->d_spot_ids ? h->d_spot_ids + first_history : nullptr;
+    }
+    const size_t smem = transport_smem_bytes(h->nx, h->ny, h->nz);
+    int          bps  = 0;
+    CU(transport_occupancy(h->variant, smem, &bps));
+    if (bps < 1) return fail(MQI_ECUDA, "transport kernel does not fit on an SM");
+    if (h->blocks_per_sm_override > 0) bps = std::min(bps, h->blocks_per_sm_override);
+    // persistent grid: a whole number of CTAs per SM, never more lanes than histories
+    unsigned long long want = (count + MQI_K_BLOCK - 1) / MQI_K_BLOCK;
+    int                grid = (int) std::min<unsigned long long>((unsigned long long) h->sm_count * bps, want);
+    CU(cudaMemsetAsync(h->d_counters, 0, C_COUNT * sizeof(unsigned long long), h->stream));
+    CU(cudaEventRecord(h->ev0, h->stream));
+    CU(launch_transport(p, h->variant, grid, smem, h->stream));
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    unsigned long long c[C_COUNT];
+    CU(cudaMemcpy(c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.histories       = c[C_DONE];
+    h->stats.steps           = c[C_STEPS];
+    h->stats.secondaries     = c[C_SECONDARIES];
+    h->stats.stack_overflows = c[C_OVERFLOW];
+    h->stats.dij_table_full  = c[C_DIJ_FULL];
+    h->stats.kernel_ms       = ms;
+    h->stats.launches        = 1;
+    return MQI_OK;
+}
+
+int
+mqi_get_run_stats(mqi_handle* h, mqi_run_stats* out) {
+    if (!h || !out) return fail(MQI_EINVAL, "null argument");
+    *out = h->stats;
+    return MQI_OK;
+}
+
+int
+mqi_get_dense(mqi_handle* h, int scorer, double* out, double scale) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (scorer < 0 || scorer >= (int) h->scorers.size() || !out) return fail(MQI_EINVAL, "bad scorer index");
+    HostScorer& s = h->scorers[scorer];
+    if (s.kind == MQI_SCORER_DIJ) return fail(MQI_EINVAL, "use mqi_get_sparse for Dij scorers");
+    const size_t nv = nvox(h);
+    if (!s.d_dense) {
+        std::memset(out, 0, nv * sizeof(double));
+        return MQI_OK;
+    }
+    CU(cudaMemcpyAsync(out, s.d_dense, nv * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (scale != 1.0)
+        for (size_t i = 0; i < nv; ++i) out[i] *= scale;
+    return MQI_OK;
+}
+
+int
+mqi_get_scorer_device_ptr(mqi_handle* h, int scorer, void** d_ptr, uint64_t* n_elements) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (scorer < 0 || scorer >= (int) h->scorers.size() || !d_ptr) return fail(MQI_EINVAL, "bad scorer index");
+    if (!h->has_grid) return fail(MQI_ESTATE, "no grid set");
+    rc = ensure_scorer_buffers(h);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    HostScorer& s = h->scorers[scorer];
+    if (s.kind == MQI_SCORER_DIJ) {
+        *d_ptr = s.d_table;
+        if (n_elements) *n_elements = s.capacity;
+    } else {
+        *d_ptr = s.d_dense;
+        if (n_elements) *n_elements = nvox(h);
+    }
+    return MQI_OK;
+}
+
+static const size_t kDijChunk = 1u << 16;
+
+int
+mqi_get_sparse_count(mqi_handle* h, int scorer, uint64_t* nnz) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (scorer < 0 || scorer >= (int) h->scorers.size() || !nnz) return fail(MQI_EINVAL, "bad scorer index");
+    HostScorer& s = h->scorers[scorer];
+    if (s.kind != MQI_SCORER_DIJ) return fail(MQI_EINVAL, "not a Dij scorer");
+    *nnz = 0;
+    if (!s.d_table) return MQI_OK;
+    DevBuf<unsigned long long> cnt;
+    CU(cnt.alloc(1));
+    CU(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), h->stream));
+    CU(launch_dij_count(s.d_table, s.capacity, cnt.p, h->stream));
+    unsigned long long c = 0;
+    CU(cudaMemcpyAsync(&c, cnt.p, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *nnz = c;
+    return MQI_OK;
+}
+
+int
+mqi_get_sparse(mqi_handle* h, int scorer, uint32_t* key1, uint32_t* key2, double* value, uint64_t nnz, double scale) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (scorer < 0 || scorer >= (int) h->scorers.size()) return fail(MQI_EINVAL, "bad scorer index");
+    HostScorer& s = h->scorers[scorer];
+    if (s.kind != MQI_SCORER_DIJ) return fail(MQI_EINVAL, "not a Dij scorer");
+    if (nnz == 0 || !s.d_table) return MQI_OK;
+    if (!key1 || !key2 || !value) return fail(MQI_EINVAL, "null output");
+    const size_t nchunks = (s.capacity + kDijChunk - 1) / kDijChunk;
+    DevBuf<unsigned long long> d_cnt;
+    CU(d_cnt.alloc(nchunks));
+    CU(cudaMemsetAsync(d_cnt.p, 0, nchunks * sizeof(unsigned long long), h->stream));
+    CU(launch_dij_chunk_count(s.d_table, s.capacity, kDijChunk, d_cnt.p, h->stream));
+    std::vector<unsigned long long> cnt(nchunks);
+    CU(cudaMemcpyAsync(cnt.data(), d_cnt.p, nchunks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    unsigned long long acc = 0;
+    for (size_t i = 0; i < nchunks; ++i) {
+        const unsigned long long c = cnt[i];
+        cnt[i] = acc;
+        acc += c;
+    }
+    if (acc != nnz) return fail(MQI_EINVAL, "nnz does not match the table (call mqi_get_sparse_count first)");
+    CU(cudaMemcpyAsync(d_cnt.p, cnt.data(), nchunks * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+    DevBuf<uint32_t> d_k1, d_k2;
+    DevBuf<double>   d_v;
+    CU(d_k1.alloc(nnz)); CU(d_k2.alloc(nnz)); CU(d_v.alloc(nnz));
+    CU(launch_dij_chunk_write(s.d_table, s.capacity, kDijChunk, d_cnt.p, d_k1.p, d_k2.p, d_v.p, scale, h->stream));
+    CU(cudaMemcpyAsync(key1, d_k1.p, nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(key2, d_k2.p, nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(value, d_v.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return MQI_OK;
+}
+
+int
+mqi_stat_partial(mqi_handle* h, int scorer_sum, int scorer_sumsq, uint64_t n_histories, double threshold_fraction,
+                 double max_mean, double out[3]) {
+    int rc = activate(h);
+    if (rc) return rc;
+    const int ns = (int) h->scorers.size();
+    if (scorer_sum < 0 || scorer_sum >= ns || scorer_sumsq < 0 || scorer_sumsq >= ns || !out) return fail(MQI_EINVAL, "bad scorer index");
+    const double* sum = h->scorers[scorer_sum].d_dense;
+    const double* sq  = h->scorers[scorer_sumsq].d_dense;
+    if (!sum || !sq || n_histories < 2) return fail(MQI_ESTATE, "stat scorers are empty");
+    DevBuf<double> d;
+    CU(d.alloc(3));
+    CU(cudaMemsetAsync(d.p, 0, 3 * sizeof(double), h->stream));
+    if (max_mean < 0.0) {
+        CU(launch_stat_max(sum, nvox(h), 1.0 / (double) n_histories, d.p + 2, h->stream));
+        CU(cudaMemcpyAsync(&max_mean, d.p + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    CU(launch_stat_partial(sum, sq, nvox(h), (double) n_histories, threshold_fraction * max_mean, d.p, h->stream));
+    CU(cudaMemcpyAsync(out, d.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    out[2] = max_mean;
+    return MQI_OK;
+}
+
+int
+mqi_scale_scorer(mqi_handle* h, int scorer, double factor) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (scorer < 0 || scorer >= (int) h->scorers.size()) return fail(MQI_EINVAL, "bad scorer index");
+    HostScorer& s = h->scorers[scorer];
+    if (s.kind == MQI_SCORER_DIJ || !s.d_dense) return fail(MQI_ESTATE, "scorer has no dense buffer");
+    CU(launch_scale(s.d_dense, nvox(h), factor, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return MQI_OK;
+}
+
+// ---- deterministic device pieces ---------------------------------------------------------------
+int
+mqi_dev_hu_to_density(mqi_handle* h, const int16_t* hu, uint64_t n, float density_scale, float* rho_out) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (!hu || !rho_out) return fail(MQI_EINVAL, "null argument");
+    if (n == 0) return MQI_OK;
+    DevBuf<int16_t> d_hu;
+    DevBuf<float>   d_rho;
+    CU(d_hu.alloc(n)); CU(d_rho.alloc(n));
+    CU(cudaMemcpyAsync(d_hu.p, hu, n * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream));
+    CU(launch_hu_to_density(d_hu.p, d_rho.p, n, h->d_correction, density_scale, h->stream));
+    CU(cudaMemcpyAsync(rho_out, d_rho.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return MQI_OK;
+}
+
+int
+mqi_dev_rsp(mqi_handle* h, const float* rho, const float* ek, uint64_t n, float* rsp_out, float* rl_out) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (!rho || !ek || !rsp_out || !rl_out) return fail(MQI_EINVAL, "null argument");
+    if (n == 0) return MQI_OK;
+    std::vector<MatEntry> m(n);
+    for (uint64_t i = 0; i < n; ++i) m[i] = make_mat_entry(rho[i], h->variant);
+    DevBuf<MatEntry> d_m;
+    DevBuf<float>    d_ek, d_rsp, d_rl;
+    CU(d_m.alloc(n)); CU(d_ek.alloc(n)); CU(d_rsp.alloc(n)); CU(d_rl.alloc(n));
+    CU(cudaMemcpyAsync(d_m.p, m.data(), n * sizeof(MatEntry), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_ek.p, ek, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(launch_dev_rsp(d_m.p, d_ek.p, n, d_rsp.p, d_rl.p, h->stream));
+    CU(cudaMemcpyAsync(rsp_out, d_rsp.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(rl_out, d_rl.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return MQI_OK;
+}
+
+int
+mqi_dev_grid_step(mqi_handle* h, const float* p, const float* d, uint64_t n, int32_t* cell, uint64_t* cnb, float* dist,
+                  float* dir_after, float* p_exit, int32_t* cell_after) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (!h->has_grid) return fail(MQI_ESTATE, "no grid set");
+    if (!p || !d || !cell || !cnb || !dist || !dir_after || !p_exit || !cell_after) return fail(MQI_EINVAL, "null argument");
+    if (n == 0) return MQI_OK;
+    DevBuf<float>              dp, dd, ddist, ddir, dpe;
+    DevBuf<int32_t>            dc, dca;
+    DevBuf<unsigned long long> dcnb;
+    CU(dp.alloc(3 * n)); CU(dd.alloc(3 * n)); CU(ddist.alloc(n)); CU(ddir.alloc(3 * n)); CU(dpe.alloc(3 * n));
+    CU(dc.alloc(3 * n)); CU(dca.alloc(3 * n)); CU(dcnb.alloc(n));
+    CU(cudaMemcpyAsync(dp.p, p, 3 * n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dd.p, d, 3 * n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    Params prm;
+    fill_params(h, prm);
+    CU(launch_dev_grid_step(prm, dp.p, dd.p, n, dc.p, dcnb.p, ddist.p, ddir.p, dpe.p, dca.p, h->stream));
+    CU(cudaMemcpyAsync(cell, dc.p, 3 * n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(cnb, dcnb.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(dist, ddist.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(dir_after, ddir.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(p_exit, dpe.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(cell_after, dca.p, 3 * n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return MQI_OK;
+}
+
+int
+mqi_dev_grid_entry(mqi_handle* h, const float* p, const float* d, uint64_t n, float* dist, int32_t* cell) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (!h->has_grid) return fail(MQI_ESTATE, "no grid set");
+    if (!p || !d || !dist || !cell) return fail(MQI_EINVAL, "null argument");
+    if (n == 0) return MQI_OK;
+    DevBuf<float>   dp, dd, ddist;
+    DevBuf<int32_t> dc;
+    CU(dp.alloc(3 * n)); CU(dd.alloc(3 * n)); CU(ddist.alloc(n)); CU(dc.alloc(3 * n));
+    CU(cudaMemcpyAsync(dp.p, p, 3 * n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dd.p, d, 3 * n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    Params prm;
+    fill_params(h, prm);
+    CU(launch_dev_grid_entry(prm, dp.p, dd.p, n, ddist.p, dc.p, h->stream));
+    CU(cudaMemcpyAsync(dist, ddist.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(cell, dc.p, 3 * n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return MQI_OK;
+}
+
+int
+mqi_dev_hash(mqi_handle* h, const uint32_t* k1, const uint32_t* k2, const uint64_t* capacity, uint64_t n, uint32_t* out) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (!k1 || !k2 || !capacity || !out) return fail(MQI_EINVAL, "null argument");
+    if (n == 0) return MQI_OK;
+    DevBuf<uint32_t>           d1, d2, dout;
+    DevBuf<unsigned long long> dc;
+    CU(d1.alloc(n)); CU(d2.alloc(n)); CU(dout.alloc(n)); CU(dc.alloc(n));
+    CU(cudaMemcpyAsync(d1.p, k1, n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d2.p, k2, n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dc.p, capacity, n * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(launch_dev_hash(d1.p, d2.p, dc.p, n, dout.p, h->stream));
+    CU(cudaMemcpyAsync(out, dout.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return MQI_OK;
+}
+
+int
+mqi_dev_sample_vertices(mqi_handle* h, uint64_t seed, uint64_t first, uint64_t n, mqi_vertex* out, uint32_t* spot_out) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (!h->d_beamlets) return fail(MQI_ESTATE, "no beam source set");
+    if (!out || !spot_out) return fail(MQI_EINVAL, "null argument");
+    if (first + n > h->total_histories) return fail(MQI_EINVAL, "history range exceeds the beam source");
+    if (n == 0) return MQI_OK;
+    DevBuf<VertexDev> dv;
+    DevBuf<uint32_t>  ds;
+    CU(dv.alloc(n)); CU(ds.alloc(n));
+    Params prm;
+    fill_params(h, prm);
+    prm.seed = seed;
+    CU(launch_dev_sample(prm, first, n, dv.p, ds.p, h->stream));
+    CU(cudaMemcpyAsync(out, dv.p, n * sizeof(VertexDev), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(spot_out, ds.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return MQI_OK;
+}
+
+}   // extern "C"

@@ -1,0 +1,68 @@
+// mqi_kernels.h -- host-visible launch interface of the CUDA kernels (internal to libmqi_b200.so)
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define MQI_K_RELEASE 0
+#define MQI_K_DEBUG 1
+
+#define MQI_K_DOSE 0
+#define MQI_K_EDEP 1
+#define MQI_K_LETD_NUMER 2
+#define MQI_K_LETD_DENOM 3
+#define MQI_K_DOSE_SQ 4
+#define MQI_K_DIJ 5
+
+#define MQI_K_QUIRK_B2 1u
+#define MQI_K_ACCUM_ATOMIC 0
+#define MQI_K_ACCUM_WARP_MATCH 1
+
+#ifndef MQI_K_BLOCK
+#define MQI_K_BLOCK 256
+#endif
+#ifndef MQI_K_MIN_BLOCKS
+#define MQI_K_MIN_BLOCKS 2
+#endif
+
+namespace mqib
+{
+struct Params;
+struct MatEntry;
+struct BeamletDev;
+struct VertexDev;
+
+size_t      transport_smem_bytes(int nx, int ny, int nz);
+cudaError_t transport_occupancy(int variant, size_t smem, int* blocks_per_sm);
+cudaError_t launch_transport(const Params& p, int variant, int grid, size_t smem, cudaStream_t st);
+
+// HU volume -> 16-bit material index volume (index = clamp(hu) + 1000)
+cudaError_t launch_hu_to_material(const int16_t* d_hu, uint16_t* d_mat, size_t n, cudaStream_t st);
+// HU -> density on the device (bit-exact restatement of hu_to_density)
+cudaError_t launch_hu_to_density(const int16_t* d_hu, float* d_rho, size_t n, const float* d_correction,
+                                 float density_scale, cudaStream_t st);
+cudaError_t launch_dev_rsp(const MatEntry* lut_entries, const float* ek, size_t n, float* rsp, float* rl,
+                           cudaStream_t st);
+cudaError_t launch_dev_grid_step(const Params& p, const float* pin, const float* din, size_t n, int32_t* cell,
+                                 unsigned long long* cnb, float* dist, float* dir_after, float* p_exit,
+                                 int32_t* cell_after, cudaStream_t st);
+cudaError_t launch_dev_grid_entry(const Params& p, const float* pin, const float* din, size_t n, float* dist,
+                                  int32_t* cell, cudaStream_t st);
+cudaError_t launch_dev_hash(const uint32_t* k1, const uint32_t* k2, const unsigned long long* cap, size_t n,
+                            uint32_t* out, cudaStream_t st);
+cudaError_t launch_dev_sample(const Params& p, unsigned long long first, size_t n, VertexDev* out,
+                              uint32_t* spot, cudaStream_t st);
+cudaError_t launch_fill_u64(unsigned long long* p, unsigned long long v, size_t n, cudaStream_t st);
+cudaError_t launch_dij_clear(void* table, size_t capacity, cudaStream_t st);
+cudaError_t launch_dij_count(const void* table, size_t capacity, unsigned long long* d_count, cudaStream_t st);
+cudaError_t launch_dij_chunk_count(const void* table, size_t capacity, size_t chunk,
+                                   unsigned long long* d_chunk_count, cudaStream_t st);
+cudaError_t launch_dij_chunk_write(const void* table, size_t capacity, size_t chunk,
+                                   const unsigned long long* d_chunk_off, uint32_t* k1, uint32_t* k2, double* val,
+                                   double scale, cudaStream_t st);
+cudaError_t launch_scale(double* p, size_t n, double f, cudaStream_t st);
+// stopping criterion: per-voxel mean / sigma from sum and sum of squares, partial reductions
+cudaError_t launch_stat_max(const double* sum, size_t n, double inv_n, double* d_out_max, cudaStream_t st);
+cudaError_t launch_stat_partial(const double* sum, const double* sumsq, size_t n, double n_hist, double cut,
+                                double* d_out2, cudaStream_t st);
+}   // namespace mqib
