@@ -72,7 +72,8 @@ lerp_ref(float x, float x0, float x1, float y0, float y1) {
     return (x1 == x0) ? y0 : y0 + (x - x0) * (y1 - y0) / (x1 - x0);
 }
 
-// spr_default / radiation_length_default (:414-473) folded into per-density coefficients
+// spr_default / radiation_length_default (:414-473): the density-only parts, evaluated once per
+// distinct density in the reference's precision (R = float variables, double literals)
 MatEntry
 make_mat_entry(float rho, int variant) {
     MatEntry m;
@@ -82,39 +83,32 @@ make_mat_entry(float rho, int variant) {
     const float d = rho * 1000.0;
     const bool  water_shortcut = (variant == MQI_PHYSICS_DEBUG) && std::fabs(d - 1.0) < 1e-3;
     if (water_shortcut) {
-        m.a = 1.0f;
-    } else if (d <= 0.26f) {
-        m.a = d < 0.0012f ? 0.0f : lerp_ref(d, 0.0012f, 0.26f, 0.8815f, 0.9925f);
+        m.mode = 0;
+        m.a    = 1.0f;
+    } else if (d <= 0.26) {
+        m.mode = 0;
+        m.a    = d < 0.0012 ? 0.0f : lerp_ref(d, 0.0012f, 0.26f, 0.8815f, 0.9925f);
     } else {
-        const float P = (float) ((double) powf(d, -0.7f) - 1.0);
-        if (d >= 0.9f) {
-            m.b = 1.0f;
-            m.c = P;
+        m.Pd = (double) powf(d, -0.7f) - 1.0;
+        if (d >= 0.9) {
+            m.mode = 1;
         } else {
-            const float w = (d - 0.26f) / (0.9f - 0.26f);
-            m.a = 0.9925f - 0.9925f * w;
-            m.b = w;
-            m.c = w * P;
+            m.mode = 2;
+            m.a    = d - 0.26f;
         }
     }
-    // radiation length
     float x0;
     if (water_shortcut) {
         x0 = 360.863f;
     } else {
         float f = 0.f;
-        if (d <= 0.26f) f = 0.9857 + 0.0085 * d;
-        else if (d <= 0.9f) f = 1.0446 - 0.2180 * d;
+        if (d <= 0.26) f = 0.9857 + 0.0085 * d;
+        else if (d <= 0.9) f = 1.0446 - 0.2180 * d;
         else f = 1.19 + 0.44 * std::log((double) d - 0.44);
         x0 = (0.001f * 360.863f) / (d * 0.001 * f);
     }
-    m.pad    = x0;
+    m.x0     = x0;
     m.inv_x0 = 1.0f / x0;
-    // rsp(rho, Ek = 0) for the zero-energy delta daughter of the debug variant
-    float rsp0;
-    if (m.c != 0.f) rsp0 = INFINITY;   // Ek^-0.3421 -> inf
-    else rsp0 = m.a + m.b * 1.0123f;
-    m.inv_rsp0 = (std::isfinite(rsp0) && rsp0 > 0.f) ? 1.0f / rsp0 : 0.f;
     return m;
 }
 
@@ -139,8 +133,11 @@ struct mqi_handle {
     int          count_steps = 0;
     int          blocks_per_sm_override = 0;
     // physics tables
-    float4* d_tab_a = nullptr;
-    float4* d_tab_b = nullptr;
+    float4* d_tab_a0 = nullptr;
+    float4* d_tab_a1 = nullptr;
+    float2* d_tab_bs = nullptr;
+    float4* d_tab_n0 = nullptr;
+    float2* d_tab_n1 = nullptr;
     float*  d_correction = nullptr;
     // grid
     bool      has_grid = false;
@@ -152,6 +149,7 @@ struct mqi_handle {
     float     rot[9]   = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
     float     trans[3] = { 0, 0, 0 };
     int       identity = 1;
+    float     inv_w[3] = { 0, 0, 0 };
     // source
     BeamletDev*         d_beamlets = nullptr;
     unsigned long long* d_cum      = nullptr;
@@ -212,6 +210,9 @@ set_grid_common(mqi_handle* h, const float* xe, int n_xe, const float* ye, int n
     CU(cudaMalloc(&h->d_edges, e.size() * sizeof(float)));
     CU(cudaMemcpyAsync(h->d_edges, e.data(), e.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    h->inv_w[0] = (float) (n_xe - 1) / (xe[n_xe - 1] - xe[0]);
+    h->inv_w[1] = (float) (n_ye - 1) / (ye[n_ye - 1] - ye[0]);
+    h->inv_w[2] = (float) (n_ze - 1) / (ze[n_ze - 1] - ze[0]);
     const float I[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
     std::memcpy(h->rot, rot ? rot : I, sizeof(I));
     h->trans[0] = trans ? trans[0] : 0.f; h->trans[1] = trans ? trans[1] : 0.f; h->trans[2] = trans ? trans[2] : 0.f;
@@ -261,6 +262,7 @@ fill_params(const mqi_handle* h, Params& p) {
     p.g.identity = h->identity;
     std::memcpy(p.g.rot_fwd, h->rot, sizeof(h->rot));
     std::memcpy(p.g.trans, h->trans, sizeof(h->trans));
+    std::memcpy(p.g.inv_w, h->inv_w, sizeof(h->inv_w));
     p.src.beamlets = h->d_beamlets;
     p.src.cum      = h->d_cum;
     p.src.n_spots  = h->n_spots;
@@ -277,8 +279,11 @@ fill_params(const mqi_handle* h, Params& p) {
     p.accum_mode  = h->accum;
     p.count_steps = h->count_steps;
     p.dedx_term0  = dedx_term0();
-    p.tab_a       = h->d_tab_a;
-    p.tab_b       = h->d_tab_b;
+    p.tab_a0      = h->d_tab_a0;
+    p.tab_a1      = h->d_tab_a1;
+    p.tab_bs      = h->d_tab_bs;
+    p.tab_n0      = h->d_tab_n0;
+    p.tab_n1      = h->d_tab_n1;
     p.counters    = h->d_counters;
 }
 
@@ -326,18 +331,33 @@ mqi_create(int device_id, mqi_handle** out) {
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
-    // physics tables -> interleaved float4 arrays (one 16-byte shared-memory load per grid point)
-    std::vector<float4> a(kTableN), b(kTableN);
+    // physics tables -> value + slope rows (one shared-memory row per interpolation); tables 0-2 live
+    // on the p-ionisation grid (Ei = 0.1), 3-5 on the nuclear grid (Ei = 0.5), step 0.5 MeV
+    std::vector<float4> a0(kTableN), a1(kTableN), n0(kTableN);
+    std::vector<float2> bs(kTableN), n1(kTableN);
+    auto slope = [](const float* t, int i) { return i + 1 < kTableN ? (t[i + 1] - t[i]) * 2.0f : 0.0f; };
     for (int i = 0; i < kTableN; ++i) {
-        a[i] = make_float4(table_ptr(0)[i], table_ptr(1)[i], table_ptr(2)[i], 0.f);
-        b[i] = make_float4(table_ptr(3)[i], table_ptr(4)[i], table_ptr(5)[i], 0.f);
+        const float* cs = table_ptr(0); const float* sp = table_ptr(1); const float* rg = table_ptr(2);
+        const float* pp = table_ptr(3); const float* pe = table_ptr(4); const float* pi = table_ptr(5);
+        const float dedr = (i + 1 < kTableN && rg[i + 1] > rg[i]) ? 0.5f / (rg[i + 1] - rg[i]) : 0.0f;
+        a0[i] = make_float4(cs[i], slope(cs, i), sp[i], slope(sp, i));
+        a1[i] = make_float4(rg[i], slope(rg, i), dedr, 0.f);
+        n0[i] = make_float4(pp[i], slope(pp, i), pe[i], slope(pe, i));
+        n1[i] = make_float2(pi[i], slope(pi, i));
+        bs[i] = make_float2(pp[i] + pe[i] + pi[i], slope(pp, i) + slope(pe, i) + slope(pi, i));
     }
-    CU(cudaMalloc(&h->d_tab_a, kTableN * sizeof(float4)));
-    CU(cudaMalloc(&h->d_tab_b, kTableN * sizeof(float4)));
+    CU(cudaMalloc(&h->d_tab_a0, kTableN * sizeof(float4)));
+    CU(cudaMalloc(&h->d_tab_a1, kTableN * sizeof(float4)));
+    CU(cudaMalloc(&h->d_tab_n0, kTableN * sizeof(float4)));
+    CU(cudaMalloc(&h->d_tab_bs, kTableN * sizeof(float2)));
+    CU(cudaMalloc(&h->d_tab_n1, kTableN * sizeof(float2)));
+    CU(cudaMemcpy(h->d_tab_a0, a0.data(), kTableN * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_tab_a1, a1.data(), kTableN * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_tab_n0, n0.data(), kTableN * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_tab_bs, bs.data(), kTableN * sizeof(float2), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_tab_n1, n1.data(), kTableN * sizeof(float2), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&h->d_correction, 3996 * sizeof(float)));
     CU(cudaMalloc(&h->d_counters, C_COUNT * sizeof(unsigned long long)));
-    CU(cudaMemcpy(h->d_tab_a, a.data(), kTableN * sizeof(float4), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->d_tab_b, b.data(), kTableN * sizeof(float4), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_correction, correction_ptr(), 3996 * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaMemset(h->d_counters, 0, C_COUNT * sizeof(unsigned long long)));
     *out = h;
@@ -354,7 +374,7 @@ mqi_destroy(mqi_handle* h) {
         if (s.d_dense && !s.external) cudaFree(s.d_dense);
         cudaFree(s.d_table);
     }
-    cudaFree(h->d_tab_a); cudaFree(h->d_tab_b); cudaFree(h->d_correction); cudaFree(h->d_counters);
+    cudaFree(h->d_tab_a0); cudaFree(h->d_tab_a1); cudaFree(h->d_tab_bs); cudaFree(h->d_tab_n0); cudaFree(h->d_tab_n1); cudaFree(h->d_correction); cudaFree(h->d_counters);
     cudaFree(h->d_beamlets); cudaFree(h->d_cum); cudaFree(h->d_vertices); cudaFree(h->d_spot_ids);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);

@@ -17,78 +17,101 @@ namespace mqib
 {
 
 // ---------------------------------------------------------------------------------------------
-// shared-memory view
+// shared-memory view of the physics tables and grid edges
 // ---------------------------------------------------------------------------------------------
 struct Smem {
-    const float4* tab_a;
-    const float4* tab_b;
+    const float4* a0;   // {cs_p_ion, slope, restricted stopping power, slope}   per 0.5 MeV row, Ei = 0.1
+    const float4* a1;   // {csda range, slope, dE/drange (inverse slope), 0}
+    const float2* bs;   // {cs_pp + cs_pO_el + cs_pO_inel, slope}                  Ei = 0.5
     const float*  xe;
     const float*  ye;
     const float*  ze;
 };
 
-__device__ __forceinline__ int tab_index(float ek, float e0) {
-    // uint16_t((Ek - Ei) / 0.5)
-    return (int) (unsigned short) (int) ((ek - e0) * 2.0f);
+// row of the p-ionisation grid (Ei = 0.1, step 0.5): uint16_t((Ek - Ei) / 0.5)
+__device__ __forceinline__ int row_a(float ek) { return min(max((int) ((ek - 0.1f) * 2.0f), 0), kTableN - 1); }
+__device__ __forceinline__ int row_b(float ek) { return min(max((int) ((ek - 0.5f) * 2.0f), 0), kTableN - 1); }
+
+// sum of the four tabulated cross sections [mm^2/g] at kinetic energy e: delta production on the
+// p-ion grid plus the three nuclear channels (pre-summed: linear interpolation commutes with the sum)
+// mqi_p_ionization.hpp:254-268, mqi_pp_elastic.hpp:221-235, mqi_po_elastic.hpp:243-256,
+// mqi_po_inelastic.hpp:141-155
+__device__ __forceinline__ float
+cs_total(const Smem& sm, float e) {
+    float cs = 0.f;
+    if (e >= 0.1f && e <= 299.6f) {
+        const int    i = row_a(e);
+        const float4 a = sm.a0[i];
+        cs             = fmaf(e - (0.1f + i * 0.5f), a.y, a.x);
+    }
+    if (e >= 0.5f && e <= 300.0f) {
+        const int    i = row_b(e);
+        const float2 b = sm.bs[i];
+        cs += fmaf(e - (0.5f + i * 0.5f), b.y, b.x);
+    }
+    return cs;
 }
 
-// tabulated cross sections of the four discrete processes at kinetic energy ek, times rho
-// (mqi_p_ionization.hpp:254-268, mqi_pp_elastic.hpp:221-235, mqi_po_elastic.hpp:243-256,
-// mqi_po_inelastic.hpp:141-155)
+// the four channels separately (only needed when a discrete interaction was selected)
 __device__ __forceinline__ void
-cross_sections(const Smem& sm, float ek, float rho, float cs[4]) {
+cs_channels(const Smem& sm, const Params& P, float e, float cs[4]) {
     cs[0] = cs[1] = cs[2] = cs[3] = 0.f;
-    if (ek >= 0.1f && ek <= 299.6f) {
-        const int   i0 = tab_index(ek, 0.1f);
-        const int   i1 = min(i0 + 1, kTableN - 1);
-        const float x0 = 0.1f + i0 * 0.5f;
-        cs[0]          = intpl1d(ek, x0, x0 + 0.5f, sm.tab_a[i0].x, sm.tab_a[i1].x);
+    if (e >= 0.1f && e <= 299.6f) {
+        const int    i = row_a(e);
+        const float4 a = sm.a0[i];
+        cs[0]          = fmaf(e - (0.1f + i * 0.5f), a.y, a.x);
     }
-    if (ek >= 0.5f && ek <= 300.0f) {
-        const int    i0 = min(tab_index(ek, 0.5f), kTableN - 1);
-        const int    i1 = min(i0 + 1, kTableN - 1);
-        const float  x0 = 0.5f + i0 * 0.5f;
-        const float  x1 = x0 + 0.5f;
-        const float4 a = sm.tab_b[i0], b = sm.tab_b[i1];
-        cs[1] = intpl1d(ek, x0, x1, a.x, b.x);
-        cs[2] = intpl1d(ek, x0, x1, a.y, b.y);
-        cs[3] = intpl1d(ek, x0, x1, a.z, b.z);
+    if (e >= 0.5f && e <= 300.0f) {
+        const int    i = row_b(e);
+        const float  t = e - (0.5f + i * 0.5f);
+        const float4 n0 = __ldg(P.tab_n0 + i);
+        const float2 n1 = __ldg(P.tab_n1 + i);
+        cs[1] = fmaf(t, n0.y, n0.x);
+        cs[2] = fmaf(t, n0.w, n0.z);
+        cs[3] = fmaf(t, n1.y, n1.x);
     }
-    cs[0] *= rho; cs[1] *= rho; cs[2] *= rho; cs[3] *= rho;
 }
 
 // |dEdx| in water (restricted stopping power), mqi_p_ionization.hpp:271-286
 __device__ __forceinline__ float
 stopping_power(const Smem& sm, float ek) {
     if (ek >= 0.1f && ek <= 299.6f) {
-        const int   i0 = tab_index(ek, 0.1f);
-        const int   i1 = min(i0 + 1, kTableN - 1);
-        const float x0 = 0.1f + i0 * 0.5f;
-        return intpl1d(ek, x0, x0 + 0.5f, sm.tab_a[i0].y, sm.tab_a[i1].y);
+        const int    i = row_a(ek);
+        const float4 a = sm.a0[i];
+        return fmaf(ek - (0.1f + i * 0.5f), a.w, a.z);
     }
-    if (ek < 0.1f && ek > 0.f) return sm.tab_a[0].y;
+    if (ek < 0.1f && ek > 0.f) return sm.a0[0].z;
     return 0.f;
 }
 
-// CSDA energy loss over a water-equivalent length + Gaussian straggling,
-// p_ionization_tabulated::energy_loss / energy_straggling  mqi_p_ionization.hpp:298-345
+// ---------------------------------------------------------------------------------------------
+// RNG plumbing.  Protocol (shared with the oracle): Philox4x32-10, key = seed, counter =
+// (block, 0, history_lo, history_hi); one aligned block {u_mfp, u_a, u_b, u_phi} per physics step,
+// further blocks on demand inside a discrete interaction.  The per-step block is generated inline;
+// every other use goes through one out-of-line copy to keep the hot loop small.
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ uint4
+philox_block(uint32_t blk, uint32_t h0, uint32_t h1, uint32_t k0, uint32_t k1) {
+    uint32_t o[4];
+    philox4x32_10(blk, 0u, h0, h1, k0, k1, o);
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+struct RngBuf {
+    uint4    w;
+    int      pos;
+    uint32_t blk, h0, h1, k0, k1;
+};
 __device__ __forceinline__ float
-energy_loss(const Smem& sm, const Rel& rel, float rho, float liw, float z, float dedx_term0) {
-    int         n  = tab_index(rel.Ek, 0.1f);
-    const float x0 = 0.1f + n * 0.5f;
-    const float x1 = x0 + 0.5f;
-    if (x0 > rel.Ek) n -= 1;
-    if (x1 < rel.Ek) n += 1;
-    n       = max(0, min(n, kTableN - 2));
-    float r = intpl1d(rel.Ek, x0, x1, sm.tab_a[n].z, sm.tab_a[n + 1].z);
-    if (r < liw) return rel.Ek;
-    r -= liw;
-    while (n > 0 && r < sm.tab_a[n].z) --n;   // do { if (r >= r_steps[n]) break; } while (--n > 0)
-    const float y0      = 0.1f + n * 0.5f;
-    const float dE_mean = rel.Ek - intpl1d(r, sm.tab_a[n].z, sm.tab_a[n + 1].z, y0, y0 + 0.5f);
-    const float Te      = fminf(rel.Te_max, 0.08511f);
-    const float var     = dedx_term0 * rho / kWaterRho * liw * (Te / rel.beta_sq * (1.0f - 0.5f * rel.beta_sq));
-    return fabsf(z * sqrtf(var) + dE_mean);
+rb_uniform(RngBuf& r) {
+    if (r.pos == 4) {
+        r.w   = philox_block(r.blk, r.h0, r.h1, r.k0, r.k1);
+        r.blk += 1;
+        r.pos = 0;
+    }
+    const int      p = r.pos++;
+    const uint32_t x = p == 0 ? r.w.x : (p == 1 ? r.w.y : (p == 2 ? r.w.z : r.w.w));
+    return u32_to_uniform(x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -106,14 +129,27 @@ struct Secondary {
     float dE_pre;   // energy already carried as trk.dE (debug recoil daughters), else 0
 };
 
+// in/out record of the (rare) nuclear interactions, kept in local memory
+struct NucIO {
+    float px, py, pz, dx, dy, dz;   // pre-step vertex (vtx0)
+    float p1x, p1y, p1z;            // post-step position (vtx1.pos)
+    float d1x, d1y, d1z;            // vtx1.dir, in/out
+    float ke1;                      // vtx1.ke, in/out
+    float dE, local_dE;             // deposits, in/out
+    float u, c1, c2, c3;            // selector (already reduced by the delta channel) and channel cross sections
+    int   stopped;
+    int   sp;                       // stack pointer, in/out
+    unsigned n_sec, n_ovf;          // counters, out
+    RngBuf rb;
+};
+
 template<int VARIANT>
 __device__ __forceinline__ void
-push_secondary(const Params& P, Secondary* stack, int& sp, float x, float y, float z, float ux, float uy,
-               float uz, float ke0, float ke1_off, float dE_pre, unsigned long long& n_sec,
-               unsigned long long& n_ovf) {
+push_secondary(const Params& P, Secondary* stack, NucIO& io, float x, float y, float z, float ux, float uy,
+               float uz, float ke0, float ke1_off, float dE_pre) {
     constexpr int DEPTH = StackCfg<VARIANT>::depth;
-    if (sp >= DEPTH) {   // overflow silently drops the secondary: mqi_track_stack.hpp:36-41 (B10)
-        ++n_ovf;
+    if (io.sp >= DEPTH) {   // overflow silently drops the secondary: mqi_track_stack.hpp:36-41 (B10)
+        ++io.n_ovf;
         return;
     }
     if (!P.g.identity) {
@@ -128,10 +164,109 @@ push_secondary(const Params& P, Secondary* stack, int& sp, float x, float y, flo
         uy = R[3] * ex + R[4] * ey + R[5] * ez;
         uz = R[6] * ex + R[7] * ey + R[8] * ez;
     }
-    Secondary& s = stack[sp++];
+    Secondary& s = stack[io.sp++];
     s.px = x; s.py = y; s.pz = z; s.dx = ux; s.dy = uy; s.dz = uz;
     s.ke0 = ke0; s.ke1_off = ke1_off; s.dE_pre = dE_pre;
-    ++n_sec;
+    ++io.n_sec;
+}
+
+// p-p elastic, p-O elastic and p-O inelastic post-step interactions (0.5 events per 200 MeV history):
+// out of line so that the voxel-step loop stays small.
+template<int VARIANT>
+__device__ __noinline__ void
+nuclear_event(const Params& P, Secondary* stack, NucIO& io) {
+    RngBuf& rb = io.rb;
+    if (io.u < io.c1) {
+        // p-p elastic, pp_elastic_tabulated::post_step mqi_pp_elastic.hpp:119-219
+        const Rel   r1   = rel_make(io.ke1);
+        const float minv = kTpCut / r1.Ek;
+        const float uu   = rb_uniform(rb) * (1.0f - 2.0f * minv) + minv;
+        const float E1 = r1.Et;
+        const float dE = r1.Ek * uu;
+        const float E3 = (r1.Ek - dE) + kMp;
+        const float E4 = dE + kMp;
+        const float P1 = sqrtf(r1.Et * r1.Et - kMpSq);
+        const float P3 = sqrtf(E3 * E3 - kMpSq);
+        const float P4 = sqrtf(E4 * E4 - kMpSq);
+        float cos_th3  = (E1 * E3 - kMpSq - kMp * (E1 - E3)) / (P1 * P3);
+        float cos_th34 = (E3 * E4 - E1 * kMp) / (P3 * P4);
+        cos_th3  = fminf(1.f, fmaxf(-1.f, cos_th3));
+        cos_th34 = fminf(1.f, fmaxf(-1.f, cos_th34));
+        const float th3 = acosf(cos_th3);
+        const float th4 = th3 - acosf(cos_th34);
+        const float phi = kTwoPi * rb_uniform(rb);
+        io.ke1 -= dE;
+        rotate_direction(io.d1x, io.d1y, io.d1z, th3, phi);
+        // recoil proton: direction rotated from the already scattered primary direction
+        float sx = io.d1x, sy = io.d1y, sz = io.d1z;
+        rotate_direction(sx, sy, sz, th4, phi);
+        push_secondary<VARIANT>(P, stack, io, io.p1x, io.p1y, io.p1z, sx, sy, sz, dE, 0.f, 0.f);
+    } else if (io.u < io.c1 + io.c2) {
+        // p-O elastic, po_elastic::post_step mqi_po_elastic.hpp:97-217
+        const Rel r1 = rel_make(io.ke1);
+        if (r1.Ek <= 5.5f) {
+            const float dE = r1.Ek;
+            if (VARIANT == MQI_K_DEBUG)
+                push_secondary<VARIANT>(P, stack, io, io.p1x, io.p1y, io.p1z, io.d1x, io.d1y, io.d1z, dE, -dE, dE);
+            else io.local_dE += dE;
+            io.ke1 -= dE;
+            io.stopped = 1;
+        } else {
+            const float Tp_avg = 0.65f * expf(-0.0013f * r1.Ek) - 0.71f * expf(-0.0177f * r1.Ek);
+            const float Tp_max = (2.0f * kMo * r1.beta_sq * r1.gamma_sq) /
+                                 (1.0f + 2.0f * r1.gamma * kMoMp + kMoMp * kMoMp);
+            float dE;
+            do {   // mqi_exponential (GPU definition, truncated) base/mqi_math.hpp:298-307
+                dE = -Tp_avg * logf(1.0f - rb_uniform(rb));
+            } while (dE > Tp_max || dE != dE);
+            const float E1 = r1.Ek * (r1.Ek + 2.0f * kMp);
+            const float E3 = (r1.Ek - dE) * (r1.Ek - dE + 2.0f * kMp);
+            float cos_th3  = (E1 + E3 - dE * (dE + 2.0f * kMo)) / 2.0f / sqrtf(E1 * E3);
+            cos_th3        = fminf(1.f, fmaxf(-1.f, cos_th3));
+            const float th3 = acosf(cos_th3);
+            const float phi = kTwoPi * rb_uniform(rb);
+            if (VARIANT == MQI_K_DEBUG)   // daughter starts at the parent's PRE-step vertex
+                push_secondary<VARIANT>(P, stack, io, io.px, io.py, io.pz, io.dx, io.dy, io.dz, dE, -dE, dE);
+            else io.local_dE += dE;
+            io.ke1 -= dE;
+            rotate_direction(io.d1x, io.d1y, io.d1z, th3, phi);
+        }
+    } else if (io.u < io.c1 + io.c2 + io.c3) {
+        // p-O inelastic cascade, po_inelastic_tabulated::post_step mqi_po_inelastic.hpp:159-288
+        const float Ek = io.ke1;
+        float       Eb = 5.0f, Er = Ek;
+        float       prob_2nd, prob_long, power;
+        if (Ek <= 215.f && Ek > 200.f) { prob_2nd = 0.78f; prob_long = prob_2nd + (1.f - prob_2nd) * 0.9f; power = 0.4f; }
+        else if (Ek > 215.f) { prob_2nd = 0.78f; prob_long = prob_2nd + (1.f - prob_2nd) * 1.0f; power = 0.4f; }
+        else if (Ek <= 200.f && Ek > 150.f) { prob_2nd = 0.72f; prob_long = prob_2nd + (1.f - prob_2nd) * 0.83f; power = 0.45f; }
+        else { prob_2nd = 0.7f; prob_long = prob_2nd + (1.f - prob_2nd) * 0.83f; power = 0.52f; }
+        while ((Er - Eb) > 2.0f) {
+            Er -= Eb;
+            const float uu = rb_uniform(rb);
+            float       dE = powf(uu, power) * (Er - 2.0f) + 2.0f;
+            if (dE >= Er) dE = Er;
+            Er -= dE;
+            io.ke1 -= (dE + Eb);
+            const float zeta = rb_uniform(rb);
+            if (zeta < prob_2nd) {
+                float cos_th = (2.0f * dE / Ek - 1.0f) + 2.0f * (1.f - dE / Ek) * rb_uniform(rb);
+                cos_th       = fminf(1.f, fmaxf(-1.f, cos_th));
+                const float th  = acosf(cos_th);
+                const float phi = kTwoPi * rb_uniform(rb);
+                float sx = io.d1x, sy = io.d1y, sz = io.d1z;
+                rotate_direction(sx, sy, sz, th, phi);
+                push_secondary<VARIANT>(P, stack, io, io.p1x, io.p1y, io.p1z, sx, sy, sz, dE, 0.f, 0.f);
+            } else if (zeta < prob_long) {
+                // neutral / long-range: energy leaves
+            } else if (VARIANT == MQI_K_DEBUG) {
+                push_secondary<VARIANT>(P, stack, io, io.px, io.py, io.pz, io.dx, io.dy, io.dz, dE, -dE, dE);
+            }   // release: short-range energy dropped (:273-275, B4)
+            Eb *= 0.65f;
+        }
+        io.dE += Er;
+        io.ke1 -= Er;
+        io.stopped = 1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -140,11 +275,12 @@ push_secondary(const Params& P, Secondary* stack, int& sp, float x, float y, flo
 // const_1d / norm_1d.  RNG protocol: block 0 = {Ux, Vx, Uy, Vy}, block 1 = {za, zb, uc, -}.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void
-sample_vertex(const BeamletDev& b, Rng& rng, VertexDev& out) {
+sample_vertex(const BeamletDev& b, unsigned long long seed, unsigned long long h, VertexDev& out) {
+    const uint32_t k0 = (uint32_t) seed, k1 = (uint32_t) (seed >> 32), h0 = (uint32_t) h, h1 = (uint32_t) (h >> 32);
     float Ux, Vx, Uy, Vy;
-    rng_begin_step(rng);
     {
-        const float u0 = rng_uniform(rng), u1 = rng_uniform(rng), u2 = rng_uniform(rng), u3 = rng_uniform(rng);
+        const uint4 w  = philox_block(0u, h0, h1, k0, k1);
+        const float u0 = u32_to_uniform(w.x), u1 = u32_to_uniform(w.y), u2 = u32_to_uniform(w.z), u3 = u32_to_uniform(w.w);
         if (b.phsp_uniform) {
             Ux = 2.0f * u0 - 1.0f; Vx = 2.0f * u1 - 1.0f; Uy = 2.0f * u2 - 1.0f; Vy = 2.0f * u3 - 1.0f;
         } else {
@@ -152,13 +288,10 @@ sample_vertex(const BeamletDev& b, Rng& rng, VertexDev& out) {
             box_muller(u2, u3, Uy, Vy);
         }
     }
-    rng_begin_step(rng);
-    float za, zb;
-    {
-        const float u0 = rng_uniform(rng), u1 = rng_uniform(rng);
-        box_muller(u0, u1, za, zb);
-    }
-    const float uc = rng_uniform(rng);
+    const uint4 w = philox_block(1u, h0, h1, k0, k1);
+    float       za, zb;
+    box_muller(u32_to_uniform(w.x), u32_to_uniform(w.y), za, zb);
+    const float uc = u32_to_uniform(w.z);
     const float Uz = b.phsp_uniform ? 2.0f * uc - 1.0f : za;
     float       ph[6];
 #pragma unroll
@@ -207,25 +340,26 @@ dense_add(double* __restrict__ acc, unsigned cnb, double v, int accum_mode) {
 // open-addressing (voxel, spot) -> dose table with a single 64-bit CAS per claim.  Same hash
 // function, home slot and linear probing as insert_hashtable (mqi_transport.hpp:68-111), so the set
 // of occupied keys is identical; the reference's two independent 32-bit CAS (race B5) are replaced.
-__device__ __forceinline__ void
-dij_add(const ScorerDev& s, uint32_t key1, uint32_t key2, double v, unsigned long long* counters) {
+__device__ __noinline__ void
+dij_add(DijSlot* table, unsigned long long capacity, uint32_t key1, uint32_t key2, double v,
+        unsigned long long* counters) {
     unsigned long long slot;
     if (key2 == kEmptyKey32) {   // dense mode of the reference: slot = voxel, key2 := 0
         slot = key1;
         key2 = 0;
     } else {
-        slot = hash_fun(key1, key2, s.capacity);
+        slot = hash_fun(key1, key2, capacity);
     }
     const unsigned long long key = ((unsigned long long) key2 << 32) | key1;
-    for (unsigned long long probes = 0; probes < s.capacity; ++probes) {
-        DijSlot*           e    = s.table + slot;
+    for (unsigned long long probes = 0; probes < capacity; ++probes) {
+        DijSlot*           e    = table + slot;
         unsigned long long prev = *reinterpret_cast<volatile unsigned long long*>(&e->key);
         if (prev == kEmptyKey64) prev = atomicCAS(&e->key, kEmptyKey64, key);
         if (prev == kEmptyKey64 || prev == key) {
             atomicAdd(&e->value, v);
             return;
         }
-        slot = (slot + 1) % s.capacity;
+        slot = slot + 1 == capacity ? 0 : slot + 1;
     }
     atomicAdd(counters + C_DIJ_FULL, 1ull);   // the reference would spin forever here
 }
@@ -235,9 +369,10 @@ struct StepResult {
     float local_dE;  // trk.local_dE
     float te_debug;  // delta-electron energy carried by the (folded) zero-energy daughter, debug only
     float len;       // |vtx1.pos - vtx0.pos|
-    float ke0;       // vtx0.ke
 };
 
+// one insert per scorer per step, keyed to the voxel occupied at step start: mqi_transport.hpp:204-225,
+// hit functions scorers/mqi_scorer_energy_deposit.hpp:14-137
 template<int VARIANT>
 __device__ __forceinline__ void
 score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, float inv_vol, float rsp0,
@@ -245,36 +380,26 @@ score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, 
     if ((int) cnb <= 0) return;   // roi_->idx(cnb) > 0 with a DIRECT roi: voxel 0 is never scored (B1)
     // dose_to_water: (dE + local_dE) * 1.60218e-10 / (V * rho * rsp(rho, vtx0.ke))
     const float  kdose   = 1.60218e-10f * inv_vol * M.inv_rho;
-    const double dose    = (M.rho < 1.0e-7f) ? 0.0 : (double) ((r.dE + r.local_dE) * kdose / rsp0);
-    const double dose_te = (VARIANT == MQI_K_DEBUG && M.rho >= 1.0e-7f) ? (double) (r.te_debug * kdose * M.inv_rsp0) : 0.0;
-    const int n = P.n_scorers;
+    const double dose    = (double) ((r.dE + r.local_dE) * kdose / rsp0);
+    const double dose_te = (VARIANT == MQI_K_DEBUG) ? (double) (r.te_debug * kdose * inv_rsp_at_zero_energy(M)) : 0.0;
+    const int    n       = P.n_scorers;
 #pragma unroll 1
-    for (int pass = (P.quirks & MQI_K_QUIRK_B2) ? 0 : 1; pass < 2; ++pass) {
-        const int s_end = pass == 0 ? n - 2 : n;
-#pragma unroll 1
-        for (int s = 0; s < s_end; ++s) {
-            const ScorerDev& sc = P.sc[s];
-            double           v  = 0.0;
-            switch (sc.kind) {
-            case MQI_K_DOSE: v = dose + dose_te; break;
-            case MQI_K_DIJ: v = dose + dose_te; break;
-            case MQI_K_DOSE_SQ: v = dose * dose + dose_te * dose_te; break;
-            case MQI_K_EDEP: v = (double) (r.dE + r.local_dE) + (double) r.te_debug; break;
-            case MQI_K_LETD_NUMER:
-            case MQI_K_LETD_DENOM: {
-                // LETd_weight1/2: scorers/mqi_scorer_energy_deposit.hpp:93-137
-                if (r.len > 0.f) {
-                    const double let = (double) r.dE / (double) r.len / (double) (M.rho * 1000.0f);
-                    if (let < 25.0) v = sc.kind == MQI_K_LETD_NUMER ? (double) r.dE * let : (double) r.dE;
-                }
-                break;
-            }
-            default: break;
-            }
-            if (!(v > 0.0)) continue;   // insert_hashtable: value <= 0 -> skip
-            if (sc.kind == MQI_K_DIJ) dij_add(sc, cnb, spot_ind, v, P.counters);
-            else dense_add(sc.dense, cnb, v, P.accum_mode);
+    for (int s = 0; s < n; ++s) {
+        const int kind = P.sc[s].kind;
+        double    v    = 0.0;
+        if (kind == MQI_K_DOSE || kind == MQI_K_DIJ) v = dose + dose_te;
+        else if (kind == MQI_K_DOSE_SQ) v = dose * dose + dose_te * dose_te;
+        else if (kind == MQI_K_EDEP) v = (double) (r.dE + r.local_dE) + (double) r.te_debug;
+        else if (r.len > 0.f) {
+            // LETd_weight1/2: scorers/mqi_scorer_energy_deposit.hpp:93-137
+            const double let = (double) r.dE / (double) r.len / (double) (M.rho * 1000.0f);
+            if (let < 25.0) v = kind == MQI_K_LETD_NUMER ? (double) r.dE * let : (double) r.dE;
         }
+        if (!(v > 0.0)) continue;   // insert_hashtable: value <= 0 -> skip
+        // quirk B2: the reference's non-stat kernel scores scorers [0, n-2) twice when n >= 3
+        if ((P.quirks & MQI_K_QUIRK_B2) && s < n - 2) v += v;
+        if (kind == MQI_K_DIJ) dij_add(P.sc[s].table, P.sc[s].capacity, cnb, spot_ind, v, P.counters);
+        else dense_add(P.sc[s].dense, cnb, v, P.accum_mode);
     }
 }
 
@@ -285,22 +410,25 @@ template<int VARIANT>
 __global__ void __launch_bounds__(MQI_K_BLOCK, MQI_K_MIN_BLOCKS)
 transport_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* s_tab_a = reinterpret_cast<float4*>(smem_raw);
-    float4* s_tab_b = s_tab_a + kTableN;
-    float*  s_edges = reinterpret_cast<float*>(s_tab_b + kTableN);
+    float4* s_a0    = reinterpret_cast<float4*>(smem_raw);
+    float4* s_a1    = s_a0 + kTableN;
+    float2* s_bs    = reinterpret_cast<float2*>(s_a1 + kTableN);
+    float*  s_edges = reinterpret_cast<float*>(s_bs + kTableN);
     const int nx = P.g.nx, ny = P.g.ny, nz = P.g.nz;
     for (int i = threadIdx.x; i < kTableN; i += blockDim.x) {
-        s_tab_a[i] = P.tab_a[i];
-        s_tab_b[i] = P.tab_b[i];
+        s_a0[i] = P.tab_a0[i];
+        s_a1[i] = P.tab_a1[i];
+        s_bs[i] = P.tab_bs[i];
     }
     for (int i = threadIdx.x; i < nx + ny + nz + 3; i += blockDim.x) s_edges[i] = P.g.edges[i];
     __syncthreads();
     Smem sm;
-    sm.tab_a = s_tab_a;
-    sm.tab_b = s_tab_b;
-    sm.xe    = s_edges;
-    sm.ye    = s_edges + nx + 1;
-    sm.ze    = s_edges + nx + 1 + ny + 1;
+    sm.a0 = s_a0;
+    sm.a1 = s_a1;
+    sm.bs = s_bs;
+    sm.xe = s_edges;
+    sm.ye = s_edges + nx + 1;
+    sm.ze = s_edges + nx + 1 + ny + 1;
 
     constexpr float T_cut = (VARIANT == MQI_K_DEBUG) ? 0.08511f : 0.0815f;   // mqi_interaction.hpp:24-28
     constexpr int   DEPTH = StackCfg<VARIANT>::depth;
@@ -312,9 +440,9 @@ transport_kernel(const __grid_constant__ Params P) {
     int      ix = 0, iy = 0, iz = 0;
     bool     alive = false;
     uint32_t spot_ind = kEmptyKey32;
-    Rng      rng;
-    rng_init(rng, P.seed, 0);
-    unsigned long long n_steps = 0, n_done = 0, n_sec = 0, n_ovf = 0;
+    uint32_t h0 = 0, h1 = 0, blk = 0;   // Philox counter of the current history
+    const uint32_t k0 = (uint32_t) P.seed, k1 = (uint32_t) (P.seed >> 32);
+    unsigned n_steps = 0, n_done = 0, n_sec = 0, n_ovf = 0;
 
     while (true) {
         // ------------------------------------------------------------------ re-arm the lane
@@ -327,7 +455,9 @@ transport_kernel(const __grid_constant__ Params P) {
                 const unsigned long long i = atomicAdd(P.counters + C_NEXT, 1ull);
                 if (i >= P.count) break;
                 const unsigned long long h = P.first + i;
-                rng_init(rng, P.seed, h);
+                h0  = (uint32_t) h;
+                h1  = (uint32_t) (h >> 32);
+                blk = 0;
                 uint32_t spot = 0;
                 if (P.src.vertices) {
                     const VertexDev v = P.src.vertices[i];
@@ -344,7 +474,8 @@ transport_kernel(const __grid_constant__ Params P) {
                     }
                     spot = min(lo, P.src.n_spots - 1);
                     VertexDev v;
-                    sample_vertex(P.src.beamlets[spot], rng, v);
+                    sample_vertex(P.src.beamlets[spot], P.seed, h, v);
+                    blk = 2;
                     px = v.pos[0]; py = v.pos[1]; pz = v.pos[2];
                     dx = v.dir[0]; dy = v.dir[1]; dz = v.dir[2];
                     ke = v.ke;
@@ -367,13 +498,13 @@ transport_kernel(const __grid_constant__ Params P) {
                 dz = R[2] * ex + R[5] * ey + R[8] * ez;
             }
             {
-                const float n = sqrtf(dx * dx + dy * dy + dz * dz);
-                dx /= n; dy /= n; dz /= n;
+                const float n = rsqrtf(dx * dx + dy * dy + dz * dz);
+                dx *= n; dy *= n; dz *= n;
             }
             // locate: index(p, dir) or entry intersect, :171-190
-            ix = index_axis(sm.xe, nx, px, dx);
-            iy = index_axis(sm.ye, ny, py, dy);
-            iz = index_axis(sm.ze, nz, pz, dz);
+            ix = index_axis_guess(sm.xe, nx, px, dx, P.g.inv_w[0]);
+            iy = index_axis_guess(sm.ye, ny, py, dy, P.g.inv_w[1]);
+            iz = index_axis_guess(sm.ze, nz, pz, dz, P.g.inv_w[2]);
             alive = true;
             if (ix < 0 || iy < 0 || iz < 0 || ix >= nx || iy >= ny || iz >= nz) {
                 const float p[3] = { px, py, pz };
@@ -391,9 +522,9 @@ transport_kernel(const __grid_constant__ Params P) {
                     ke += ke1_off;
                     ke1_off = 0.f;
                     dE_pre  = 0.f;
-                    ix = index_axis(sm.xe, nx, px, dx);
-                    iy = index_axis(sm.ye, ny, py, dy);
-                    iz = index_axis(sm.ze, nz, pz, dz);
+                    ix = index_axis_guess(sm.xe, nx, px, dx, P.g.inv_w[0]);
+                    iy = index_axis_guess(sm.ye, ny, py, dy, P.g.inv_w[1]);
+                    iz = index_axis_guess(sm.ze, nz, pz, dz, P.g.inv_w[2]);
                     if (ix < 0 || iy < 0 || iz < 0 || ix >= nx || iy >= ny || iz >= nz) alive = false;
                 }
             }
@@ -406,6 +537,7 @@ transport_kernel(const __grid_constant__ Params P) {
         const float ey0 = sm.ye[iy], ey1 = sm.ye[iy + 1];
         const float ez0 = sm.ze[iz], ez1 = sm.ze[iz + 1];
         const unsigned cnb = ((unsigned) iz * (unsigned) ny + (unsigned) iy) * (unsigned) nx + (unsigned) ix;
+        const MatEntry M   = P.g.lut[__ldg(P.g.mat + cnb)];
         float       d1x = dx, d1y = dy, d1z = dz;   // vtx1.dir: copy taken before intersect() zeroes tiny components
         const float tx = cell_tmax_axis(ex0, ex1, nx, px, dx, ix);
         const float ty = cell_tmax_axis(ey0, ey1, ny, py, dy, iy);
@@ -415,14 +547,13 @@ transport_kernel(const __grid_constant__ Params P) {
             alive = false;
             continue;
         }
-        const MatEntry M   = P.g.lut[__ldg(P.g.mat + cnb)];
-        const float    rho = M.rho;
+        const float rho = M.rho;
 
         bool  stopped = false;
         float p1x, p1y, p1z;              // vtx1.pos
         float ke1 = ke + ke1_off;         // vtx1.ke
         StepResult res;
-        res.dE = dE_pre; res.local_dE = 0.f; res.te_debug = 0.f; res.len = 0.f; res.ke0 = ke;
+        res.dE = dE_pre; res.local_dE = 0.f; res.te_debug = 0.f; res.len = 0.f;
         float rsp0 = 1.f;
 
         if (rho < 1.0e-7f) {
@@ -435,7 +566,6 @@ transport_kernel(const __grid_constant__ Params P) {
             // below the tracking cut: dump the energy, :86-94 + last_step mqi_p_ionization.hpp:482-490
             if (ke < 0.f) ke = 0.f;
             rsp0 = rsp_eval(M, ke);
-            res.ke0 = ke;
             res.dE += ke;
             ke1 -= ke;
             float step_len = 0.f;
@@ -448,30 +578,45 @@ transport_kernel(const __grid_constant__ Params P) {
             stopped = true;
         } else {
             // ---------------- class-II condensed-history step, fippel_physics::stepping :95-216
-            const Rel   rel = rel_make(ke);
-            rsp0            = rsp_eval(M, ke);
-            const float cms = 1.0f * rsp0 * rho / kWaterRho;            // WEPL of the 1 mm max step
-            const float max_loss = cms * stopping_power(sm, ke);
-            float cs1[4], cs2[4];
-            cross_sections(sm, ke, rho, cs1);
-            cross_sections(sm, ke - max_loss, rho, cs2);
-            const float cs1_sum = cs1[0] + cs1[1] + cs1[2] + cs1[3];
-            const float cs2_sum = cs2[0] + cs2[1] + cs2[2] + cs2[3];
-            const bool  use1    = cs1_sum >= cs2_sum;
-            const float cs_sum  = use1 ? cs1_sum : cs2_sum;
-            const float c0 = use1 ? cs1[0] : cs2[0], c1 = use1 ? cs1[1] : cs2[1];
-            const float c2 = use1 ? cs1[2] : cs2[2], c3 = use1 ? cs1[3] : cs2[3];
-
-            rng_begin_step(rng);
-            const float u_mfp = rng_uniform(rng);
-            const float u_a   = rng_uniform(rng);
-            const float u_b   = rng_uniform(rng);
-            const float u_phi = rng_uniform(rng);
+            // the per-step Philox block first: it only depends on the counter
+            uint32_t w[4];
+            philox4x32_10(blk, 0u, h0, h1, k0, k1, w);
+            blk += 1;
+            const float u_mfp = u32_to_uniform(w[0]);
+            const float u_phi = u32_to_uniform(w[3]);
             float z_loss, z_theta;
-            box_muller(u_a, u_b, z_loss, z_theta);
+            box_muller(u32_to_uniform(w[1]), u32_to_uniform(w[2]), z_loss, z_theta);
 
-            const float mfp        = -1.0f * logf(u_mfp) / cs_sum;
-            const float step_limit = cms * kWaterRho / (rsp0 * rho);
+            // relativistic quantities of vtx0.ke, base/mqi_relativistic_quantities.hpp:27-44
+            const float Et       = ke + kMp;
+            const float gamma    = Et * (1.0f / kMp);
+            const float gamma_sq = gamma * gamma;
+            const float beta_sq  = 1.0f - 1.0f / gamma_sq;
+            constexpr float MeMp = kMe / kMp;
+            const float Te_max   = (2.0f * kMe * beta_sq * gamma_sq) / (1.0f + 2.0f * gamma * MeMp + MeMp * MeMp);
+
+            rsp0            = rsp_eval(M, ke);
+            const float cms = rsp0 * rho * (1.0f / kWaterRho);   // WEPL of the 1 mm max step
+            // one row of the p-ion grid serves the delta cross section, |dEdx| and the csda range
+            const int    ia  = row_a(ke);
+            const float  ta  = ke - (0.1f + ia * 0.5f);
+            const float4 A0  = sm.a0[ia];
+            const float4 A1  = sm.a1[ia];
+            const bool   in_a = ke <= 299.6f;   // ke > 0.5 here
+            const float  sp_w = in_a ? fmaf(ta, A0.w, A0.z) : 0.f;
+            float cs1_sum     = in_a ? fmaf(ta, A0.y, A0.x) : 0.f;
+            if (ke <= 300.0f) {
+                const int    ib = row_b(ke);
+                const float2 b  = sm.bs[ib];
+                cs1_sum += fmaf(ke - (0.5f + ib * 0.5f), b.y, b.x);
+            }
+            const float e2      = ke - cms * sp_w;   // energy after the largest possible CSDA loss
+            const float cs2_sum = cs_total(sm, e2);
+            const bool  use1    = cs1_sum >= cs2_sum;
+            const float cs_sum  = (use1 ? cs1_sum : cs2_sum) * rho;
+
+            const float mfp = -logf(u_mfp) / cs_sum;
+            constexpr float step_limit = 1.0f;   // cms * rho_w / (rsp * rho): max_step, mqi_fippel_physics.hpp:20
             float len;
             bool  discrete = false;
             if (d2b < mfp && d2b < step_limit) {
@@ -483,132 +628,78 @@ transport_kernel(const __grid_constant__ Params P) {
             } else {
                 len = step_limit;
             }
-            // ---------------- along step (CSDA + straggling + MCS), mqi_p_ionization.hpp:349-420
+            // ---------------- along step (CSDA + straggling + MCS), mqi_p_ionization.hpp:298-420
             {
-                const float liw = len * rsp0 * rho / kWaterRho;
-                float       dE  = energy_loss(sm, rel, rho, liw, z_loss, P.dedx_term0);
-                float       r   = 1.0f;
+                const float liw = len * cms;
+                float       dE;
+                const float R0 = fmaf(ta, A1.y, A1.x);   // residual csda range in water
+                if (R0 < liw) {
+                    dE = ke;
+                } else {
+                    const float r = R0 - liw;
+                    int         n = ia;
+                    float4      B = A1;
+                    if (n > kTableN - 2) B = sm.a1[n = kTableN - 2];
+                    while (n > 0 && r < B.x) B = sm.a1[--n];   // do { if (r >= r_steps[n]) break; } while (--n > 0)
+                    const float dE_mean = ke - fmaf(r - B.x, B.z, 0.1f + n * 0.5f);
+                    const float Te      = fminf(Te_max, 0.08511f);
+                    const float var     = P.dedx_term0 * rho * (1.0f / kWaterRho) * liw * (Te / beta_sq * (1.0f - 0.5f * beta_sq));
+                    dE                  = fabsf(fmaf(z_loss, sqrtf(var), dE_mean));
+                }
+                float r = 1.0f;
                 if (dE >= ke) {
                     r       = ke / dE;
                     stopped = true;
                 }
-                const float P_sq  = rel.Et * rel.Et - kMpSq;
-                const float th_sq = ((13.9f * 13.9f / P_sq) / rel.beta_sq) * len * M.inv_x0;
-                const float th    = fabsf(z_theta * (1.41421356237f * sqrtf(th_sq)));
-                const float phi   = kTwoPi * u_phi;
-                rotate_direction(d1x, d1y, d1z, th, phi);
+                const float P_sq  = Et * Et - kMpSq;
+                const float th_sq = (13.9f * 13.9f) / (P_sq * beta_sq) * len * M.inv_x0;
+                const float th    = fabsf(z_theta) * sqrtf(2.0f * th_sq);
+                rotate_direction(d1x, d1y, d1z, th, kTwoPi * u_phi);
                 res.dE += dE * r;
                 const float sl = r * len;
-                p1x = px + dx * sl; p1y = py + dy * sl; p1z = pz + dz * sl;
+                p1x = fmaf(dx, sl, px); p1y = fmaf(dy, sl, py); p1z = fmaf(dz, sl, pz);
                 res.len = sl;
                 ke1 -= dE * r;
             }
             // ---------------- discrete interaction at the end of the step, :156-197
             if (discrete && ke1 > kTpCut) {
-                const float u = cs_sum * rng_uniform(rng);
                 d1x = dx; d1y = dy; d1z = dz;   // vtx1.dir = vtx0.dir (B11)
+                RngBuf rb;
+                rb.w   = philox_block(blk, h0, h1, k0, k1);
+                rb.blk = blk + 1; rb.pos = 0; rb.h0 = h0; rb.h1 = h1; rb.k0 = k0; rb.k1 = k1;
+                float cs[4];
+                cs_channels(sm, P, use1 ? ke : e2, cs);
+                const float u  = cs_sum * rb_uniform(rb);
+                const float c0 = cs[0] * rho;
                 if (u < c0) {
                     // delta electron, p_ionization_tabulated::post_step mqi_p_ionization.hpp:425-477
                     const Rel r1 = rel_make(ke1);
                     float     Te;
                     while (true) {
-                        const float n = rng_uniform(rng);
+                        const float n = rb_uniform(rb);
                         Te = T_cut * r1.Te_max / ((1.0f - n) * r1.Te_max + n * T_cut);
-                        if (rng_uniform(rng) < 1.0f - r1.beta_sq * Te / r1.Te_max + Te * Te / (2.0f * r1.Et * r1.Et)) break;
+                        if (rb_uniform(rb) < 1.0f - r1.beta_sq * Te / r1.Te_max + Te * Te / (2.0f * r1.Et * r1.Et)) break;
                     }
                     if (VARIANT == MQI_K_DEBUG) res.te_debug = Te;   // carried by a zero-energy daughter
                     else res.dE += Te;
                     ke1 -= Te;
-                } else if (u < c0 + c1) {
-                    // p-p elastic, pp_elastic_tabulated::post_step mqi_pp_elastic.hpp:119-219
-                    const Rel   r1   = rel_make(ke1);
-                    const float minv = kTpCut / r1.Ek;
-                    const float uu   = rng_uniform(rng) * (1.0f - 2.0f * minv) + minv;
-                    const float E1 = r1.Et;
-                    const float dE = r1.Ek * uu;
-                    const float E3 = (r1.Ek - dE) + kMp;
-                    const float E4 = dE + kMp;
-                    const float P1 = sqrtf(r1.Et * r1.Et - kMpSq);
-                    const float P3 = sqrtf(E3 * E3 - kMpSq);
-                    const float P4 = sqrtf(E4 * E4 - kMpSq);
-                    float cos_th3  = (E1 * E3 - kMpSq - kMp * (E1 - E3)) / (P1 * P3);
-                    float cos_th34 = (E3 * E4 - E1 * kMp) / (P3 * P4);
-                    cos_th3  = fminf(1.f, fmaxf(-1.f, cos_th3));
-                    cos_th34 = fminf(1.f, fmaxf(-1.f, cos_th34));
-                    const float th3 = acosf(cos_th3);
-                    const float th4 = th3 - acosf(cos_th34);
-                    const float phi = kTwoPi * rng_uniform(rng);
-                    ke1 -= dE;
-                    rotate_direction(d1x, d1y, d1z, th3, phi);
-                    // recoil proton: direction rotated from the already scattered primary direction
-                    float sx = d1x, sy = d1y, sz = d1z;
-                    rotate_direction(sx, sy, sz, th4, phi);
-                    push_secondary<VARIANT>(P, stack, sp, p1x, p1y, p1z, sx, sy, sz, dE, 0.f, 0.f, n_sec, n_ovf);
-                } else if (u < c0 + c1 + c2) {
-                    // p-O elastic, po_elastic::post_step mqi_po_elastic.hpp:97-217
-                    const Rel r1 = rel_make(ke1);
-                    if (r1.Ek <= 5.5f) {
-                        const float dE = r1.Ek;
-                        if (VARIANT == MQI_K_DEBUG)
-                            push_secondary<VARIANT>(P, stack, sp, p1x, p1y, p1z, d1x, d1y, d1z, dE, -dE, dE, n_sec, n_ovf);
-                        else res.local_dE += dE;
-                        ke1 -= dE;
-                        stopped = true;
-                    } else {
-                        const float Tp_avg = 0.65f * expf(-0.0013f * r1.Ek) - 0.71f * expf(-0.0177f * r1.Ek);
-                        const float Tp_max = (2.0f * kMo * r1.beta_sq * r1.gamma_sq) /
-                                             (1.0f + 2.0f * r1.gamma * kMoMp + kMoMp * kMoMp);
-                        float dE;
-                        do {   // mqi_exponential (GPU definition, truncated) base/mqi_math.hpp:298-307
-                            dE = -Tp_avg * logf(1.0f - rng_uniform(rng));
-                        } while (dE > Tp_max || dE != dE);
-                        const float E1 = r1.Ek * (r1.Ek + 2.0f * kMp);
-                        const float E3 = (r1.Ek - dE) * (r1.Ek - dE + 2.0f * kMp);
-                        float cos_th3  = (E1 + E3 - dE * (dE + 2.0f * kMo)) / 2.0f / sqrtf(E1 * E3);
-                        cos_th3        = fminf(1.f, fmaxf(-1.f, cos_th3));
-                        const float th3 = acosf(cos_th3);
-                        const float phi = kTwoPi * rng_uniform(rng);
-                        if (VARIANT == MQI_K_DEBUG)   // daughter starts at the parent's PRE-step vertex
-                            push_secondary<VARIANT>(P, stack, sp, px, py, pz, dx, dy, dz, dE, -dE, dE, n_sec, n_ovf);
-                        else res.local_dE += dE;
-                        ke1 -= dE;
-                        rotate_direction(d1x, d1y, d1z, th3, phi);
-                    }
-                } else if (u < c0 + c1 + c2 + c3) {
-                    // p-O inelastic cascade, po_inelastic_tabulated::post_step mqi_po_inelastic.hpp:159-288
-                    const float Ek = ke1;
-                    float       Eb = 5.0f, Er = Ek;
-                    float       prob_2nd, prob_long, power;
-                    if (Ek <= 215.f && Ek > 200.f) { prob_2nd = 0.78f; prob_long = prob_2nd + (1.f - prob_2nd) * 0.9f; power = 0.4f; }
-                    else if (Ek > 215.f) { prob_2nd = 0.78f; prob_long = prob_2nd + (1.f - prob_2nd) * 1.0f; power = 0.4f; }
-                    else if (Ek <= 200.f && Ek > 150.f) { prob_2nd = 0.72f; prob_long = prob_2nd + (1.f - prob_2nd) * 0.83f; power = 0.45f; }
-                    else { prob_2nd = 0.7f; prob_long = prob_2nd + (1.f - prob_2nd) * 0.83f; power = 0.52f; }
-                    while ((Er - Eb) > 2.0f) {
-                        Er -= Eb;
-                        const float uu = rng_uniform(rng);
-                        float       dE = powf(uu, power) * (Er - 2.0f) + 2.0f;
-                        if (dE >= Er) dE = Er;
-                        Er -= dE;
-                        ke1 -= (dE + Eb);
-                        const float zeta = rng_uniform(rng);
-                        if (zeta < prob_2nd) {
-                            float cos_th = (2.0f * dE / Ek - 1.0f) + 2.0f * (1.f - dE / Ek) * rng_uniform(rng);
-                            cos_th       = fminf(1.f, fmaxf(-1.f, cos_th));
-                            const float th  = acosf(cos_th);
-                            const float phi = kTwoPi * rng_uniform(rng);
-                            float sx = d1x, sy = d1y, sz = d1z;
-                            rotate_direction(sx, sy, sz, th, phi);
-                            push_secondary<VARIANT>(P, stack, sp, p1x, p1y, p1z, sx, sy, sz, dE, 0.f, 0.f, n_sec, n_ovf);
-                        } else if (zeta < prob_long) {
-                            // neutral / long-range: energy leaves
-                        } else if (VARIANT == MQI_K_DEBUG) {
-                            push_secondary<VARIANT>(P, stack, sp, px, py, pz, dx, dy, dz, dE, -dE, dE, n_sec, n_ovf);
-                        }   // release: short-range energy dropped (:273-275, B4)
-                        Eb *= 0.65f;
-                    }
-                    res.dE += Er;
-                    ke1 -= Er;
-                    stopped = true;
+                    blk = rb.blk;
+                } else {
+                    NucIO io;
+                    io.px = px; io.py = py; io.pz = pz; io.dx = dx; io.dy = dy; io.dz = dz;
+                    io.p1x = p1x; io.p1y = p1y; io.p1z = p1z;
+                    io.d1x = d1x; io.d1y = d1y; io.d1z = d1z;
+                    io.ke1 = ke1; io.dE = res.dE; io.local_dE = res.local_dE;
+                    io.u = u - c0; io.c1 = cs[1] * rho; io.c2 = cs[2] * rho; io.c3 = cs[3] * rho;
+                    io.stopped = stopped ? 1 : 0;
+                    io.sp = sp; io.n_sec = 0; io.n_ovf = 0;
+                    io.rb = rb;
+                    nuclear_event<VARIANT>(P, stack, io);
+                    d1x = io.d1x; d1y = io.d1y; d1z = io.d1z;
+                    ke1 = io.ke1; res.dE = io.dE; res.local_dE = io.local_dE;
+                    stopped = io.stopped != 0;
+                    sp = io.sp; n_sec += io.n_sec; n_ovf += io.n_ovf;
+                    blk = io.rb.blk;
                 }
             }
         }
@@ -636,10 +727,10 @@ transport_kernel(const __grid_constant__ Params P) {
     }
 
     // per-lane counters -> global (one atomic per lane per launch)
-    if (n_done) atomicAdd(P.counters + C_DONE, n_done);
-    if (n_steps) atomicAdd(P.counters + C_STEPS, n_steps);
-    if (n_sec) atomicAdd(P.counters + C_SECONDARIES, n_sec);
-    if (n_ovf) atomicAdd(P.counters + C_OVERFLOW, n_ovf);
+    if (n_done) atomicAdd(P.counters + C_DONE, (unsigned long long) n_done);
+    if (n_steps) atomicAdd(P.counters + C_STEPS, (unsigned long long) n_steps);
+    if (n_sec) atomicAdd(P.counters + C_SECONDARIES, (unsigned long long) n_sec);
+    if (n_ovf) atomicAdd(P.counters + C_OVERFLOW, (unsigned long long) n_ovf);
 }
 
 
@@ -682,7 +773,7 @@ __global__ void
 dev_rsp_kernel(const MatEntry* __restrict__ m, const float* __restrict__ ek, size_t n, float* rsp, float* rl) {
     for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
         rsp[i] = rsp_eval(m[i], ek[i]);
-        rl[i]  = 1.0f / m[i].inv_x0;
+        rl[i]  = m[i].x0;
     }
 }
 
@@ -760,10 +851,8 @@ dev_sample_kernel(SourceDev src, unsigned long long seed, unsigned long long fir
             if (src.cum[mid] > h) hi = mid; else lo = mid + 1;
         }
         const uint32_t spot = min(lo, src.n_spots - 1);
-        Rng            rng;
-        rng_init(rng, seed, h);
         VertexDev v;
-        sample_vertex(src.beamlets[spot], rng, v);
+        sample_vertex(src.beamlets[spot], seed, h, v);
         out[i]      = v;
         spot_out[i] = spot;
     }
@@ -889,7 +978,7 @@ static inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
 
 size_t
 transport_smem_bytes(int nx, int ny, int nz) {
-    return 2 * kTableN * sizeof(float4) + (size_t) (nx + ny + nz + 3) * sizeof(float);
+    return kTableN * (2 * sizeof(float4) + sizeof(float2)) + (size_t) (nx + ny + nz + 3) * sizeof(float);
 }
 
 template<int V>
