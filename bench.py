@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- primary proton histories/s of the per-history transport hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json north_star target case): config C1 -- 200 MeV protons, 30 mm uniform square
+spot, water phantom 100x100x350 mm on a 200x200x350 grid (HU 0), phantom_env physics
+(__PHYSICS_DEBUG__), one Dose (dose-to-water) scorer accumulated in fp64.  One step = one pass of
+the hot path over one batch of --histories primaries per GPU (default 1e7): device beam source ->
+transport -> scoring, plus (N > 1) one NCCL reduce of the per-GPU dose grids to rank 0.  Histories
+are sharded by index range, no other collective: scaling is weak (per-GPU work fixed).
+
+  value  whole-job histories/s with the HU volume, beam model and dose grid resident in HBM,
+         timed with CUDA events on the launching stream, max over ranks;
+  e2e    the same through the reference-facing C ABI with HOST buffers: every step uploads the int16
+         HU volume (pinned) and the beam model, transports, and downloads the fp64 dose grid;
+  roofline  HBM bound of the transport kernel: algorithmic bytes = 20 B per scored step (4 B density
+         read + 8 B + 8 B fp64 dose read-modify-write) x 446.3 oracle-measured steps per 200 MeV
+         history = 8 926 B per history, against MEASURED_PEAKS.json;
+  cpu_baseline  the reference's own CPU phantom_env (oracle/_ref, built from /root/reference with
+         the two documented patches) on all host cores, bounded sample, rank 0, N = 1.
+
+--impl reference times that CPU reference alone (all host cores, bounded sample per step).
+"""
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "primary proton histories/s (C1: 200 MeV, water phantom 200x200x350, Dose scorer)"
+UNIT = "histories/s"
+NXYZ = (200, 200, 350)
+LXYZ = (100.0, 100.0, 350.0)
+ENERGY = 200.0
+SPOT = 30.0
+STEPS_PER_HISTORY = 446.3      # SURVEY.md section 8d, oracle-measured scored steps per 200 MeV history
+BYTES_PER_STEP = 20.0          # 4 B density + 8 B + 8 B fp64 dose RMW
+WORKLOAD = ("C1 phantom_env case at throughput size: 200 MeV pencil beam, 30 mm uniform square spot, "
+            "water phantom 100x100x350 mm on a 200x200x350 grid, debug physics, 1 Dose scorer (fp64)")
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampled during the timed region
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        self.proc = subprocess.Popen([exe, "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                      "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self.t = threading.Thread(target=self._pump, daemon=True)
+        self.t.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference's own CPU implementation (oracle/_ref), all host cores
+# --------------------------------------------------------------------------------------------------
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "phantom_env_cpu_debug")
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_sample(procs, histories_per_proc, seed):
+    """P independent single-threaded reference processes (the reference CPU path is single-threaded,
+    mqi_phantom_env.hpp:420) on the bench workload.  Returns (total histories, seconds) where seconds
+    is the slowest process's transport phase: the reference's own 'Run done <x> s' print, rescaled
+    by 10 because it multiplies milliseconds by 1e-4 (mqi_phantom_env.hpp:427)."""
+    import numpy as np
+    if not os.path.exists(REF_EXE):
+        raise RuntimeError("oracle/_ref/phantom_env_cpu_debug is missing (run `make -C oracle ref` in the build container)")
+    work = tempfile.mkdtemp(prefix="mqi_bench_ref_")
+    try:
+        ph = os.path.join(work, "phantom.raw")
+        np.zeros((NXYZ[2], NXYZ[1], NXYZ[0]), dtype=np.int16).tofile(ph)
+        ps = []
+        for p in range(procs):
+            od = os.path.join(work, "o%d" % p)
+            os.makedirs(od)
+            cmd = [REF_EXE, "--lxyz", "100", "100", "350", "--pxyz", "0.0", "0.0", "-175", "--nxyz", "200", "200", "350",
+                   "--spot_energy", str(ENERGY), "0.0", "--spot_position", "0", "0", "0.5",
+                   "--spot_size", str(SPOT), str(SPOT), "--histories", str(histories_per_proc),
+                   "--phantom_path", ph, "--output_prefix", od, "--random_seed", str(seed + 7919 * p), "--gpu_id", "0"]
+            ps.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        slowest = 0.0
+        for pr in ps:
+            out, _ = pr.communicate()
+            if pr.returncode != 0:
+                raise RuntimeError("reference process failed: rc=%d" % pr.returncode)
+            m = re.search(r"Run done ([0-9.eE+-]+) s", out)
+            if not m:
+                raise RuntimeError("reference output has no 'Run done' line")
+            slowest = max(slowest, 10.0 * float(m.group(1)))
+        return procs * histories_per_proc, slowest
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def reference_procs():
+    # each process holds ~0.35 GB (224 MB scorer table + 56 MB density + 28 MB HU); stay within RAM
+    cores = host_cores()
+    try:
+        avail_gb = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2**30
+        cores = max(1, min(cores, int(avail_gb / 0.5)))
+    except (ValueError, OSError):
+        pass
+    return cores
+
+
+def bench_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    procs = reference_procs()
+    n = args.ref_histories_per_proc
+    for _ in range(args.warmup):
+        run_reference_sample(procs, max(200, n // 10), 1)
+    total_h, total_s = 0, 0.0
+    for s in range(args.steps):
+        h, sec = run_reference_sample(procs, n, 1000 + s)
+        total_h += h
+        total_s += sec
+    value = total_h / total_s
+    sample = "%d processes x %d histories per step of the bench workload, transport phase only" % (procs, n)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 transport, f64 dose accumulation", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "histories_per_step": procs * n, "device": "host CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# the B200 path
+# --------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(histories_per_launch):
+    """dram bytes per launch of the transport kernel from the committed ncu --set full capture, if it
+    was taken at this launch size (profiles/roofline_traffic.json), else None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        d = json.load(open(p))
+        if int(d["histories_per_launch"]) == int(histories_per_launch):
+            return float(d["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
+def bench_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from moquimc_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with --nproc-per-node %d" % (args.gpus, args.gpus))
+        raise SystemExit("WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the transport path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    H = int(args.histories)
+    K, W = args.steps, args.warmup
+    nx, ny, nz = NXYZ
+    nvox = nx * ny * nz
+    xe, ye, ze = capi.uniform_edges(-50, 50, nx), capi.uniform_edges(-50, 50, ny), capi.uniform_edges(-350, 0, nz)
+    beamlet = capi.make_beamlet(ENERGY, [0, 0, 0.5, 0, 0, -1], [SPOT, SPOT, 0, 0, 0, 0], uniform=True)
+    total = (W + K) * world * H
+
+    # ---------------- HBM-resident leg ----------------
+    eng = capi.Engine(local, physics=capi.PHYSICS_DEBUG)
+    # the transport kernel is launched on torch's current stream so that torch events bracket it; a
+    # side stream, because the legacy default stream has handle 0 (= "use the handle's own stream")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    d_hu = torch.zeros(nvox, dtype=torch.int16, device=dev)
+    eng.set_grid_hu_device(xe, ye, ze, d_hu.data_ptr())
+    s_dose = eng.add_scorer(capi.SCORER_DOSE, "Dose")
+    dose = torch.zeros(nvox, dtype=torch.float64, device=dev)       # this rank's grid of the current step
+    eng.bind_scorer_buffer(s_dose, dose.data_ptr())
+    total_dose = torch.zeros(nvox, dtype=torch.float64, device=dev) if world > 1 and rank == 0 else None
+    eng.set_beamlets([beamlet], [total])
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(s):
+        """one batch on this rank: histories [(s*world + rank)*H, +H), then the dose reduce"""
+        if world > 1:
+            dose.zero_()
+        eng.run_async(args.seed, (s * world + rank) * H, H)
+        if world > 1:
+            dist.reduce(dose, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                total_dose.add_(dose)
+
+    for s in range(W):
+        step(s)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kernel_ms, launches = [], 0
+    t_wall = time.perf_counter()
+    for s in range(K):
+        flush.fill_(s & 0xff)            # evict the dose / material volumes from L2 between steps (untimed)
+        ev[s][0].record(stream)
+        step(W + s)
+        ev[s][1].record(stream)
+        st = eng.run_stats()             # waits for the kernel; device time of this launch
+        kernel_ms.append(st.kernel_ms)
+        launches += st.launches
+        assert st.histories == H, (st.histories, H)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * H * K / (ms * 1e-3)
+    checksum = float((total_dose if total_dose is not None else dose).sum().item()) if rank == 0 else 0.0
+    eng.set_stream(None)
+    eng.close()
+    del dose, total_dose, d_hu, flush
+    torch.cuda.empty_cache()
+
+    # ---------------- end-to-end leg: host buffers through the C ABI ----------------
+    hu_host = torch.zeros(nvox, dtype=torch.int16).pin_memory()
+    out_host = torch.empty(nvox, dtype=torch.float64).pin_memory()
+    red = torch.zeros(nvox, dtype=torch.float64, device=dev) if world > 1 else None
+    e2 = capi.Engine(local, physics=capi.PHYSICS_DEBUG)
+    e2_s = e2.add_scorer(capi.SCORER_DOSE, "Dose")
+    if world > 1:
+        e2.set_stream(stream.cuda_stream)
+        e2.bind_scorer_buffer(e2_s, red.data_ptr())
+
+    e2e_kernel_ms = []
+
+    def e2e_step(s):
+        e2.set_grid_hu(xe, ye, ze, hu_host.numpy().reshape(nz, ny, nx))          # H2D: HU volume
+        e2.set_beamlets([beamlet], [total])                                       # H2D: beam model
+        if world > 1:
+            red.zero_()
+        else:
+            e2.clear_scorers()
+        st = e2.run(args.seed, (s * world + rank) * H, H)
+        e2e_kernel_ms.append(st.kernel_ms)
+        if world > 1:
+            dist.reduce(red, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                out_host.copy_(red, non_blocking=False)                          # D2H: reduced dose
+            torch.cuda.synchronize()
+        else:
+            e2.get_dense(e2_s, out=out_host.numpy())                              # D2H: dose grid
+
+    ke = max(1, min(K, args.e2e_steps))
+    e2e_step(0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for s in range(ke):
+        e2e_step(W + s)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * H * ke / e2e_s
+    h2d = world * (nvox * 2 + 4 * (nx + ny + nz + 3) + 128 + 8)
+    d2h = nvox * 8
+    e2.close()
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        k_ms = sum(kernel_ms) / len(kernel_ms)
+        alg_bytes = H * STEPS_PER_HISTORY * BYTES_PER_STEP
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 transport, f64 dose accumulation", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "histories_per_gpu_per_step": H, "global_histories_per_step": world * H,
+                       "parallelism": "histories sharded over %d GPU(s), one NCCL reduce of the dose grid per step" % world
+                       if world > 1 else "1 GPU",
+                       "l2": "256 MB flush written between timed steps (untimed); working set 140 MB > 126 MB L2",
+                       "timer": "CUDA events on the launching stream per step, max over ranks",
+                       "dose_checksum": checksum, "wall_s_timed_region": t_wall},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": ke, "kernel_ms_per_step": sum(e2e_kernel_ms[1:]) / max(1, len(e2e_kernel_ms) - 1), "timer": "host wall clock around blocking C-ABI calls, synchronised both sides"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(H), "peak_source": peak_src, "kernel": "transport_kernel<debug>",
+                         "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "latency/issue bound, not HBM bound: the dose grid hot set stays in L2 (see DESIGN.md)"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                procs = reference_procs()
+                n = args.ref_histories_per_proc
+                h, sec = run_reference_sample(procs, n, 4242)
+                line["cpu_baseline"] = {"value": h / sec, "unit": UNIT, "cores": procs, "kind": "reference",
+                                        "sample": "%d reference processes x %d histories of the bench workload, "
+                                                  "transport phase only" % (procs, n)}
+            except Exception as ex:   # the checker is missing: report it, never fake a number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %s" % ex}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--histories", type=float, default=1e7, help="primaries per GPU per step")
+    ap.add_argument("--seed", type=int, default=12345)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--ref-histories-per-proc", type=int, default=20000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return bench_reference(args)
+    return bench_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -146,8 +146,18 @@ MQI_API int mqi_set_vertices(mqi_handle* h, const mqi_vertex* vertices, uint64_t
  * Scorers accumulate across calls until mqi_clear_scorers (device tables persist across batches,
  * mqi_upload_data.hpp:250-253). */
 MQI_API int mqi_run(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t count, int per_spot);
+/* Same launch without the trailing synchronisation: returns as soon as the kernel is queued on the
+ * handle's stream; mqi_get_run_stats (or any download) waits for it.  Lets the caller overlap
+ * transport with NCCL reductions / copies on other streams and time it with its own events. */
+MQI_API int mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t count, int per_spot);
+/* waits for the last mqi_run_async and returns its counters and device time */
 MQI_API int mqi_get_run_stats(mqi_handle* h, mqi_run_stats* out);
+/* options: "count_steps" (0/1), "blocks_per_sm" (cap on resident CTAs per SM, 0 = occupancy limit) */
 MQI_API int mqi_set_option(mqi_handle* h, const char* key, int64_t value);
+/* Launch on a caller-owned cudaStream_t (e.g. the framework's current stream, so that its events
+ * bracket the kernels) instead of the handle's own stream; NULL restores the handle's stream.  The
+ * reference uses the default stream throughout (mqi_phantom_env.hpp:391-397). */
+MQI_API int mqi_set_stream(mqi_handle* h, void* cuda_stream);
 
 /* download_node + reshape_data (mqi_download_data.hpp:37-121, mqi_xenvironment.hpp:150-167):
  * dense float64 [nz][ny][nx] of a scorer, times scale. */
@@ -185,6 +195,11 @@ MQI_API int mqi_dev_grid_entry(mqi_handle* h, const float* p, const float* d, ui
 /* mc::hash_fun(k1,k2,capacity) (mqi_transport.hpp:32-51) */
 MQI_API int mqi_dev_hash(mqi_handle* h, const uint32_t* k1, const uint32_t* k2, const uint64_t* capacity, uint64_t n,
                  uint32_t* out);
+/* mc::insert_hashtable (mqi_transport.hpp:68-111) on its own: score n caller-supplied hits
+ * (key1 = voxel, key2 = spot or 0xffffffff for the dense mode, value) into a scorer; hits with
+ * value <= 0 are skipped like in the reference.  Host pointers. */
+MQI_API int mqi_dev_insert(mqi_handle* h, int scorer, const uint32_t* key1, const uint32_t* key2, const double* value,
+                   uint64_t n);
 /* beamlet::operator() on the device for history ids [first, first+n) (subsystem 1) */
 MQI_API int mqi_dev_sample_vertices(mqi_handle* h, uint64_t seed, uint64_t first, uint64_t n, mqi_vertex* out,
                             uint32_t* spot_out);

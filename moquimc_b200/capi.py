@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmqi_b200.so")
+# MQI_B200_LIB: alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("MQI_B200_LIB") or os.path.join(HERE, "libmqi_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "mqi_b200.h")
 
 PHYSICS_RELEASE, PHYSICS_DEBUG = 0, 1
@@ -73,6 +74,8 @@ def load():
         "mqi_set_beamlets": [vp, C.POINTER(Beamlet), u32, C.POINTER(u64)],
         "mqi_set_vertices": [vp, vp, u64, vp],
         "mqi_run": [vp, u64, u64, u64, i32],
+        "mqi_run_async": [vp, u64, u64, u64, i32],
+        "mqi_set_stream": [vp, vp],
         "mqi_get_run_stats": [vp, C.POINTER(RunStats)],
         "mqi_set_option": [vp, C.c_char_p, C.c_int64],
         "mqi_get_dense": [vp, i32, vp, C.c_double],
@@ -87,6 +90,7 @@ def load():
         "mqi_dev_grid_entry": [vp, vp, vp, u64, vp, vp],
         "mqi_dev_hash": [vp, vp, vp, vp, u64, vp],
         "mqi_dev_sample_vertices": [vp, u64, u64, u64, vp, vp],
+        "mqi_dev_insert": [vp, i32, vp, vp, vp, u64],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -239,8 +243,22 @@ class Engine:
         self._check(self.L.mqi_get_run_stats(self.h, C.byref(st)))
         return st
 
-    def get_dense(self, scorer, scale=1.0):
-        out = np.empty(self.nvox, dtype=np.float64)
+    def run_async(self, seed, first, count, per_spot=False):
+        self._check(self.L.mqi_run_async(self.h, seed, first, count, 1 if per_spot else 0))
+
+    def run_stats(self):
+        st = RunStats()
+        self._check(self.L.mqi_get_run_stats(self.h, C.byref(st)))
+        return st
+
+    def set_stream(self, cuda_stream):
+        self._check(self.L.mqi_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def get_dense(self, scorer, scale=1.0, out=None):
+        """out: optional caller-owned host buffer (e.g. pinned memory) of nvox float64."""
+        if out is None:
+            out = np.empty(self.nvox, dtype=np.float64)
+        assert out.size == self.nvox and out.dtype == np.float64
         self._check(self.L.mqi_get_dense(self.h, scorer, out.ctypes.data, scale))
         return out.reshape(self.shape)
 
@@ -311,6 +329,13 @@ class Engine:
         out = np.empty(k1.size, dtype=np.uint32)
         self._check(self.L.mqi_dev_hash(self.h, k1.ctypes.data, k2.ctypes.data, cap.ctypes.data, k1.size, out.ctypes.data))
         return out
+
+    def dev_insert(self, scorer, key1, key2, value):
+        key1 = np.ascontiguousarray(key1, dtype=np.uint32)
+        key2 = np.ascontiguousarray(key2, dtype=np.uint32)
+        value = np.ascontiguousarray(value, dtype=np.float64)
+        assert key1.size == key2.size == value.size
+        self._check(self.L.mqi_dev_insert(self.h, scorer, key1.ctypes.data, key2.ctypes.data, value.ctypes.data, key1.size))
 
     def dev_sample_vertices(self, seed, first, n):
         v = np.empty((n, 7), dtype=np.float32)

@@ -124,7 +124,9 @@ dedx_term0() {   // physics_constants::two_pi_re2_mc2_h2o  base/mqi_physics_cons
 
 struct mqi_handle {
     int          device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // the stream kernels are launched on
+    cudaStream_t own_stream = nullptr;   // created by mqi_create
+    bool         pending = false;        // an mqi_run_async launch has not been collected yet
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
     int          sm_count = 148;
     int          variant  = MQI_PHYSICS_RELEASE;
@@ -328,7 +330,8 @@ mqi_create(int device_id, mqi_handle** out) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device_id));
     h->sm_count = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
     // physics tables -> value + slope rows (one shared-memory row per interpolation); tables 0-2 live
@@ -377,7 +380,7 @@ mqi_destroy(mqi_handle* h) {
     cudaFree(h->d_tab_a0); cudaFree(h->d_tab_a1); cudaFree(h->d_tab_bs); cudaFree(h->d_tab_n0); cudaFree(h->d_tab_n1); cudaFree(h->d_correction); cudaFree(h->d_counters);
     cudaFree(h->d_beamlets); cudaFree(h->d_cum); cudaFree(h->d_vertices); cudaFree(h->d_spot_ids);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
-    cudaStreamDestroy(h->stream);
+    cudaStreamDestroy(h->own_stream);
     delete h;
     return MQI_OK;
 }
@@ -564,8 +567,27 @@ mqi_set_vertices(mqi_handle* h, const mqi_vertex* vertices, uint64_t n, const ui
     return MQI_OK;
 }
 
+static int
+collect_run(mqi_handle* h) {
+    if (!h->pending) return MQI_OK;
+    CU(cudaStreamSynchronize(h->stream));
+    unsigned long long c[C_COUNT];
+    CU(cudaMemcpy(c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.histories       = c[C_DONE];
+    h->stats.steps           = c[C_STEPS];
+    h->stats.secondaries     = c[C_SECONDARIES];
+    h->stats.stack_overflows = c[C_OVERFLOW];
+    h->stats.dij_table_full  = c[C_DIJ_FULL];
+    h->stats.kernel_ms       = ms;
+    h->stats.launches        = 1;
+    h->pending               = false;
+    return MQI_OK;
+}
+
 int
-mqi_run(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t count, int per_spot) {
+mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t count, int per_spot) {
     int rc = activate(h);
     if (rc) return rc;
     if (!h->has_grid) return fail(MQI_ESTATE, "no grid set");
@@ -576,6 +598,8 @@ mqi_run(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t count, in
         if (!h->d_beamlets) return fail(MQI_ESTATE, "no beam source set");
         if (first_history + count > h->total_histories) return fail(MQI_EINVAL, "history range exceeds the beam source");
     }
+    rc = collect_run(h);   // counters of a previous asynchronous launch are overwritten below
+    if (rc) return rc;
     rc = ensure_scorer_buffers(h);
     if (rc) return rc;
     std::memset(&h->stats, 0, sizeof(h->stats));
@@ -592,7 +616,7 @@ mqi_run(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t count, in
     }
     const size_t smem = transport_smem_bytes(h->nx, h->ny, h->nz);
     int          bps  = 0;
-    CU(transport_occupancy(h->variant, smem, &bps));
+    CU(transport_occupancy(h->variant, transport_is_simple(p), smem, &bps));
     if (bps < 1) return fail(MQI_ECUDA, "transport kernel does not fit on an SM");
     if (h->blocks_per_sm_override > 0) bps = std::min(bps, h->blocks_per_sm_override);
     // persistent grid: a whole number of CTAs per SM, never more lanes than histories
@@ -602,25 +626,36 @@ mqi_run(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t count, in
     CU(cudaEventRecord(h->ev0, h->stream));
     CU(launch_transport(p, h->variant, grid, smem, h->stream));
     CU(cudaEventRecord(h->ev1, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    unsigned long long c[C_COUNT];
-    CU(cudaMemcpy(c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
-    float ms = 0.f;
-    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-    h->stats.histories       = c[C_DONE];
-    h->stats.steps           = c[C_STEPS];
-    h->stats.secondaries     = c[C_SECONDARIES];
-    h->stats.stack_overflows = c[C_OVERFLOW];
-    h->stats.dij_table_full  = c[C_DIJ_FULL];
-    h->stats.kernel_ms       = ms;
-    h->stats.launches        = 1;
+    h->pending = true;
     return MQI_OK;
+}
+
+int
+mqi_run(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t count, int per_spot) {
+    int rc = mqi_run_async(h, seed, first_history, count, per_spot);
+    if (rc) return rc;
+    return collect_run(h);
 }
 
 int
 mqi_get_run_stats(mqi_handle* h, mqi_run_stats* out) {
     if (!h || !out) return fail(MQI_EINVAL, "null argument");
+    int rc = activate(h);
+    if (rc) return rc;
+    rc = collect_run(h);
+    if (rc) return rc;
     *out = h->stats;
+    return MQI_OK;
+}
+
+int
+mqi_set_stream(mqi_handle* h, void* cuda_stream) {
+    int rc = activate(h);
+    if (rc) return rc;
+    rc = collect_run(h);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
     return MQI_OK;
 }
 
@@ -858,6 +893,32 @@ mqi_dev_hash(mqi_handle* h, const uint32_t* k1, const uint32_t* k2, const uint64
     CU(cudaMemcpyAsync(dc.p, capacity, n * 8, cudaMemcpyHostToDevice, h->stream));
     CU(launch_dev_hash(d1.p, d2.p, dc.p, n, dout.p, h->stream));
     CU(cudaMemcpyAsync(out, dout.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return MQI_OK;
+}
+
+int
+mqi_dev_insert(mqi_handle* h, int scorer, const uint32_t* key1, const uint32_t* key2, const double* value, uint64_t n) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (scorer < 0 || scorer >= (int) h->scorers.size()) return fail(MQI_EINVAL, "bad scorer index");
+    if (!key1 || !key2 || !value) return fail(MQI_EINVAL, "null argument");
+    if (!h->has_grid) return fail(MQI_ESTATE, "no grid set");
+    if (n == 0) return MQI_OK;
+    if (h->scorers[scorer].kind != MQI_SCORER_DIJ)
+        for (uint64_t i = 0; i < n; ++i)
+            if (key1[i] >= nvox(h)) return fail(MQI_EINVAL, "voxel key out of range");
+    rc = ensure_scorer_buffers(h);
+    if (rc) return rc;
+    DevBuf<uint32_t> d1, d2;
+    DevBuf<double>   dv;
+    CU(d1.alloc(n)); CU(d2.alloc(n)); CU(dv.alloc(n));
+    CU(cudaMemcpyAsync(d1.p, key1, n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d2.p, key2, n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dv.p, value, n * 8, cudaMemcpyHostToDevice, h->stream));
+    Params prm;
+    fill_params(h, prm);
+    CU(launch_dev_insert(prm, scorer, d1.p, d2.p, dv.p, n, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return MQI_OK;
 }

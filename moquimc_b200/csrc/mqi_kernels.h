@@ -22,7 +22,7 @@
 #define MQI_K_BLOCK 256
 #endif
 #ifndef MQI_K_MIN_BLOCKS
-#define MQI_K_MIN_BLOCKS 2
+#define MQI_K_MIN_BLOCKS 4   /* 64 registers/thread: measured best of 2/3/4 on B200 (profiles/) */
 #endif
 
 namespace mqib
@@ -33,7 +33,8 @@ struct BeamletDev;
 struct VertexDev;
 
 size_t      transport_smem_bytes(int nx, int ny, int nz);
-cudaError_t transport_occupancy(int variant, size_t smem, int* blocks_per_sm);
+bool        transport_is_simple(const Params& p);
+cudaError_t transport_occupancy(int variant, bool simple, size_t smem, int* blocks_per_sm);
 cudaError_t launch_transport(const Params& p, int variant, int grid, size_t smem, cudaStream_t st);
 
 // HU volume -> 16-bit material index volume (index = clamp(hu) + 1000)
@@ -52,6 +53,8 @@ cudaError_t launch_dev_hash(const uint32_t* k1, const uint32_t* k2, const unsign
                             uint32_t* out, cudaStream_t st);
 cudaError_t launch_dev_sample(const Params& p, unsigned long long first, size_t n, VertexDev* out,
                               uint32_t* spot, cudaStream_t st);
+cudaError_t launch_dev_insert(const Params& p, int scorer, const uint32_t* k1, const uint32_t* k2, const double* v,
+                              size_t n, cudaStream_t st);
 cudaError_t launch_fill_u64(unsigned long long* p, unsigned long long v, size_t n, cudaStream_t st);
 cudaError_t launch_dij_clear(void* table, size_t capacity, cudaStream_t st);
 cudaError_t launch_dij_count(const void* table, size_t capacity, unsigned long long* d_count, cudaStream_t st);

@@ -28,49 +28,12 @@ struct Smem {
     const float*  ze;
 };
 
+// Cross sections [mm^2/g]: delta production on the p-ion grid plus the three nuclear channels
+// (pre-summed for the mean free path: linear interpolation commutes with the sum), mqi_p_ionization.hpp:
+// 254-268, mqi_pp_elastic.hpp:221-235, mqi_po_elastic.hpp:243-256, mqi_po_inelastic.hpp:141-155.
 // row of the p-ionisation grid (Ei = 0.1, step 0.5): uint16_t((Ek - Ei) / 0.5)
 __device__ __forceinline__ int row_a(float ek) { return min(max((int) ((ek - 0.1f) * 2.0f), 0), kTableN - 1); }
 __device__ __forceinline__ int row_b(float ek) { return min(max((int) ((ek - 0.5f) * 2.0f), 0), kTableN - 1); }
-
-// sum of the four tabulated cross sections [mm^2/g] at kinetic energy e: delta production on the
-// p-ion grid plus the three nuclear channels (pre-summed: linear interpolation commutes with the sum)
-// mqi_p_ionization.hpp:254-268, mqi_pp_elastic.hpp:221-235, mqi_po_elastic.hpp:243-256,
-// mqi_po_inelastic.hpp:141-155
-__device__ __forceinline__ float
-cs_total(const Smem& sm, float e) {
-    float cs = 0.f;
-    if (e >= 0.1f && e <= 299.6f) {
-        const int    i = row_a(e);
-        const float4 a = sm.a0[i];
-        cs             = fmaf(e - (0.1f + i * 0.5f), a.y, a.x);
-    }
-    if (e >= 0.5f && e <= 300.0f) {
-        const int    i = row_b(e);
-        const float2 b = sm.bs[i];
-        cs += fmaf(e - (0.5f + i * 0.5f), b.y, b.x);
-    }
-    return cs;
-}
-
-// the four channels separately (only needed when a discrete interaction was selected)
-__device__ __forceinline__ void
-cs_channels(const Smem& sm, const Params& P, float e, float cs[4]) {
-    cs[0] = cs[1] = cs[2] = cs[3] = 0.f;
-    if (e >= 0.1f && e <= 299.6f) {
-        const int    i = row_a(e);
-        const float4 a = sm.a0[i];
-        cs[0]          = fmaf(e - (0.1f + i * 0.5f), a.y, a.x);
-    }
-    if (e >= 0.5f && e <= 300.0f) {
-        const int    i = row_b(e);
-        const float  t = e - (0.5f + i * 0.5f);
-        const float4 n0 = __ldg(P.tab_n0 + i);
-        const float2 n1 = __ldg(P.tab_n1 + i);
-        cs[1] = fmaf(t, n0.y, n0.x);
-        cs[2] = fmaf(t, n0.w, n0.z);
-        cs[3] = fmaf(t, n1.y, n1.x);
-    }
-}
 
 // |dEdx| in water (restricted stopping power), mqi_p_ionization.hpp:271-286
 __device__ __forceinline__ float
@@ -136,7 +99,8 @@ struct NucIO {
     float d1x, d1y, d1z;            // vtx1.dir, in/out
     float ke1;                      // vtx1.ke, in/out
     float dE, local_dE;             // deposits, in/out
-    float u, c1, c2, c3;            // selector (already reduced by the delta channel) and channel cross sections
+    float u, e_cs, rho;             // selector (already reduced by the delta channel), energy of the cross sections
+    float c1, c2, c3;               // nuclear channel cross sections (filled by nuclear_event)
     int   stopped;
     int   sp;                       // stack pointer, in/out
     unsigned n_sec, n_ovf;          // counters, out
@@ -176,6 +140,19 @@ template<int VARIANT>
 __device__ __noinline__ void
 nuclear_event(const Params& P, Secondary* stack, NucIO& io) {
     RngBuf& rb = io.rb;
+    {   // the three nuclear channels at the energy whose total was the larger one (:111-118)
+        io.c1 = io.c2 = io.c3 = 0.f;
+        const float e = io.e_cs;
+        if (e >= 0.5f && e <= 300.0f) {
+            const int    i  = row_b(e);
+            const float  t  = e - (0.5f + i * 0.5f);
+            const float4 n0 = __ldg(P.tab_n0 + i);
+            const float2 n1 = __ldg(P.tab_n1 + i);
+            io.c1 = fmaf(t, n0.y, n0.x) * io.rho;
+            io.c2 = fmaf(t, n0.w, n0.z) * io.rho;
+            io.c3 = fmaf(t, n1.y, n1.x) * io.rho;
+        }
+    }
     if (io.u < io.c1) {
         // p-p elastic, pp_elastic_tabulated::post_step mqi_pp_elastic.hpp:119-219
         const Rel   r1   = rel_make(io.ke1);
@@ -371,6 +348,14 @@ struct StepResult {
     float len;       // |vtx1.pos - vtx0.pos|
 };
 
+// LETd_weight1/2: scorers/mqi_scorer_energy_deposit.hpp:93-137 (out of line: fp64 divisions)
+__device__ __noinline__ double
+letd_hit(int kind, float dE, float len, float rho) {
+    const double let = (double) dE / (double) len / (double) (rho * 1000.0f);
+    if (!(let < 25.0)) return 0.0;
+    return kind == MQI_K_LETD_NUMER ? (double) dE * let : (double) dE;
+}
+
 // one insert per scorer per step, keyed to the voxel occupied at step start: mqi_transport.hpp:204-225,
 // hit functions scorers/mqi_scorer_energy_deposit.hpp:14-137
 template<int VARIANT>
@@ -390,11 +375,7 @@ score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, 
         if (kind == MQI_K_DOSE || kind == MQI_K_DIJ) v = dose + dose_te;
         else if (kind == MQI_K_DOSE_SQ) v = dose * dose + dose_te * dose_te;
         else if (kind == MQI_K_EDEP) v = (double) (r.dE + r.local_dE) + (double) r.te_debug;
-        else if (r.len > 0.f) {
-            // LETd_weight1/2: scorers/mqi_scorer_energy_deposit.hpp:93-137
-            const double let = (double) r.dE / (double) r.len / (double) (M.rho * 1000.0f);
-            if (let < 25.0) v = kind == MQI_K_LETD_NUMER ? (double) r.dE * let : (double) r.dE;
-        }
+        else if (r.len > 0.f) v = letd_hit(kind, r.dE, r.len, M.rho);
         if (!(v > 0.0)) continue;   // insert_hashtable: value <= 0 -> skip
         // quirk B2: the reference's non-stat kernel scores scorers [0, n-2) twice when n >= 3
         if ((P.quirks & MQI_K_QUIRK_B2) && s < n - 2) v += v;
@@ -406,7 +387,9 @@ score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, 
 // ---------------------------------------------------------------------------------------------
 // the transport kernel
 // ---------------------------------------------------------------------------------------------
-template<int VARIANT>
+// SIMPLE: exactly one dense Dose scorer (phantom_env, and the tps "Dose" case): the scorer loop and
+// the other hit functions are compiled out of the voxel-step loop.
+template<int VARIANT, bool SIMPLE>
 __global__ void __launch_bounds__(MQI_K_BLOCK, MQI_K_MIN_BLOCKS)
 transport_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -510,21 +493,27 @@ transport_kernel(const __grid_constant__ Params P) {
                 const float p[3] = { px, py, pz };
                 float       d[3] = { dx, dy, dz };
                 int         c[3];
-                const float dist = grid_entry(sm.xe, sm.ye, sm.ze, nx, ny, nz, p, d, c);
+                const float dist = grid_entry(sm.xe, sm.ye, sm.ze, nx, ny, nz, P.g.inv_w, p, d, c);
                 if (dist < 0.f) {
                     alive = false;
                 } else {
                     // update_post_vertex_position uses the (possibly zeroed) direction, move() then
-                    // restores the un-zeroed copy held in vtx1.dir; vtx1.ke becomes vtx0.ke
+                    // restores the un-zeroed copy held in vtx1.dir; vtx1.ke becomes vtx0.ke.  The cell
+                    // of the moved point is the one intersect() already looked up (same point, same d
+                    // up to the zeroed components, which only matter exactly on an edge).
                     px = __fadd_rn(px, __fmul_rn(d[0], dist));
                     py = __fadd_rn(py, __fmul_rn(d[1], dist));
                     pz = __fadd_rn(pz, __fmul_rn(d[2], dist));
                     ke += ke1_off;
                     ke1_off = 0.f;
                     dE_pre  = 0.f;
-                    ix = index_axis_guess(sm.xe, nx, px, dx, P.g.inv_w[0]);
-                    iy = index_axis_guess(sm.ye, ny, py, dy, P.g.inv_w[1]);
-                    iz = index_axis_guess(sm.ze, nz, pz, dz, P.g.inv_w[2]);
+                    if (d[0] == dx && d[1] == dy && d[2] == dz) {
+                        ix = c[0]; iy = c[1]; iz = c[2];
+                    } else {
+                        ix = index_axis_guess(sm.xe, nx, px, dx, P.g.inv_w[0]);
+                        iy = index_axis_guess(sm.ye, ny, py, dy, P.g.inv_w[1]);
+                        iz = index_axis_guess(sm.ze, nz, pz, dz, P.g.inv_w[2]);
+                    }
                     if (ix < 0 || iy < 0 || iz < 0 || ix >= nx || iy >= ny || iz >= nz) alive = false;
                 }
             }
@@ -604,16 +593,29 @@ transport_kernel(const __grid_constant__ Params P) {
             const float4 A1  = sm.a1[ia];
             const bool   in_a = ke <= 299.6f;   // ke > 0.5 here
             const float  sp_w = in_a ? fmaf(ta, A0.w, A0.z) : 0.f;
-            float cs1_sum     = in_a ? fmaf(ta, A0.y, A0.x) : 0.f;
+            const float cs1_ion = in_a ? fmaf(ta, A0.y, A0.x) : 0.f;
+            float       cs1_sum = cs1_ion;
             if (ke <= 300.0f) {
                 const int    ib = row_b(ke);
                 const float2 b  = sm.bs[ib];
                 cs1_sum += fmaf(ke - (0.5f + ib * 0.5f), b.y, b.x);
             }
-            const float e2      = ke - cms * sp_w;   // energy after the largest possible CSDA loss
-            const float cs2_sum = cs_total(sm, e2);
-            const bool  use1    = cs1_sum >= cs2_sum;
-            const float cs_sum  = (use1 ? cs1_sum : cs2_sum) * rho;
+            const float e2 = ke - cms * sp_w;   // energy after the largest possible CSDA loss
+            float       cs2_ion = 0.f, cs2_sum = 0.f;
+            if (e2 >= 0.1f) {   // e2 < ke <= 299.6 inside the table
+                const int    i = row_a(e2);
+                const float4 a = sm.a0[i];
+                cs2_ion        = fmaf(e2 - (0.1f + i * 0.5f), a.y, a.x);
+                cs2_sum        = cs2_ion;
+                if (e2 >= 0.5f) {
+                    const int    j = row_b(e2);
+                    const float2 b = sm.bs[j];
+                    cs2_sum += fmaf(e2 - (0.5f + j * 0.5f), b.y, b.x);
+                }
+            }
+            const bool  use1   = cs1_sum >= cs2_sum;
+            const float cs_sum = (use1 ? cs1_sum : cs2_sum) * rho;
+            const float c0     = (use1 ? cs1_ion : cs2_ion) * rho;   // delta-electron channel
 
             const float mfp = -logf(u_mfp) / cs_sum;
             constexpr float step_limit = 1.0f;   // cms * rho_w / (rsp * rho): max_step, mqi_fippel_physics.hpp:20
@@ -665,20 +667,31 @@ transport_kernel(const __grid_constant__ Params P) {
             if (discrete && ke1 > kTpCut) {
                 d1x = dx; d1y = dy; d1z = dz;   // vtx1.dir = vtx0.dir (B11)
                 RngBuf rb;
-                rb.w   = philox_block(blk, h0, h1, k0, k1);
-                rb.blk = blk + 1; rb.pos = 0; rb.h0 = h0; rb.h1 = h1; rb.k0 = k0; rb.k1 = k1;
-                float cs[4];
-                cs_channels(sm, P, use1 ? ke : e2, cs);
-                const float u  = cs_sum * rb_uniform(rb);
-                const float c0 = cs[0] * rho;
+                {
+                    uint32_t w2[4];
+                    philox4x32_10(blk, 0u, h0, h1, k0, k1, w2);
+                    rb.w = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+                }
+                rb.blk = blk + 1; rb.pos = 1; rb.h0 = h0; rb.h1 = h1; rb.k0 = k0; rb.k1 = k1;
+                const float u = cs_sum * u32_to_uniform(rb.w.x);
                 if (u < c0) {
                     // delta electron, p_ionization_tabulated::post_step mqi_p_ionization.hpp:425-477
-                    const Rel r1 = rel_make(ke1);
-                    float     Te;
-                    while (true) {
-                        const float n = rb_uniform(rb);
-                        Te = T_cut * r1.Te_max / ((1.0f - n) * r1.Te_max + n * T_cut);
-                        if (rb_uniform(rb) < 1.0f - r1.beta_sq * Te / r1.Te_max + Te * Te / (2.0f * r1.Et * r1.Et)) break;
+                    const float Et1   = ke1 + kMp;
+                    const float g1    = Et1 * (1.0f / kMp);
+                    const float g1_sq = g1 * g1;
+                    const float b1_sq = 1.0f - 1.0f / g1_sq;
+                    const float Tmax1 = (2.0f * kMe * b1_sq * g1_sq) / (1.0f + 2.0f * g1 * MeMp + MeMp * MeMp);
+                    const float inv_Tmax1 = 1.0f / Tmax1, inv_2Et_sq = 0.5f / (Et1 * Et1);
+                    // first attempt from the words already at hand, further attempts (about 1 in 10) buffered
+                    float n  = u32_to_uniform(rb.w.y);
+                    float Te = T_cut * Tmax1 / ((1.0f - n) * Tmax1 + n * T_cut);
+                    rb.pos   = 3;
+                    if (!(u32_to_uniform(rb.w.z) < 1.0f - b1_sq * Te * inv_Tmax1 + Te * Te * inv_2Et_sq)) {
+                        while (true) {
+                            n  = rb_uniform(rb);
+                            Te = T_cut * Tmax1 / ((1.0f - n) * Tmax1 + n * T_cut);
+                            if (rb_uniform(rb) < 1.0f - b1_sq * Te * inv_Tmax1 + Te * Te * inv_2Et_sq) break;
+                        }
                     }
                     if (VARIANT == MQI_K_DEBUG) res.te_debug = Te;   // carried by a zero-energy daughter
                     else res.dE += Te;
@@ -690,7 +703,7 @@ transport_kernel(const __grid_constant__ Params P) {
                     io.p1x = p1x; io.p1y = p1y; io.p1z = p1z;
                     io.d1x = d1x; io.d1y = d1y; io.d1z = d1z;
                     io.ke1 = ke1; io.dE = res.dE; io.local_dE = res.local_dE;
-                    io.u = u - c0; io.c1 = cs[1] * rho; io.c2 = cs[2] * rho; io.c3 = cs[3] * rho;
+                    io.u = u - c0; io.e_cs = use1 ? ke : e2; io.rho = rho;
                     io.stopped = stopped ? 1 : 0;
                     io.sp = sp; io.n_sec = 0; io.n_ovf = 0;
                     io.rb = rb;
@@ -707,7 +720,16 @@ transport_kernel(const __grid_constant__ Params P) {
         // ------------------------------------------------------------------ scoring, :204-225
         if (rho >= 1.0e-7f && rho <= 99.9f) {
             const float inv_vol = 1.0f / ((ex1 - ex0) * (ey1 - ey0) * (ez1 - ez0));
-            score_step<VARIANT>(P, M, cnb, spot_ind, inv_vol, rsp0, res);
+            if (SIMPLE) {
+                // dose_to_water: (dE + local_dE) * 1.60218e-10 / (V * rho * rsp(rho, vtx0.ke)); voxel 0 is
+                // never scored (roi_->idx(cnb) > 0, B1); insert_hashtable skips value <= 0
+                const float kdose = 1.60218e-10f * inv_vol * M.inv_rho;
+                double      v     = (double) ((res.dE + res.local_dE) * kdose / rsp0);
+                if (VARIANT == MQI_K_DEBUG) v += (double) (res.te_debug * kdose * inv_rsp_at_zero_energy(M));
+                if (cnb != 0u && v > 0.0) dense_add(P.sc[0].dense, cnb, v, P.accum_mode);
+            } else {
+                score_step<VARIANT>(P, M, cnb, spot_ind, inv_vol, rsp0, res);
+            }
         }
 
         // ------------------------------------------------------------------ advance, :227-232
@@ -829,7 +851,7 @@ dev_grid_entry_kernel(GridDev g, const float* __restrict__ pin, const float* __r
         const float p[3] = { pin[3 * i], pin[3 * i + 1], pin[3 * i + 2] };
         float       d[3] = { din[3 * i], din[3 * i + 1], din[3 * i + 2] };
         int         c[3];
-        dist[i] = grid_entry(xe, ye, ze, g.nx, g.ny, g.nz, p, d, c);
+        dist[i] = grid_entry(xe, ye, ze, g.nx, g.ny, g.nz, g.inv_w, p, d, c);
         cell[3 * i] = c[0]; cell[3 * i + 1] = c[1]; cell[3 * i + 2] = c[2];
     }
 }
@@ -855,6 +877,18 @@ dev_sample_kernel(SourceDev src, unsigned long long seed, unsigned long long fir
         sample_vertex(src.beamlets[spot], seed, h, v);
         out[i]      = v;
         spot_out[i] = spot;
+    }
+}
+
+// scores externally computed hits (voxel, spot, value) into a scorer: the insert_hashtable half of
+// the path on its own (deterministic parity tests; also usable to merge deposits computed elsewhere)
+__global__ void
+dev_insert_kernel(ScorerDev sc, const uint32_t* __restrict__ k1, const uint32_t* __restrict__ k2,
+                  const double* __restrict__ v, size_t n, unsigned long long* counters) {
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        if (!(v[i] > 0.0)) continue;
+        if (sc.kind == MQI_K_DIJ) dij_add(sc.table, sc.capacity, k1[i], k2[i], v[i], counters);
+        else atomicAdd(sc.dense + k1[i], v[i]);
     }
 }
 
@@ -981,25 +1015,30 @@ transport_smem_bytes(int nx, int ny, int nz) {
     return kTableN * (2 * sizeof(float4) + sizeof(float2)) + (size_t) (nx + ny + nz + 3) * sizeof(float);
 }
 
-template<int V>
-static cudaError_t
-prep_transport(size_t smem) {
-    return cudaFuncSetAttribute(transport_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+typedef void (*transport_fn)(const Params);
+static transport_fn
+pick_transport(int variant, bool simple) {
+    if (variant == MQI_K_DEBUG) return simple ? transport_kernel<MQI_K_DEBUG, true> : transport_kernel<MQI_K_DEBUG, false>;
+    return simple ? transport_kernel<MQI_K_RELEASE, true> : transport_kernel<MQI_K_RELEASE, false>;
+}
+
+// one dense Dose scorer -> the specialised kernel
+bool
+transport_is_simple(const Params& p) {
+    return p.n_scorers == 1 && p.sc[0].kind == MQI_K_DOSE && !(p.quirks & MQI_K_QUIRK_B2);
 }
 
 cudaError_t
-transport_occupancy(int variant, size_t smem, int* blocks_per_sm) {
-    cudaError_t e = variant == MQI_K_DEBUG ? prep_transport<MQI_K_DEBUG>(smem) : prep_transport<MQI_K_RELEASE>(smem);
+transport_occupancy(int variant, bool simple, size_t smem, int* blocks_per_sm) {
+    transport_fn f = pick_transport(variant, simple);
+    cudaError_t  e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
-    if (variant == MQI_K_DEBUG)
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, transport_kernel<MQI_K_DEBUG>, MQI_K_BLOCK, smem);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, transport_kernel<MQI_K_RELEASE>, MQI_K_BLOCK, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, f, MQI_K_BLOCK, smem);
 }
 
 cudaError_t
 launch_transport(const Params& p, int variant, int grid, size_t smem, cudaStream_t st) {
-    if (variant == MQI_K_DEBUG) transport_kernel<MQI_K_DEBUG><<<grid, MQI_K_BLOCK, smem, st>>>(p);
-    else transport_kernel<MQI_K_RELEASE><<<grid, MQI_K_BLOCK, smem, st>>>(p);
+    pick_transport(variant, transport_is_simple(p))<<<grid, MQI_K_BLOCK, smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -1040,6 +1079,12 @@ launch_dev_hash(const uint32_t* k1, const uint32_t* k2, const unsigned long long
 cudaError_t
 launch_dev_sample(const Params& p, unsigned long long first, size_t n, VertexDev* out, uint32_t* spot, cudaStream_t st) {
     dev_sample_kernel<<<grid_for(n), 256, 0, st>>>(p.src, p.seed, first, n, out, spot);
+    return cudaGetLastError();
+}
+cudaError_t
+launch_dev_insert(const Params& p, int scorer, const uint32_t* k1, const uint32_t* k2, const double* v, size_t n,
+                  cudaStream_t st) {
+    dev_insert_kernel<<<grid_for(n), 256, 0, st>>>(p.sc[scorer], k1, k2, v, n, p.counters);
     return cudaGetLastError();
 }
 cudaError_t

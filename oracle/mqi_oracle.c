@@ -1179,6 +1179,13 @@ insert_scorer(mqo_scorer* s, uint32_t key1, uint32_t key2, double value) {
     }
 }
 
+/* insert_hashtable applied to a list of (key1, key2, value) hits, in order (KAT entry point) */
+void
+mqo_insert(mqo_scorer* s, const uint32_t* key1, const uint32_t* key2, const double* value, uint64_t n) {
+    uint64_t i;
+    for (i = 0; i < n; ++i) insert_scorer(s, key1[i], key2[i], value[i]);
+}
+
 /* ------------------------------------------------------------------------------------------- */
 /* transport_particles_patient mqi_transport.hpp:113-250                                         */
 /* ------------------------------------------------------------------------------------------- */

@@ -108,6 +108,7 @@ void mqo_sample_vertex(const mqo_beamlet* b, uint64_t seed, uint64_t history, mq
 /* ---- the transport path: transport_particles_patient mqi_transport.hpp:113-250 ----
  * histories [h0, h0+n) of the beam source (spot of history h found through cum_histories) or, if
  * vertices != NULL, explicit vertices[i] / spot_ids[i] for i in [0,n) with history id h0+i. */
+void mqo_insert(mqo_scorer* s, const uint32_t* key1, const uint32_t* key2, const double* value, uint64_t n);
 int mqo_transport(const mqo_grid* g, int variant, uint32_t quirks, const mqo_beamlet* beamlets,
                   const uint64_t* cum_histories, uint32_t n_beamlets, const mqo_vertex* vertices,
                   const uint32_t* spot_ids, int per_spot, uint64_t seed, uint64_t h0, uint64_t n,

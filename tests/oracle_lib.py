@@ -129,6 +129,32 @@ def make_beamlet(energy, mean, sigma, uniform=True, sigma_energy=0.0, corr=(0, 0
     return b
 
 
+def insert(kind, key1, key2, value, capacity=0, nvox=0):
+    """mc::insert_hashtable restatement applied to a hit list, sequentially.  Returns the occupied
+    slots (structured array, slot order) for Dij, or the dense float64 array."""
+    L = lib()
+    key1 = np.ascontiguousarray(key1, dtype=np.uint32)
+    key2 = np.ascontiguousarray(key2, dtype=np.uint32)
+    value = np.ascontiguousarray(value, dtype=np.float64)
+    sc = Scorer()
+    sc.kind = kind
+    if kind == SCORER_DIJ:
+        tab = np.zeros(capacity, dtype=[("key1", "<u4"), ("key2", "<u4"), ("value", "<f8")])
+        tab["key1"] = EMPTY
+        tab["key2"] = EMPTY
+        sc.table = tab.ctypes.data_as(C.POINTER(KeyValue))
+        sc.capacity = capacity
+    else:
+        tab = np.zeros(nvox, dtype=np.float64)
+        sc.dense = tab.ctypes.data_as(C.POINTER(C.c_double))
+    L.mqo_insert(C.byref(sc), key1.ctypes.data_as(C.POINTER(C.c_uint32)), key2.ctypes.data_as(C.POINTER(C.c_uint32)),
+                 value.ctypes.data_as(C.POINTER(C.c_double)), C.c_uint64(key1.size))
+    if kind == SCORER_DIJ:
+        occ = (tab["key1"] != EMPTY) & (tab["key2"] != EMPTY)
+        return tab[occ].copy(), np.nonzero(occ)[0]
+    return tab
+
+
 def transport(grid, variant, beamlets, histories_per_spot, seed, h0, n, kinds, quirks=0, per_spot=False,
               dij_capacity=0, vertices=None, spot_ids=None):
     """Run the oracle; returns (list of outputs per scorer, Stats).  Dense scorers -> float64[nvox];
