@@ -265,10 +265,12 @@ sample_vertex(const BeamletDev& b, unsigned long long seed, unsigned long long h
             box_muller(u2, u3, Uy, Vy);
         }
     }
-    const uint4 w = philox_block(1u, h0, h1, k0, k1);
-    float       za, zb;
-    box_muller(u32_to_uniform(w.x), u32_to_uniform(w.y), za, zb);
-    const float uc = u32_to_uniform(w.z);
+    float za = 0.f, zb = 0.f, uc = 0.5f;
+    if (b.energy_normal || b.sigma[2] != 0.f) {   // block 1 only feeds the energy and the z spread
+        const uint4 w = philox_block(1u, h0, h1, k0, k1);
+        box_muller(u32_to_uniform(w.x), u32_to_uniform(w.y), za, zb);
+        uc = u32_to_uniform(w.z);
+    }
     const float Uz = b.phsp_uniform ? 2.0f * uc - 1.0f : za;
     float       ph[6];
 #pragma unroll
@@ -484,10 +486,16 @@ transport_kernel(const __grid_constant__ Params P) {
                 const float n = rsqrtf(dx * dx + dy * dy + dz * dz);
                 dx *= n; dy *= n; dz *= n;
             }
-            // locate: index(p, dir) or entry intersect, :171-190
-            ix = index_axis_guess(sm.xe, nx, px, dx, P.g.inv_w[0]);
-            iy = index_axis_guess(sm.ye, ny, py, dy, P.g.inv_w[1]);
-            iz = index_axis_guess(sm.ze, nz, pz, dz, P.g.inv_w[2]);
+            // locate: index(p, dir) or entry intersect, :171-190.  A point farther than the geometry
+            // tolerance outside the bounding box has no valid index on that axis: skip the search.
+            if (px < sm.xe[0] - 2.f * kGeomTol || px > sm.xe[nx] + 2.f * kGeomTol || py < sm.ye[0] - 2.f * kGeomTol ||
+                py > sm.ye[ny] + 2.f * kGeomTol || pz < sm.ze[0] - 2.f * kGeomTol || pz > sm.ze[nz] + 2.f * kGeomTol) {
+                ix = iy = iz = -1;
+            } else {
+                ix = index_axis_guess(sm.xe, nx, px, dx, P.g.inv_w[0]);
+                iy = index_axis_guess(sm.ye, ny, py, dy, P.g.inv_w[1]);
+                iz = index_axis_guess(sm.ze, nz, pz, dz, P.g.inv_w[2]);
+            }
             alive = true;
             if (ix < 0 || iy < 0 || iz < 0 || ix >= nx || iy >= ny || iz >= nz) {
                 const float p[3] = { px, py, pz };
@@ -619,17 +627,10 @@ transport_kernel(const __grid_constant__ Params P) {
 
             const float mfp = -logf(u_mfp) / cs_sum;
             constexpr float step_limit = 1.0f;   // cms * rho_w / (rsp * rho): max_step, mqi_fippel_physics.hpp:20
-            float len;
-            bool  discrete = false;
-            if (d2b < mfp && d2b < step_limit) {
-                len = d2b;
-            } else if ((mfp < d2b || fabsf(mfp - d2b) < kGeomTol) &&
-                       (mfp < step_limit || fabsf(mfp - step_limit) < kGeomTol)) {
-                len      = mfp;
-                discrete = true;
-            } else {
-                len = step_limit;
-            }
+            const bool  to_boundary = d2b < mfp && d2b < step_limit;
+            const bool  discrete    = !to_boundary && (mfp < d2b || fabsf(mfp - d2b) < kGeomTol) &&
+                                      (mfp < step_limit || fabsf(mfp - step_limit) < kGeomTol);
+            const float len         = to_boundary ? d2b : (discrete ? mfp : step_limit);
             // ---------------- along step (CSDA + straggling + MCS), mqi_p_ionization.hpp:298-420
             {
                 const float liw = len * cms;
@@ -642,7 +643,15 @@ transport_kernel(const __grid_constant__ Params P) {
                     int         n = ia;
                     float4      B = A1;
                     if (n > kTableN - 2) B = sm.a1[n = kTableN - 2];
-                    while (n > 0 && r < B.x) B = sm.a1[--n];   // do { if (r >= r_steps[n]) break; } while (--n > 0)
+                    // do { if (r >= r_steps[n]) break; } while (--n > 0): at most one row per step above
+                    // ~70 MeV, so the first move is a select and only the rest a (divergent) loop
+                    {
+                        const float4 Bm  = sm.a1[max(n - 1, 0)];
+                        const bool   mv  = n > 0 && r < B.x;
+                        B                = mv ? Bm : B;
+                        n                = mv ? n - 1 : n;
+                    }
+                    while (n > 0 && r < B.x) B = sm.a1[--n];
                     const float dE_mean = ke - fmaf(r - B.x, B.z, 0.1f + n * 0.5f);
                     const float Te      = fminf(Te_max, 0.08511f);
                     const float var     = P.dedx_term0 * rho * (1.0f / kWaterRho) * liw * (Te / beta_sq * (1.0f - 0.5f * beta_sq));
@@ -666,14 +675,7 @@ transport_kernel(const __grid_constant__ Params P) {
             // ---------------- discrete interaction at the end of the step, :156-197
             if (discrete && ke1 > kTpCut) {
                 d1x = dx; d1y = dy; d1z = dz;   // vtx1.dir = vtx0.dir (B11)
-                RngBuf rb;
-                {
-                    uint32_t w2[4];
-                    philox4x32_10(blk, 0u, h0, h1, k0, k1, w2);
-                    rb.w = make_uint4(w2[0], w2[1], w2[2], w2[3]);
-                }
-                rb.blk = blk + 1; rb.pos = 1; rb.h0 = h0; rb.h1 = h1; rb.k0 = k0; rb.k1 = k1;
-                const float u = cs_sum * u32_to_uniform(rb.w.x);
+                const float u = cs_sum * u_phi;  // u_phi is unused on this step: selects the process
                 if (u < c0) {
                     // delta electron, p_ionization_tabulated::post_step mqi_p_ionization.hpp:425-477
                     const float Et1   = ke1 + kMp;
@@ -682,21 +684,19 @@ transport_kernel(const __grid_constant__ Params P) {
                     const float b1_sq = 1.0f - 1.0f / g1_sq;
                     const float Tmax1 = (2.0f * kMe * b1_sq * g1_sq) / (1.0f + 2.0f * g1 * MeMp + MeMp * MeMp);
                     const float inv_Tmax1 = 1.0f / Tmax1, inv_2Et_sq = 0.5f / (Et1 * Et1);
-                    // first attempt from the words already at hand, further attempts (about 1 in 10) buffered
-                    float n  = u32_to_uniform(rb.w.y);
-                    float Te = T_cut * Tmax1 / ((1.0f - n) * Tmax1 + n * T_cut);
-                    rb.pos   = 3;
-                    if (!(u32_to_uniform(rb.w.z) < 1.0f - b1_sq * Te * inv_Tmax1 + Te * Te * inv_2Et_sq)) {
-                        while (true) {
-                            n  = rb_uniform(rb);
-                            Te = T_cut * Tmax1 / ((1.0f - n) * Tmax1 + n * T_cut);
-                            if (rb_uniform(rb) < 1.0f - b1_sq * Te * inv_Tmax1 + Te * Te * inv_2Et_sq) break;
-                        }
+                    const uint32_t key2 = k0 ^ (k1 * 0x85EBCA6Bu) ^ (h1 * 0xC2B2AE35u);
+                    float Te;
+                    while (true) {   // accepted at the first attempt about 9 times in 10
+                        uint32_t wn, wa;
+                        philox2x32_10(blk, h0, key2, wn, wa);
+                        blk += 1;
+                        const float n = u32_to_uniform(wn);
+                        Te = T_cut * Tmax1 / ((1.0f - n) * Tmax1 + n * T_cut);
+                        if (u32_to_uniform(wa) < 1.0f - b1_sq * Te * inv_Tmax1 + Te * Te * inv_2Et_sq) break;
                     }
                     if (VARIANT == MQI_K_DEBUG) res.te_debug = Te;   // carried by a zero-energy daughter
                     else res.dE += Te;
                     ke1 -= Te;
-                    blk = rb.blk;
                 } else {
                     NucIO io;
                     io.px = px; io.py = py; io.pz = pz; io.dx = dx; io.dy = dy; io.dz = dz;
@@ -706,7 +706,7 @@ transport_kernel(const __grid_constant__ Params P) {
                     io.u = u - c0; io.e_cs = use1 ? ke : e2; io.rho = rho;
                     io.stopped = stopped ? 1 : 0;
                     io.sp = sp; io.n_sec = 0; io.n_ovf = 0;
-                    io.rb = rb;
+                    io.rb.blk = blk; io.rb.pos = 4; io.rb.h0 = h0; io.rb.h1 = h1; io.rb.k0 = k0; io.rb.k1 = k1;
                     nuclear_event<VARIANT>(P, stack, io);
                     d1x = io.d1x; d1y = io.d1y; d1z = io.d1z;
                     ke1 = io.ke1; res.dE = io.dE; res.local_dE = io.local_dE;

@@ -581,6 +581,21 @@ mqo_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t o
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+/* Philox2x32-10 (Random123): the short generator of the delta-electron rejection loop */
+void
+mqo_philox2x32_10(const uint32_t ctr_in[2], uint32_t key, uint32_t out[2]) {
+    uint32_t c0 = ctr_in[0], c1 = ctr_in[1];
+    int      i;
+    for (i = 0; i < 10; ++i) {
+        uint64_t p  = (uint64_t) 0xD256D193u * c0;
+        uint32_t n0 = (uint32_t) (p >> 32) ^ key ^ c1;
+        c1          = (uint32_t) p;
+        c0          = n0;
+        key += 0x9E3779B9u;
+    }
+    out[0] = c0; out[1] = c1;
+}
+
 float
 mqo_u32_to_uniform(uint32_t x) { /* open interval (0,1): ((x >> 8) + 0.5) * 2^-24 */
     return ((float) (x >> 8) + 0.5f) * (1.0f / 16777216.0f);
@@ -614,6 +629,19 @@ rng_u32(rng_t* r) {
     return r->buf[r->pos++];
 }
 static inline float rng_uniform(rng_t* r) { return mqo_u32_to_uniform(rng_u32(r)); }
+/* one (n, accept) pair of the delta-electron sampler: Philox2x32-10, counter = (block, history_lo),
+ * key = seed_lo ^ seed_hi * 0x85EBCA6B ^ history_hi * 0xC2B2AE35; consumes one block number */
+static inline void
+rng_pair2(rng_t* r, float* a, float* b) {
+    uint32_t ctr[2], out[2];
+    ctr[0] = r->ctr[0];
+    ctr[1] = r->ctr[2];
+    mqo_philox2x32_10(ctr, r->key[0] ^ (r->key[1] * 0x85EBCA6Bu) ^ (r->ctr[3] * 0xC2B2AE35u), out);
+    r->ctr[0] += 1;
+    r->pos = 4;
+    *a = mqo_u32_to_uniform(out[0]);
+    *b = mqo_u32_to_uniform(out[1]);
+}
 static inline void
 rng_normal_pair(rng_t* r, float* z1, float* z2) { /* Box-Muller on two uniforms */
     float u1  = rng_uniform(r);
@@ -806,13 +834,13 @@ last_step(ctx_t* c, track_t* trk, float rho_mass) {
 static void
 delta_post_step(ctx_t* c, track_t* trk) {
     relq  rel = rel_make(trk->vtx1.ke);
-    float Te, n;
+    float Te, n, acc;
     if (c->st) c->st->delta_events++;
     while (1) {
-        n  = rng_uniform(c->rng);
+        rng_pair2(c->rng, &n, &acc);
         Te = c->T_cut * rel.Te_max;
         Te /= ((1.0 - n) * rel.Te_max + n * c->T_cut);
-        if (rng_uniform(c->rng) < 1.0 - rel.beta_sq * Te / rel.Te_max + Te * Te / (2.0 * rel.Et_sq)) break;
+        if (acc < 1.0 - rel.beta_sq * Te / rel.Te_max + Te * Te / (2.0 * rel.Et_sq)) break;
     }
     if (c->variant == MQO_VARIANT_DEBUG) {
         track_t d  = *trk;
@@ -1066,7 +1094,9 @@ stepping(ctx_t* c, track_t* trk, float rho_mass, float distance_to_boundary) {
     cs_sum  = (cs1_sum >= cs2_sum) ? cs1_sum : cs2_sum;
     cs      = (cs1_sum >= cs2_sum) ? cs1 : cs2;
 
-    /* RNG protocol: one aligned Philox block per physics step = {u_mfp, u_a, u_b, u_phi} */
+    /* RNG protocol: one aligned Philox4x32 block per physics step = {u_mfp, u_a, u_b, u_phi}; a
+     * discrete interaction is selected with u_phi; delta-electron sampling draws Philox2x32 pairs;
+     * nuclear interactions draw from further Philox4x32 blocks */
     rng_begin_step(c->rng);
     prob = rng_uniform(c->rng);
     rng_normal_pair(c->rng, &z1, &z2);
@@ -1082,7 +1112,9 @@ stepping(ctx_t* c, track_t* trk, float rho_mass, float distance_to_boundary) {
         float u;
         along_step(c, trk, mfp, rho_mass, z1, z2, u_phi);
         if (trk->vtx1.ke <= k_Tp_cut) { return; }
-        u             = cs_sum * rng_uniform(c->rng);
+        /* the step's multiple-scattering deflection is discarded below (B11), so its azimuth deviate
+         * u_phi is otherwise unused on this step and selects the process */
+        u             = cs_sum * u_phi;
         trk->vtx1.dir = trk->vtx0.dir;
         if (u < cs[0]) {
             delta_post_step(c, trk);

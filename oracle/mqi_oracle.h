@@ -101,6 +101,7 @@ void     mqo_physics_probe(float ek, float out[9]);
 /* ---- RNG protocol (shared with the CUDA path) ---- */
 void  mqo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 float mqo_u32_to_uniform(uint32_t x);
+void  mqo_philox2x32_10(const uint32_t ctr[2], uint32_t key, uint32_t out[2]);
 
 /* ---- source sampling: beamlet::operator() mqi_beamlet.hpp:81-90 ---- */
 void mqo_sample_vertex(const mqo_beamlet* b, uint64_t seed, uint64_t history, mqo_vertex* out);

@@ -183,3 +183,14 @@ def test_philox_known_answers():
     L.mqo_philox4x32_10((C.c_uint32 * 4)(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344),
                         (C.c_uint32 * 2)(0xa4093822, 0x299f31d0), out)
     assert list(out) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox2x32_known_answers():
+    # Random123 kat_vectors for Philox2x32-10 (the delta-electron sampler's generator)
+    L = O.lib()
+    out = (C.c_uint32 * 2)()
+    for ctr, key, exp in (((0, 0), 0, (0xff1dae59, 0x6cd10df2)),
+                          ((0xffffffff, 0xffffffff), 0xffffffff, (0x2c3f628b, 0xab4fd7ad)),
+                          ((0x243f6a88, 0x85a308d3), 0x13198a2e, (0xdd7ce038, 0xf62a4c12))):
+        L.mqo_philox2x32_10((C.c_uint32 * 2)(*ctr), C.c_uint32(key), out)
+        assert (out[0], out[1]) == exp
