@@ -89,7 +89,7 @@ make_mat_entry(float rho, int variant) {
         m.mode = 0;
         m.a    = d < 0.0012 ? 0.0f : lerp_ref(d, 0.0012f, 0.26f, 0.8815f, 0.9925f);
     } else {
-        m.Pd = (double) powf(d, -0.7f) - 1.0;
+        m.P = (float) ((double) powf(d, -0.7f) - 1.0);
         if (d >= 0.9) {
             m.mode = 1;
         } else {
