@@ -180,6 +180,17 @@ MQI_API int mqi_stat_partial(mqi_handle* h, int scorer_sum, int scorer_sumsq, ui
 /* calculate_average (mqi_variables.hpp:50-66): scale a dense scorer in place */
 MQI_API int mqi_scale_scorer(mqi_handle* h, int scorer, double factor);
 
+/* ---- multi-GPU inside one process (subsystem 5) ----
+ * Sum dense scorer `scorer` of n handles (one per GPU, same grid) into the handle at index `root`
+ * with ONE ncclReduce over NVLink (ncclCommInitAll communicator, created on first use and cached
+ * for the handle set; NCCL is loaded with dlopen so the library also loads where NCCL is absent).
+ * The reference has no multi-GPU mode (one cudaSetDevice per process, mqi_phantom_env.hpp:45).
+ * With all_ranks != 0 an all-reduce leaves the sum on every handle (stopping-criterion passes).
+ * One process per GPU deployments reduce the device pointer of mqi_get_scorer_device_ptr with their
+ * own communicator instead (bench.py does, through torch.distributed). */
+MQI_API int mqi_reduce_dense(mqi_handle* const* handles, int n, int scorer, int root);
+MQI_API int mqi_allreduce_dense(mqi_handle* const* handles, int n, int scorer);
+
 /* ---- deterministic device pieces, exposed for bit-exact parity tests ---- */
 /* patient_material_t::hu_to_density on the device (materials/mqi_patient_materials.hpp:514-542) */
 MQI_API int mqi_dev_hu_to_density(mqi_handle* h, const int16_t* hu, uint64_t n, float density_scale, float* rho_out);

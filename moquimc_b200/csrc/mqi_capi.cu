@@ -8,6 +8,8 @@
 #include "mqi_device.cuh"
 #include "mqi_kernels.h"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -791,6 +793,115 @@ mqi_scale_scorer(mqi_handle* h, int scorer, double factor) {
     CU(launch_scale(s.d_dense, nvox(h), factor, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return MQI_OK;
+}
+
+// ---- multi-GPU reduction over NCCL (loaded at run time) ----------------------------------------
+namespace
+{
+typedef struct ncclComm* ncclComm_t;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+std::vector<int>        g_comm_devices;
+std::vector<ncclComm_t> g_comms;
+const int kNcclFloat64 = 8, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values of nccl.h (2.x)
+
+int
+load_nccl() {
+    if (g_nccl.ok) return MQI_OK;
+    const char* names[] = { "libnccl.so.2", "libnccl.so" };
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return fail(MQI_ESTATE, "NCCL is not available (dlopen libnccl.so.2 failed)");
+#define MQI_SYM(field, name)                                                                           \
+    *reinterpret_cast<void**>(&g_nccl.field) = dlsym(g_nccl.lib, name);                                \
+    if (!g_nccl.field) return fail(MQI_ESTATE, std::string("NCCL symbol missing: ") + name)
+    MQI_SYM(CommInitAll, "ncclCommInitAll");
+    MQI_SYM(CommDestroy, "ncclCommDestroy");
+    MQI_SYM(Reduce, "ncclReduce");
+    MQI_SYM(AllReduce, "ncclAllReduce");
+    MQI_SYM(GroupStart, "ncclGroupStart");
+    MQI_SYM(GroupEnd, "ncclGroupEnd");
+    MQI_SYM(GetErrorString, "ncclGetErrorString");
+#undef MQI_SYM
+    g_nccl.ok = true;
+    return MQI_OK;
+}
+
+#define NC(call)                                                                                       \
+    do {                                                                                               \
+        int r__ = (call);                                                                              \
+        if (r__ != 0) return fail(MQI_ECUDA, std::string(#call) + ": " + g_nccl.GetErrorString(r__));   \
+    } while (0)
+
+int
+reduce_impl(mqi_handle* const* handles, int n, int scorer, int root, bool all) {
+    if (!handles || n < 1) return fail(MQI_EINVAL, "no handles");
+    if (root < 0 || root >= n) return fail(MQI_EINVAL, "root out of range");
+    std::vector<int> devs(n);
+    size_t           count = 0;
+    for (int i = 0; i < n; ++i) {
+        mqi_handle* h = handles[i];
+        if (!h) return fail(MQI_EINVAL, "null handle");
+        if (scorer < 0 || scorer >= (int) h->scorers.size()) return fail(MQI_EINVAL, "bad scorer index");
+        if (h->scorers[scorer].kind == MQI_SCORER_DIJ) return fail(MQI_EINVAL, "Dij tables are sharded by spot, not reduced");
+        if (!h->has_grid) return fail(MQI_ESTATE, "no grid set");
+        if (i == 0) count = nvox(h);
+        else if (nvox(h) != count) return fail(MQI_EINVAL, "handles have different grids");
+        devs[i] = h->device;
+        for (int j = 0; j < i; ++j)
+            if (devs[j] == devs[i]) return fail(MQI_EINVAL, "two handles on the same device");
+        int rc = activate(h);
+        if (rc) return rc;
+        rc = ensure_scorer_buffers(h);
+        if (rc) return rc;
+    }
+    if (n == 1) return MQI_OK;
+    int rc = load_nccl();
+    if (rc) return rc;
+    if (devs != g_comm_devices) {
+        for (auto c : g_comms) g_nccl.CommDestroy(c);
+        g_comms.assign(n, nullptr);
+        NC(g_nccl.CommInitAll(g_comms.data(), n, devs.data()));
+        g_comm_devices = devs;
+    }
+    NC(g_nccl.GroupStart());
+    for (int i = 0; i < n; ++i) {
+        mqi_handle* h = handles[i];
+        CU(cudaSetDevice(h->device));
+        double* buf = h->scorers[scorer].d_dense;
+        if (all) NC(g_nccl.AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, g_comms[i], h->stream));
+        else NC(g_nccl.Reduce(buf, buf, count, kNcclFloat64, kNcclSum, root, g_comms[i], h->stream));
+    }
+    NC(g_nccl.GroupEnd());
+    for (int i = 0; i < n; ++i) {
+        CU(cudaSetDevice(handles[i]->device));
+        CU(cudaStreamSynchronize(handles[i]->stream));
+    }
+    return MQI_OK;
+}
+}   // namespace
+
+extern "C" {
+int
+mqi_reduce_dense(mqi_handle* const* handles, int n, int scorer, int root) {
+    return reduce_impl(handles, n, scorer, root, false);
+}
+int
+mqi_allreduce_dense(mqi_handle* const* handles, int n, int scorer) {
+    return reduce_impl(handles, n, scorer, 0, true);
+}
 }
 
 // ---- deterministic device pieces ---------------------------------------------------------------
