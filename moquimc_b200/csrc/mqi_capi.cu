@@ -109,8 +109,9 @@ make_mat_entry(float rho, int variant) {
         else f = 1.19 + 0.44 * std::log((double) d - 0.44);
         x0 = (0.001f * 360.863f) / (d * 0.001 * f);
     }
-    m.x0     = x0;
-    m.inv_x0 = 1.0f / x0;
+    m.x0       = x0;
+    m.inv_x0   = 1.0f / x0;
+    m.inv_rsp0 = (m.mode == 0 && m.a > 0.f) ? 1.0f / m.a : 0.f;
     return m;
 }
 
@@ -609,6 +610,10 @@ mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t cou
     Params p;
     fill_params(h, p);
     p.seed     = seed;
+    for (int i = 0; i < 10; ++i) {   // Philox4x32 key schedule
+        p.rk[2 * i]     = (uint32_t) seed + (uint32_t) i * 0x9E3779B9u;
+        p.rk[2 * i + 1] = (uint32_t) (seed >> 32) + (uint32_t) i * 0xBB67AE85u;
+    }
     p.first    = first_history;
     p.count    = count;
     p.per_spot = per_spot;

@@ -25,6 +25,10 @@
 #define MQI_K_MIN_BLOCKS 4   /* 64 registers/thread: measured best of 2/3/4 on B200 (profiles/) */
 #endif
 
+#ifndef MQI_K_SYNC
+#define MQI_K_SYNC 0   /* per-iteration CTA (1) / sub-partition (2) barrier in the transport loop: see profiles/ */
+#endif
+
 namespace mqib
 {
 struct Params;

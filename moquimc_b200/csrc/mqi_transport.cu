@@ -387,6 +387,151 @@ score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// re-arming a lane (out of line: executed once per track, keeps the voxel-step loop compact for the
+// instruction cache): pop a secondary or fetch + sample the next primary, world -> node frame,
+// locate the start cell (index(p, dir) or entry intersect), mqi_transport.hpp:146-190
+// ---------------------------------------------------------------------------------------------
+struct LaneIO {
+    float    px, py, pz, dx, dy, dz, ke, ke1_off, dE_pre;
+    int      ix, iy, iz;
+    uint32_t spot_ind, h0, h1, blk;
+    int      sp;
+    unsigned n_done;
+};
+
+__device__ __forceinline__ Smem
+smem_view(unsigned char* raw, int nx, int ny) {
+    Smem sm;
+    float4* a0 = reinterpret_cast<float4*>(raw);
+    float4* a1 = a0 + kTableN;
+    float2* bs = reinterpret_cast<float2*>(a1 + kTableN);
+    float*  e  = reinterpret_cast<float*>(bs + kTableN);
+    sm.a0 = a0; sm.a1 = a1; sm.bs = bs;
+    sm.xe = e; sm.ye = e + nx + 1; sm.ze = e + nx + 1 + ny + 1;
+    return sm;
+}
+
+enum { REARM_EXIT = 0, REARM_ALIVE = 1, REARM_MISSED = 2 };
+
+__device__ __noinline__ int
+rearm_lane(const Params& P, Secondary* stack, LaneIO& L) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int  nx = P.g.nx, ny = P.g.ny, nz = P.g.nz;
+    const Smem sm = smem_view(smem_raw, nx, ny);
+    float px, py, pz, dx, dy, dz, ke, ke1_off, dE_pre;
+    if (L.sp > 0) {
+        const Secondary& s = stack[--L.sp];
+        px = s.px; py = s.py; pz = s.pz; dx = s.dx; dy = s.dy; dz = s.dz;
+        ke = s.ke0; ke1_off = s.ke1_off; dE_pre = s.dE_pre;
+    } else {
+        const unsigned long long i = atomicAdd(P.counters + C_NEXT, 1ull);
+        if (i >= P.count) return REARM_EXIT;
+        const unsigned long long h = P.first + i;
+        L.h0  = (uint32_t) h;
+        L.h1  = (uint32_t) (h >> 32);
+        L.blk = 0;
+        uint32_t spot = 0;
+        VertexDev v;
+        if (P.src.vertices) {
+            v    = P.src.vertices[i];
+            spot = P.src.spot_ids ? P.src.spot_ids[i] : 0u;
+        } else {
+            // beamsource::operator()(h): first spot whose cumulative count exceeds h
+            uint32_t lo = 0, hi = P.src.n_spots;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (P.src.cum[mid] > h) hi = mid; else lo = mid + 1;
+            }
+            spot = min(lo, P.src.n_spots - 1);
+            sample_vertex(P.src.beamlets[spot], P.seed, h, v);
+            L.blk = 2;
+        }
+        px = v.pos[0]; py = v.pos[1]; pz = v.pos[2];
+        dx = v.dir[0]; dy = v.dir[1]; dz = v.dir[2];
+        ke = v.ke;
+        L.spot_ind = P.per_spot ? spot : kEmptyKey32;
+        ke1_off    = 0.f;
+        dE_pre     = 0.f;
+        ++L.n_done;
+    }
+    // world -> node frame, mqi_transport.hpp:165-170
+    if (!P.g.identity) {
+        const float* R  = P.g.rot_fwd;   // inverse = transpose
+        const float  qx = px - P.g.trans[0], qy = py - P.g.trans[1], qz = pz - P.g.trans[2];
+        px = R[0] * qx + R[3] * qy + R[6] * qz;
+        py = R[1] * qx + R[4] * qy + R[7] * qz;
+        pz = R[2] * qx + R[5] * qy + R[8] * qz;
+        const float ex = dx, ey = dy, ez = dz;
+        dx = R[0] * ex + R[3] * ey + R[6] * ez;
+        dy = R[1] * ex + R[4] * ey + R[7] * ez;
+        dz = R[2] * ex + R[5] * ey + R[8] * ez;
+    }
+    {
+        const float n = rsqrtf(dx * dx + dy * dy + dz * dz);
+        dx *= n; dy *= n; dz *= n;
+    }
+    // locate: index(p, dir) or entry intersect, :171-190.  A point farther than the geometry
+    // tolerance outside the bounding box has no valid index on that axis: skip the search.
+    int ix, iy, iz;
+    if (px < sm.xe[0] - 2.f * kGeomTol || px > sm.xe[nx] + 2.f * kGeomTol || py < sm.ye[0] - 2.f * kGeomTol ||
+        py > sm.ye[ny] + 2.f * kGeomTol || pz < sm.ze[0] - 2.f * kGeomTol || pz > sm.ze[nz] + 2.f * kGeomTol) {
+        ix = iy = iz = -1;
+    } else {
+        ix = index_axis_guess(sm.xe, nx, px, dx, P.g.inv_w[0]);
+        iy = index_axis_guess(sm.ye, ny, py, dy, P.g.inv_w[1]);
+        iz = index_axis_guess(sm.ze, nz, pz, dz, P.g.inv_w[2]);
+    }
+    bool alive = true;
+    if (ix < 0 || iy < 0 || iz < 0 || ix >= nx || iy >= ny || iz >= nz) {
+        const float p[3] = { px, py, pz };
+        float       d[3] = { dx, dy, dz };
+        int         c[3];
+        const float dist = grid_entry(sm.xe, sm.ye, sm.ze, nx, ny, nz, P.g.inv_w, p, d, c);
+        if (dist < 0.f) {
+            alive = false;
+        } else {
+            // update_post_vertex_position uses the (possibly zeroed) direction, move() then
+            // restores the un-zeroed copy held in vtx1.dir; vtx1.ke becomes vtx0.ke.  The cell
+            // of the moved point is the one intersect() already looked up (same point, same d
+            // up to the zeroed components, which only matter exactly on an edge).
+            px = __fadd_rn(px, __fmul_rn(d[0], dist));
+            py = __fadd_rn(py, __fmul_rn(d[1], dist));
+            pz = __fadd_rn(pz, __fmul_rn(d[2], dist));
+            ke += ke1_off;
+            ke1_off = 0.f;
+            dE_pre  = 0.f;
+            if (d[0] == dx && d[1] == dy && d[2] == dz) {
+                ix = c[0]; iy = c[1]; iz = c[2];
+            } else {
+                ix = index_axis_guess(sm.xe, nx, px, dx, P.g.inv_w[0]);
+                iy = index_axis_guess(sm.ye, ny, py, dy, P.g.inv_w[1]);
+                iz = index_axis_guess(sm.ze, nz, pz, dz, P.g.inv_w[2]);
+            }
+            if (ix < 0 || iy < 0 || iz < 0 || ix >= nx || iy >= ny || iz >= nz) alive = false;
+        }
+    }
+    L.px = px; L.py = py; L.pz = pz; L.dx = dx; L.dy = dy; L.dz = dz;
+    L.ke = ke; L.ke1_off = ke1_off; L.dE_pre = dE_pre;
+    L.ix = ix; L.iy = iy; L.iz = iz;
+    return alive ? REARM_ALIVE : REARM_MISSED;
+}
+
+// further tries of the delta-electron energy rejection loop (about one event in ten needs them):
+// (n, accept) pairs from Philox2x32-10, counter = (block, history_lo), one block number per pair
+__device__ __noinline__ float
+delta_retry(uint32_t& blk, uint32_t h0, uint32_t key2, float T_cut, float Tmax1, float b1_sq, float inv_2Et_sq) {
+    const float inv_Tmax1 = 1.0f / Tmax1;
+    while (true) {
+        uint32_t wn, wa;
+        philox2x32_10(blk, h0, key2, wn, wa);
+        blk += 1;
+        const float n  = u32_to_uniform(wn);
+        const float Te = T_cut * Tmax1 / ((1.0f - n) * Tmax1 + n * T_cut);
+        if (u32_to_uniform(wa) < 1.0f - b1_sq * Te * inv_Tmax1 + Te * Te * inv_2Et_sq) return Te;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the transport kernel
 // ---------------------------------------------------------------------------------------------
 // SIMPLE: exactly one dense Dose scorer (phantom_env, and the tps "Dose" case): the scorer loop and
@@ -395,25 +540,21 @@ template<int VARIANT, bool SIMPLE>
 __global__ void __launch_bounds__(MQI_K_BLOCK, MQI_K_MIN_BLOCKS)
 transport_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* s_a0    = reinterpret_cast<float4*>(smem_raw);
-    float4* s_a1    = s_a0 + kTableN;
-    float2* s_bs    = reinterpret_cast<float2*>(s_a1 + kTableN);
-    float*  s_edges = reinterpret_cast<float*>(s_bs + kTableN);
     const int nx = P.g.nx, ny = P.g.ny, nz = P.g.nz;
-    for (int i = threadIdx.x; i < kTableN; i += blockDim.x) {
-        s_a0[i] = P.tab_a0[i];
-        s_a1[i] = P.tab_a1[i];
-        s_bs[i] = P.tab_bs[i];
+    {
+        float4* s_a0    = reinterpret_cast<float4*>(smem_raw);
+        float4* s_a1    = s_a0 + kTableN;
+        float2* s_bs    = reinterpret_cast<float2*>(s_a1 + kTableN);
+        float*  s_edges = reinterpret_cast<float*>(s_bs + kTableN);
+        for (int i = threadIdx.x; i < kTableN; i += blockDim.x) {
+            s_a0[i] = P.tab_a0[i];
+            s_a1[i] = P.tab_a1[i];
+            s_bs[i] = P.tab_bs[i];
+        }
+        for (int i = threadIdx.x; i < nx + ny + nz + 3; i += blockDim.x) s_edges[i] = P.g.edges[i];
     }
-    for (int i = threadIdx.x; i < nx + ny + nz + 3; i += blockDim.x) s_edges[i] = P.g.edges[i];
     __syncthreads();
-    Smem sm;
-    sm.a0 = s_a0;
-    sm.a1 = s_a1;
-    sm.bs = s_bs;
-    sm.xe = s_edges;
-    sm.ye = s_edges + nx + 1;
-    sm.ze = s_edges + nx + 1 + ny + 1;
+    const Smem sm = smem_view(smem_raw, nx, ny);
 
     constexpr float T_cut = (VARIANT == MQI_K_DEBUG) ? 0.08511f : 0.0815f;   // mqi_interaction.hpp:24-28
     constexpr int   DEPTH = StackCfg<VARIANT>::depth;
@@ -429,107 +570,46 @@ transport_kernel(const __grid_constant__ Params P) {
     const uint32_t k0 = (uint32_t) P.seed, k1 = (uint32_t) (P.seed >> 32);
     unsigned n_steps = 0, n_done = 0, n_sec = 0, n_ovf = 0;
 
+#if MQI_K_SYNC
+    bool done = false;   // this lane found the history counter exhausted
+#endif
     while (true) {
+#if MQI_K_SYNC == 1
+        // keep the warps of the CTA on the same stretch of the loop body (instruction-cache locality)
+        if (__syncthreads_and(done)) break;
+        if (done) continue;
+#elif MQI_K_SYNC == 2
+        // same, but only among the warps that share an SM sub-partition (warp id mod 4)
+        {
+            unsigned all_done;
+            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbarrier.red.and.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(all_done) : "r"((unsigned) done), "r"(1u + ((threadIdx.x >> 5) & 3u)), "r"((unsigned) (MQI_K_BLOCK / 4)) : "memory");
+            if (all_done) break;
+        }
+        if (done) continue;
+#endif
         // ------------------------------------------------------------------ re-arm the lane
         if (!alive) {
-            if (sp > 0) {
-                const Secondary& s = stack[--sp];
-                px = s.px; py = s.py; pz = s.pz; dx = s.dx; dy = s.dy; dz = s.dz;
-                ke = s.ke0; ke1_off = s.ke1_off; dE_pre = s.dE_pre;
-            } else {
-                const unsigned long long i = atomicAdd(P.counters + C_NEXT, 1ull);
-                if (i >= P.count) break;
-                const unsigned long long h = P.first + i;
-                h0  = (uint32_t) h;
-                h1  = (uint32_t) (h >> 32);
-                blk = 0;
-                uint32_t spot = 0;
-                if (P.src.vertices) {
-                    const VertexDev v = P.src.vertices[i];
-                    px = v.pos[0]; py = v.pos[1]; pz = v.pos[2];
-                    dx = v.dir[0]; dy = v.dir[1]; dz = v.dir[2];
-                    ke = v.ke;
-                    spot = P.src.spot_ids ? P.src.spot_ids[i] : 0u;
-                } else {
-                    // beamsource::operator()(h): first spot whose cumulative count exceeds h
-                    uint32_t lo = 0, hi = P.src.n_spots;
-                    while (lo < hi) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if (P.src.cum[mid] > h) hi = mid; else lo = mid + 1;
-                    }
-                    spot = min(lo, P.src.n_spots - 1);
-                    VertexDev v;
-                    sample_vertex(P.src.beamlets[spot], P.seed, h, v);
-                    blk = 2;
-                    px = v.pos[0]; py = v.pos[1]; pz = v.pos[2];
-                    dx = v.dir[0]; dy = v.dir[1]; dz = v.dir[2];
-                    ke = v.ke;
-                }
-                spot_ind = P.per_spot ? spot : kEmptyKey32;
-                ke1_off  = 0.f;
-                dE_pre   = 0.f;
-                ++n_done;
-            }
-            // world -> node frame, mqi_transport.hpp:165-170
-            if (!P.g.identity) {
-                const float* R  = P.g.rot_fwd;   // inverse = transpose
-                const float  qx = px - P.g.trans[0], qy = py - P.g.trans[1], qz = pz - P.g.trans[2];
-                px = R[0] * qx + R[3] * qy + R[6] * qz;
-                py = R[1] * qx + R[4] * qy + R[7] * qz;
-                pz = R[2] * qx + R[5] * qy + R[8] * qz;
-                const float ex = dx, ey = dy, ez = dz;
-                dx = R[0] * ex + R[3] * ey + R[6] * ez;
-                dy = R[1] * ex + R[4] * ey + R[7] * ez;
-                dz = R[2] * ex + R[5] * ey + R[8] * ez;
-            }
-            {
-                const float n = rsqrtf(dx * dx + dy * dy + dz * dz);
-                dx *= n; dy *= n; dz *= n;
-            }
-            // locate: index(p, dir) or entry intersect, :171-190.  A point farther than the geometry
-            // tolerance outside the bounding box has no valid index on that axis: skip the search.
-            if (px < sm.xe[0] - 2.f * kGeomTol || px > sm.xe[nx] + 2.f * kGeomTol || py < sm.ye[0] - 2.f * kGeomTol ||
-                py > sm.ye[ny] + 2.f * kGeomTol || pz < sm.ze[0] - 2.f * kGeomTol || pz > sm.ze[nz] + 2.f * kGeomTol) {
-                ix = iy = iz = -1;
-            } else {
-                ix = index_axis_guess(sm.xe, nx, px, dx, P.g.inv_w[0]);
-                iy = index_axis_guess(sm.ye, ny, py, dy, P.g.inv_w[1]);
-                iz = index_axis_guess(sm.ze, nz, pz, dz, P.g.inv_w[2]);
-            }
-            alive = true;
-            if (ix < 0 || iy < 0 || iz < 0 || ix >= nx || iy >= ny || iz >= nz) {
-                const float p[3] = { px, py, pz };
-                float       d[3] = { dx, dy, dz };
-                int         c[3];
-                const float dist = grid_entry(sm.xe, sm.ye, sm.ze, nx, ny, nz, P.g.inv_w, p, d, c);
-                if (dist < 0.f) {
-                    alive = false;
-                } else {
-                    // update_post_vertex_position uses the (possibly zeroed) direction, move() then
-                    // restores the un-zeroed copy held in vtx1.dir; vtx1.ke becomes vtx0.ke.  The cell
-                    // of the moved point is the one intersect() already looked up (same point, same d
-                    // up to the zeroed components, which only matter exactly on an edge).
-                    px = __fadd_rn(px, __fmul_rn(d[0], dist));
-                    py = __fadd_rn(py, __fmul_rn(d[1], dist));
-                    pz = __fadd_rn(pz, __fmul_rn(d[2], dist));
-                    ke += ke1_off;
-                    ke1_off = 0.f;
-                    dE_pre  = 0.f;
-                    if (d[0] == dx && d[1] == dy && d[2] == dz) {
-                        ix = c[0]; iy = c[1]; iz = c[2];
-                    } else {
-                        ix = index_axis_guess(sm.xe, nx, px, dx, P.g.inv_w[0]);
-                        iy = index_axis_guess(sm.ye, ny, py, dy, P.g.inv_w[1]);
-                        iz = index_axis_guess(sm.ze, nz, pz, dz, P.g.inv_w[2]);
-                    }
-                    if (ix < 0 || iy < 0 || iz < 0 || ix >= nx || iy >= ny || iz >= nz) alive = false;
-                }
-            }
+            LaneIO L;
+            L.sp = sp; L.h0 = h0; L.h1 = h1; L.blk = blk; L.spot_ind = spot_ind; L.n_done = 0;
+            const int rc = rearm_lane(P, stack, L);
+            sp = L.sp;
+            n_done += L.n_done;
+#if MQI_K_SYNC
+            if (rc == REARM_EXIT) { done = true; continue; }
+#else
+            if (rc == REARM_EXIT) break;
+#endif
+            h0 = L.h0; h1 = L.h1; blk = L.blk; spot_ind = L.spot_ind;
+            px = L.px; py = L.py; pz = L.pz; dx = L.dx; dy = L.dy; dz = L.dz;
+            ke = L.ke; ke1_off = L.ke1_off; dE_pre = L.dE_pre;
+            ix = L.ix; iy = L.iy; iz = L.iz;
+            alive = rc == REARM_ALIVE;
             if (!alive) continue;
         }
 
         // ------------------------------------------------------------------ one voxel step
-        if (P.count_steps) ++n_steps;
+        ++n_steps;
         const float ex0 = sm.xe[ix], ex1 = sm.xe[ix + 1];
         const float ey0 = sm.ye[iy], ey1 = sm.ye[iy + 1];
         const float ez0 = sm.ze[iz], ez1 = sm.ze[iz + 1];
@@ -540,192 +620,192 @@ transport_kernel(const __grid_constant__ Params P) {
         const float ty = cell_tmax_axis(ey0, ey1, ny, py, dy, iy);
         const float tz = cell_tmax_axis(ez0, ez1, nz, pz, dz, iz);
         const float d2b = min3_ref(tx, ty, tz);
-        if (!(d2b > 0.f)) {   // intersect() failed: the reference poisons the track and breaks
+        const float rho = M.rho;
+        // intersect() failed (the reference poisons the track and breaks), or a closed aperture voxel
+        // (rho > 99.9: mqi_fippel_physics.hpp:81-85): the track ends without scoring
+        if (!(d2b > 0.f) || rho > 99.9f) {
             alive = false;
             continue;
         }
-        const float rho = M.rho;
 
         bool  stopped = false;
         float p1x, p1y, p1z;              // vtx1.pos
         float ke1 = ke + ke1_off;         // vtx1.ke
-        StepResult res;
-        res.dE = dE_pre; res.local_dE = 0.f; res.te_debug = 0.f; res.len = 0.f;
-        float rsp0 = 1.f;
 
         if (rho < 1.0e-7f) {
             // vacuum: move to the boundary, nothing to score (mqi_fippel_physics.hpp:77-80)
             p1x = px + dx * d2b; p1y = py + dy * d2b; p1z = pz + dz * d2b;
-        } else if (rho > 99.9f) {
-            stopped = true;   // closed aperture (:81-85)
-            p1x = px; p1y = py; p1z = pz;
-        } else if (ke <= kTpCut) {
-            // below the tracking cut: dump the energy, :86-94 + last_step mqi_p_ionization.hpp:482-490
-            if (ke < 0.f) ke = 0.f;
-            rsp0 = rsp_eval(M, ke);
-            res.dE += ke;
-            ke1 -= ke;
-            float step_len = 0.f;
-            if (res.dE > 0.f && ke > 0.f) {
-                const float liw = res.dE / stopping_power(sm, ke);
-                step_len        = liw * kWaterRho / (rsp0 * rho);
-            }
-            p1x = px + dx * step_len; p1y = py + dy * step_len; p1z = pz + dz * step_len;
-            res.len = step_len;
-            stopped = true;
         } else {
-            // ---------------- class-II condensed-history step, fippel_physics::stepping :95-216
-            // the per-step Philox block first: it only depends on the counter
-            uint32_t w[4];
-            philox4x32_10(blk, 0u, h0, h1, k0, k1, w);
-            blk += 1;
-            const float u_mfp = u32_to_uniform(w[0]);
-            const float u_phi = u32_to_uniform(w[3]);
-            float z_loss, z_theta;
-            box_muller(u32_to_uniform(w[1]), u32_to_uniform(w[2]), z_loss, z_theta);
-
-            // relativistic quantities of vtx0.ke, base/mqi_relativistic_quantities.hpp:27-44
-            const float Et       = ke + kMp;
-            const float gamma    = Et * (1.0f / kMp);
-            const float gamma_sq = gamma * gamma;
-            const float beta_sq  = 1.0f - 1.0f / gamma_sq;
-            constexpr float MeMp = kMe / kMp;
-            const float Te_max   = (2.0f * kMe * beta_sq * gamma_sq) / (1.0f + 2.0f * gamma * MeMp + MeMp * MeMp);
-
-            rsp0            = rsp_eval(M, ke);
-            const float cms = rsp0 * rho * (1.0f / kWaterRho);   // WEPL of the 1 mm max step
-            // one row of the p-ion grid serves the delta cross section, |dEdx| and the csda range
-            const int    ia  = row_a(ke);
-            const float  ta  = ke - (0.1f + ia * 0.5f);
-            const float4 A0  = sm.a0[ia];
-            const float4 A1  = sm.a1[ia];
-            const bool   in_a = ke <= 299.6f;   // ke > 0.5 here
-            const float  sp_w = in_a ? fmaf(ta, A0.w, A0.z) : 0.f;
-            const float cs1_ion = in_a ? fmaf(ta, A0.y, A0.x) : 0.f;
-            float       cs1_sum = cs1_ion;
-            if (ke <= 300.0f) {
-                const int    ib = row_b(ke);
-                const float2 b  = sm.bs[ib];
-                cs1_sum += fmaf(ke - (0.5f + ib * 0.5f), b.y, b.x);
-            }
-            const float e2 = ke - cms * sp_w;   // energy after the largest possible CSDA loss
-            float       cs2_ion = 0.f, cs2_sum = 0.f;
-            if (e2 >= 0.1f) {   // e2 < ke <= 299.6 inside the table
-                const int    i = row_a(e2);
-                const float4 a = sm.a0[i];
-                cs2_ion        = fmaf(e2 - (0.1f + i * 0.5f), a.y, a.x);
-                cs2_sum        = cs2_ion;
-                if (e2 >= 0.5f) {
-                    const int    j = row_b(e2);
-                    const float2 b = sm.bs[j];
-                    cs2_sum += fmaf(e2 - (0.5f + j * 0.5f), b.y, b.x);
+            StepResult res;
+            res.dE = dE_pre; res.local_dE = 0.f; res.te_debug = 0.f; res.len = 0.f;
+            float rsp0;
+            if (ke <= kTpCut) {
+                // below the tracking cut: dump the energy, :86-94 + last_step mqi_p_ionization.hpp:482-490
+                if (ke < 0.f) ke = 0.f;
+                rsp0 = rsp_eval(M, ke);
+                res.dE += ke;
+                ke1 -= ke;
+                float step_len = 0.f;
+                if (res.dE > 0.f && ke > 0.f) {
+                    const float liw = res.dE / stopping_power(sm, ke);
+                    step_len        = liw * kWaterRho / (rsp0 * rho);
                 }
-            }
-            const bool  use1   = cs1_sum >= cs2_sum;
-            const float cs_sum = (use1 ? cs1_sum : cs2_sum) * rho;
-            const float c0     = (use1 ? cs1_ion : cs2_ion) * rho;   // delta-electron channel
+                p1x = px + dx * step_len; p1y = py + dy * step_len; p1z = pz + dz * step_len;
+                res.len = step_len;
+                stopped = true;
+            } else {
+                // ---------------- class-II condensed-history step, fippel_physics::stepping :95-216
+                // the per-step Philox block first: it only depends on the counter
+                uint32_t w[4];
+                philox4x32_10_rk(blk, 0u, h0, h1, P.rk, w);
+                blk += 1;
+                const float u_mfp = u32_to_uniform(w[0]);
+                const float u_phi = u32_to_uniform(w[3]);
+                float z_loss, z_theta;
+                box_muller(u32_to_uniform(w[1]), u32_to_uniform(w[2]), z_loss, z_theta);
 
-            const float mfp = -logf(u_mfp) / cs_sum;
-            constexpr float step_limit = 1.0f;   // cms * rho_w / (rsp * rho): max_step, mqi_fippel_physics.hpp:20
-            const bool  to_boundary = d2b < mfp && d2b < step_limit;
-            const bool  discrete    = !to_boundary && (mfp < d2b || fabsf(mfp - d2b) < kGeomTol) &&
-                                      (mfp < step_limit || fabsf(mfp - step_limit) < kGeomTol);
-            const float len         = to_boundary ? d2b : (discrete ? mfp : step_limit);
-            // ---------------- along step (CSDA + straggling + MCS), mqi_p_ionization.hpp:298-420
-            {
-                const float liw = len * cms;
-                float       dE;
-                const float R0 = fmaf(ta, A1.y, A1.x);   // residual csda range in water
-                if (R0 < liw) {
-                    dE = ke;
-                } else {
-                    const float r = R0 - liw;
-                    int         n = ia;
-                    float4      B = A1;
-                    if (n > kTableN - 2) B = sm.a1[n = kTableN - 2];
-                    // do { if (r >= r_steps[n]) break; } while (--n > 0): at most one row per step above
-                    // ~70 MeV, so the first move is a select and only the rest a (divergent) loop
-                    {
-                        const float4 Bm  = sm.a1[max(n - 1, 0)];
-                        const bool   mv  = n > 0 && r < B.x;
-                        B                = mv ? Bm : B;
-                        n                = mv ? n - 1 : n;
+                // relativistic quantities of vtx0.ke, base/mqi_relativistic_quantities.hpp:27-44
+                const float Et       = ke + kMp;
+                const float gamma    = Et * (1.0f / kMp);
+                const float gamma_sq = gamma * gamma;
+                const float beta_sq  = 1.0f - 1.0f / gamma_sq;
+                constexpr float MeMp = kMe / kMp;
+                const float Te_max   = (2.0f * kMe * beta_sq * gamma_sq) / (1.0f + 2.0f * gamma * MeMp + MeMp * MeMp);
+
+                rsp0            = rsp_eval(M, ke);
+                const float cms = rsp0 * rho * (1.0f / kWaterRho);   // WEPL of the 1 mm max step
+                // one row of the p-ion grid serves the delta cross section, |dEdx| and the csda range
+                const int    ia  = row_a(ke);
+                const float  ta  = ke - (0.1f + ia * 0.5f);
+                const float4 A0  = sm.a0[ia];
+                const float4 A1  = sm.a1[ia];
+                const bool   in_a = ke <= 299.6f;   // ke > 0.5 here
+                const float  sp_w = in_a ? fmaf(ta, A0.w, A0.z) : 0.f;
+                const float cs1_ion = in_a ? fmaf(ta, A0.y, A0.x) : 0.f;
+                float       cs1_sum = cs1_ion;
+                if (ke <= 300.0f) {
+                    const int    ib = row_b(ke);
+                    const float2 b  = sm.bs[ib];
+                    cs1_sum += fmaf(ke - (0.5f + ib * 0.5f), b.y, b.x);
+                }
+                const float e2 = ke - cms * sp_w;   // energy after the largest possible CSDA loss
+                float       cs2_ion = 0.f, cs2_sum = 0.f;
+                if (e2 >= 0.1f) {   // e2 < ke <= 299.6 inside the table
+                    const int    i = row_a(e2);
+                    const float4 a = sm.a0[i];
+                    cs2_ion        = fmaf(e2 - (0.1f + i * 0.5f), a.y, a.x);
+                    cs2_sum        = cs2_ion;
+                    if (e2 >= 0.5f) {
+                        const int    j = row_b(e2);
+                        const float2 b = sm.bs[j];
+                        cs2_sum += fmaf(e2 - (0.5f + j * 0.5f), b.y, b.x);
                     }
-                    while (n > 0 && r < B.x) B = sm.a1[--n];
-                    const float dE_mean = ke - fmaf(r - B.x, B.z, 0.1f + n * 0.5f);
-                    const float Te      = fminf(Te_max, 0.08511f);
-                    const float var     = P.dedx_term0 * rho * (1.0f / kWaterRho) * liw * (Te / beta_sq * (1.0f - 0.5f * beta_sq));
-                    dE                  = fabsf(fmaf(z_loss, sqrtf(var), dE_mean));
                 }
-                float r = 1.0f;
-                if (dE >= ke) {
-                    r       = ke / dE;
-                    stopped = true;
-                }
-                const float P_sq  = Et * Et - kMpSq;
-                const float th_sq = (13.9f * 13.9f) / (P_sq * beta_sq) * len * M.inv_x0;
-                const float th    = fabsf(z_theta) * sqrtf(2.0f * th_sq);
-                rotate_direction(d1x, d1y, d1z, th, kTwoPi * u_phi);
-                res.dE += dE * r;
-                const float sl = r * len;
-                p1x = fmaf(dx, sl, px); p1y = fmaf(dy, sl, py); p1z = fmaf(dz, sl, pz);
-                res.len = sl;
-                ke1 -= dE * r;
-            }
-            // ---------------- discrete interaction at the end of the step, :156-197
-            if (discrete && ke1 > kTpCut) {
-                d1x = dx; d1y = dy; d1z = dz;   // vtx1.dir = vtx0.dir (B11)
-                const float u = cs_sum * u_phi;  // u_phi is unused on this step: selects the process
-                if (u < c0) {
-                    // delta electron, p_ionization_tabulated::post_step mqi_p_ionization.hpp:425-477
-                    const float Et1   = ke1 + kMp;
-                    const float g1    = Et1 * (1.0f / kMp);
-                    const float g1_sq = g1 * g1;
-                    const float b1_sq = 1.0f - 1.0f / g1_sq;
-                    const float Tmax1 = (2.0f * kMe * b1_sq * g1_sq) / (1.0f + 2.0f * g1 * MeMp + MeMp * MeMp);
-                    const float inv_Tmax1 = 1.0f / Tmax1, inv_2Et_sq = 0.5f / (Et1 * Et1);
-                    const uint32_t key2 = k0 ^ (k1 * 0x85EBCA6Bu) ^ (h1 * 0xC2B2AE35u);
-                    float Te;
-                    while (true) {   // accepted at the first attempt about 9 times in 10
-                        uint32_t wn, wa;
-                        philox2x32_10(blk, h0, key2, wn, wa);
-                        blk += 1;
-                        const float n = u32_to_uniform(wn);
-                        Te = T_cut * Tmax1 / ((1.0f - n) * Tmax1 + n * T_cut);
-                        if (u32_to_uniform(wa) < 1.0f - b1_sq * Te * inv_Tmax1 + Te * Te * inv_2Et_sq) break;
-                    }
-                    if (VARIANT == MQI_K_DEBUG) res.te_debug = Te;   // carried by a zero-energy daughter
-                    else res.dE += Te;
-                    ke1 -= Te;
-                } else {
-                    NucIO io;
-                    io.px = px; io.py = py; io.pz = pz; io.dx = dx; io.dy = dy; io.dz = dz;
-                    io.p1x = p1x; io.p1y = p1y; io.p1z = p1z;
-                    io.d1x = d1x; io.d1y = d1y; io.d1z = d1z;
-                    io.ke1 = ke1; io.dE = res.dE; io.local_dE = res.local_dE;
-                    io.u = u - c0; io.e_cs = use1 ? ke : e2; io.rho = rho;
-                    io.stopped = stopped ? 1 : 0;
-                    io.sp = sp; io.n_sec = 0; io.n_ovf = 0;
-                    io.rb.blk = blk; io.rb.pos = 4; io.rb.h0 = h0; io.rb.h1 = h1; io.rb.k0 = k0; io.rb.k1 = k1;
-                    nuclear_event<VARIANT>(P, stack, io);
-                    d1x = io.d1x; d1y = io.d1y; d1z = io.d1z;
-                    ke1 = io.ke1; res.dE = io.dE; res.local_dE = io.local_dE;
-                    stopped = io.stopped != 0;
-                    sp = io.sp; n_sec += io.n_sec; n_ovf += io.n_ovf;
-                    blk = io.rb.blk;
-                }
-            }
-        }
+                const bool  use1   = cs1_sum >= cs2_sum;
+                const float cs_sum = (use1 ? cs1_sum : cs2_sum) * rho;
+                const float c0     = (use1 ? cs1_ion : cs2_ion) * rho;   // delta-electron channel
 
-        // ------------------------------------------------------------------ scoring, :204-225
-        if (rho >= 1.0e-7f && rho <= 99.9f) {
+                const float mfp = -logf(u_mfp) / cs_sum;
+                constexpr float step_limit = 1.0f;   // cms * rho_w / (rsp * rho): max_step, mqi_fippel_physics.hpp:20
+                const bool  to_boundary = d2b < mfp && d2b < step_limit;
+                const bool  discrete    = !to_boundary && (mfp < d2b || fabsf(mfp - d2b) < kGeomTol) &&
+                                          (mfp < step_limit || fabsf(mfp - step_limit) < kGeomTol);
+                const float len         = to_boundary ? d2b : (discrete ? mfp : step_limit);
+                // ---------------- along step (CSDA + straggling + MCS), mqi_p_ionization.hpp:298-420
+                {
+                    const float liw = len * cms;
+                    float       dE;
+                    const float R0 = fmaf(ta, A1.y, A1.x);   // residual csda range in water
+                    if (R0 < liw) {
+                        dE = ke;
+                    } else {
+                        // do { if (r >= r_steps[n]) break; } while (--n > 0) from n = min(ia, 598): the
+                        // largest row n <= ia whose range does not exceed r (ranges increase with the row).
+                        // Same row, found from a first guess (the row of ke - liw |dEdx|, exact above
+                        // ~70 MeV) corrected against the table in both directions.
+                        const float r  = R0 - liw;
+                        const int   n0 = min(ia, kTableN - 2);
+                        int         n  = min(max((int) ((fmaf(-liw, sp_w, ke) - 0.1f) * 2.0f), 0), n0);
+                        float4      B  = sm.a1[n];
+                        while (n < n0) {
+                            const float4 Bn = sm.a1[n + 1];
+                            if (r < Bn.x) break;
+                            B = Bn;
+                            ++n;
+                        }
+                        while (n > 0 && r < B.x) B = sm.a1[--n];
+                        const float dE_mean = ke - fmaf(r - B.x, B.z, 0.1f + n * 0.5f);
+                        const float Te      = fminf(Te_max, 0.08511f);
+                        const float var     = P.dedx_term0 * rho * (1.0f / kWaterRho) * liw * (Te / beta_sq * (1.0f - 0.5f * beta_sq));
+                        dE                  = fabsf(fmaf(z_loss, sqrtf(var), dE_mean));
+                    }
+                    float r = 1.0f;
+                    if (dE >= ke) {
+                        r       = ke / dE;
+                        stopped = true;
+                    }
+                    const float P_sq  = Et * Et - kMpSq;
+                    const float th_sq = (13.9f * 13.9f) / (P_sq * beta_sq) * len * M.inv_x0;
+                    const float th    = fabsf(z_theta) * sqrtf(2.0f * th_sq);
+                    rotate_direction(d1x, d1y, d1z, th, kTwoPi * u_phi);
+                    res.dE += dE * r;
+                    const float sl = r * len;
+                    p1x = fmaf(dx, sl, px); p1y = fmaf(dy, sl, py); p1z = fmaf(dz, sl, pz);
+                    res.len = sl;
+                    ke1 -= dE * r;
+                }
+                // ---------------- discrete interaction at the end of the step, :156-197
+                if (discrete && ke1 > kTpCut) {
+                    d1x = dx; d1y = dy; d1z = dz;   // vtx1.dir = vtx0.dir (B11)
+                    const float u = cs_sum * u_phi;  // u_phi is unused on this step: selects the process
+                    if (u < c0) {
+                        // delta electron, p_ionization_tabulated::post_step mqi_p_ionization.hpp:425-477.
+                        // First try of the rejection loop without another generator call: given that the
+                        // delta channel was selected, u / c0 is uniform in [0,1); the acceptance deviate
+                        // comes from the top bytes of the step's block (unused by the 23-bit uniforms).
+                        const float Et1   = ke1 + kMp;
+                        const float g1    = Et1 * (1.0f / kMp);
+                        const float g1_sq = g1 * g1;
+                        const float b1_sq = 1.0f - 1.0f / g1_sq;
+                        const float Tmax1 = (2.0f * kMe * b1_sq * g1_sq) / (1.0f + 2.0f * g1 * MeMp + MeMp * MeMp);
+                        const float inv_2Et_sq = 0.5f / (Et1 * Et1);
+                        const float n  = fminf(u / c0, 1.0f);
+                        float       Te = T_cut * Tmax1 / ((1.0f - n) * Tmax1 + n * T_cut);
+                        if (!(spare_bytes_to_uniform(w[0], w[1], w[2]) < 1.0f - b1_sq * Te / Tmax1 + Te * Te * inv_2Et_sq))
+                            Te = delta_retry(blk, h0, k0 ^ (k1 * 0x85EBCA6Bu) ^ (h1 * 0xC2B2AE35u), T_cut, Tmax1, b1_sq, inv_2Et_sq);
+                        if (VARIANT == MQI_K_DEBUG) res.te_debug = Te;   // carried by a zero-energy daughter
+                        else res.dE += Te;
+                        ke1 -= Te;
+                    } else {
+                        NucIO io;
+                        io.px = px; io.py = py; io.pz = pz; io.dx = dx; io.dy = dy; io.dz = dz;
+                        io.p1x = p1x; io.p1y = p1y; io.p1z = p1z;
+                        io.d1x = d1x; io.d1y = d1y; io.d1z = d1z;
+                        io.ke1 = ke1; io.dE = res.dE; io.local_dE = res.local_dE;
+                        io.u = u - c0; io.e_cs = use1 ? ke : e2; io.rho = rho;
+                        io.stopped = stopped ? 1 : 0;
+                        io.sp = sp; io.n_sec = 0; io.n_ovf = 0;
+                        io.rb.blk = blk; io.rb.pos = 4; io.rb.h0 = h0; io.rb.h1 = h1; io.rb.k0 = k0; io.rb.k1 = k1;
+                        nuclear_event<VARIANT>(P, stack, io);
+                        d1x = io.d1x; d1y = io.d1y; d1z = io.d1z;
+                        ke1 = io.ke1; res.dE = io.dE; res.local_dE = io.local_dE;
+                        stopped = io.stopped != 0;
+                        sp = io.sp; n_sec += io.n_sec; n_ovf += io.n_ovf;
+                        blk = io.rb.blk;
+                    }
+                }
+            }
+
+            // -------------------------------------------------------------- scoring, :204-225
             const float inv_vol = 1.0f / ((ex1 - ex0) * (ey1 - ey0) * (ez1 - ez0));
             if (SIMPLE) {
                 // dose_to_water: (dE + local_dE) * 1.60218e-10 / (V * rho * rsp(rho, vtx0.ke)); voxel 0 is
-                // never scored (roi_->idx(cnb) > 0, B1); insert_hashtable skips value <= 0
+                // never scored (roi_->idx(cnb) > 0, B1); insert_hashtable skips value <= 0.  The debug
+                // variant's zero-energy delta daughter scores its own hit with rsp(rho, 0).
                 const float kdose = 1.60218e-10f * inv_vol * M.inv_rho;
-                double      v     = (double) ((res.dE + res.local_dE) * kdose / rsp0);
-                if (VARIANT == MQI_K_DEBUG) v += (double) (res.te_debug * kdose * inv_rsp_at_zero_energy(M));
+                float       vf    = (res.dE + res.local_dE) * kdose / rsp0;
+                if (VARIANT == MQI_K_DEBUG) vf = fmaf(res.te_debug * kdose, inv_rsp_at_zero_energy(M), vf);
+                const double v    = (double) vf;
                 if (cnb != 0u && v > 0.0) dense_add(P.sc[0].dense, cnb, v, P.accum_mode);
             } else {
                 score_step<VARIANT>(P, M, cnb, spot_ind, inv_vol, rsp0, res);
@@ -744,13 +824,13 @@ transport_kernel(const __grid_constant__ Params P) {
             ke = ke1;
             ke1_off = 0.f;
             dE_pre  = 0.f;
-            if (ix < 0 || iy < 0 || iz < 0 || ix >= nx || iy >= ny || iz >= nz) alive = false;
+            if ((unsigned) ix >= (unsigned) nx || (unsigned) iy >= (unsigned) ny || (unsigned) iz >= (unsigned) nz) alive = false;
         }
     }
 
     // per-lane counters -> global (one atomic per lane per launch)
     if (n_done) atomicAdd(P.counters + C_DONE, (unsigned long long) n_done);
-    if (n_steps) atomicAdd(P.counters + C_STEPS, (unsigned long long) n_steps);
+    if (n_steps && P.count_steps) atomicAdd(P.counters + C_STEPS, (unsigned long long) n_steps);
     if (n_sec) atomicAdd(P.counters + C_SECONDARIES, (unsigned long long) n_sec);
     if (n_ovf) atomicAdd(P.counters + C_OVERFLOW, (unsigned long long) n_ovf);
 }

@@ -597,8 +597,17 @@ mqo_philox2x32_10(const uint32_t ctr_in[2], uint32_t key, uint32_t out[2]) {
 }
 
 float
-mqo_u32_to_uniform(uint32_t x) { /* open interval (0,1): ((x >> 8) + 0.5) * 2^-24 */
-    return ((float) (x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+mqo_u32_to_uniform(uint32_t x) { /* open interval (0,1), 23 bits: (m + 0.5) * 2^-23 with m = x & 0x7fffff */
+    uint32_t bits = 0x3f800000u | (x & 0x007fffffu);
+    float    f;
+    memcpy(&f, &bits, sizeof(f));
+    return f - 0.99999994f; /* exact: f = 1 + m 2^-23, constant = 1 - 2^-24 */
+}
+/* 24-bit deviate from the top bytes of three Philox words (bits the mapping above never looks at) */
+static inline float
+low_bytes_to_uniform(uint32_t w0, uint32_t w1, uint32_t w2) {
+    uint32_t v = (w0 >> 24) | ((w1 >> 24) << 8) | ((w2 >> 24) << 16);
+    return ((float) v + 0.5f) * (1.0f / 16777216.0f);
 }
 
 typedef struct {
@@ -832,12 +841,16 @@ last_step(ctx_t* c, track_t* trk, float rho_mass) {
 
 /* p_ionization_tabulated::post_step (delta electron) :425-477 */
 static void
-delta_post_step(ctx_t* c, track_t* trk) {
+delta_post_step(ctx_t* c, track_t* trk, float n_first, float acc_first) {
     relq  rel = rel_make(trk->vtx1.ke);
     float Te, n, acc;
+    int   first = 1;
     if (c->st) c->st->delta_events++;
     while (1) {
-        rng_pair2(c->rng, &n, &acc);
+        /* RNG protocol: the first try reuses the step's block (n = u / cs_delta, uniform given that the
+         * delta channel was selected; accept deviate = top bytes of the block), later tries draw pairs */
+        if (first) { n = n_first; acc = acc_first; first = 0; }
+        else rng_pair2(c->rng, &n, &acc);
         Te = c->T_cut * rel.Te_max;
         Te /= ((1.0 - n) * rel.Te_max + n * c->T_cut);
         if (acc < 1.0 - rel.beta_sq * Te / rel.Te_max + Te * Te / (2.0 * rel.Et_sq)) break;
@@ -1095,7 +1108,8 @@ stepping(ctx_t* c, track_t* trk, float rho_mass, float distance_to_boundary) {
     cs      = (cs1_sum >= cs2_sum) ? cs1 : cs2;
 
     /* RNG protocol: one aligned Philox4x32 block per physics step = {u_mfp, u_a, u_b, u_phi}; a
-     * discrete interaction is selected with u_phi; delta-electron sampling draws Philox2x32 pairs;
+     * discrete interaction is selected with u_phi; the first delta-electron try reuses the step's block
+     * (see delta_post_step), later tries draw Philox2x32 pairs;
      * nuclear interactions draw from further Philox4x32 blocks */
     rng_begin_step(c->rng);
     prob = rng_uniform(c->rng);
@@ -1117,7 +1131,9 @@ stepping(ctx_t* c, track_t* trk, float rho_mass, float distance_to_boundary) {
         u             = cs_sum * u_phi;
         trk->vtx1.dir = trk->vtx0.dir;
         if (u < cs[0]) {
-            delta_post_step(c, trk);
+            float n_first = u / cs[0];
+            if (n_first > 1.0f) n_first = 1.0f;
+            delta_post_step(c, trk, n_first, low_bytes_to_uniform(c->rng->buf[0], c->rng->buf[1], c->rng->buf[2]));
         } else if (u < (cs[0] + cs[1])) {
             pp_post_step(c, trk);
         } else if (u < (cs[0] + cs[1] + cs[2])) {

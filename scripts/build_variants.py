@@ -1,0 +1,30 @@
+"""Build tuning variants of libmqi_b200.so (block size / resident CTAs / loop barrier) into
+moquimc_b200/variants/ for A/B runs on the GPU box:  MQI_B200_LIB=<variant.so> python scripts/quick_bench.py"""
+import os
+import subprocess
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from moquimc_b200 import build as B
+
+VARIANTS = {
+    "b256_s0": (256, 4, 0), "b256_s1": (256, 4, 1), "b256_s2": (256, 4, 2),
+    "b512_s0": (512, 2, 0), "b512_s1": (512, 2, 1), "b512_s2": (512, 2, 2),
+    "b1024_s1": (1024, 1, 1), "b1024_s2": (1024, 1, 2),
+}
+
+def main(names):
+    B.gen_tables_inc()
+    out = os.path.join(B.HERE, "variants")
+    os.makedirs(out, exist_ok=True)
+    cu = [os.path.join(B.CSRC, f) for f in ("mqi_transport.cu", "mqi_capi.cu")]
+    procs = []
+    for n in names:
+        blk, mb, sync = VARIANTS[n]
+        cmd = [B.nvcc()] + B.NVCC_FLAGS + ["-DMQI_K_BLOCK=%d" % blk, "-DMQI_K_MIN_BLOCKS=%d" % mb, "-DMQI_K_SYNC=%d" % sync,
+                                           "-shared", "-o", os.path.join(out, "libmqi_%s.so" % n)] + cu + ["-ldl"]
+        procs.append(subprocess.Popen(cmd))
+    for p in procs:
+        assert p.wait() == 0
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or list(VARIANTS))
