@@ -29,6 +29,10 @@
 #define MQI_K_SYNC 0   /* per-iteration CTA (1) / sub-partition (2) barrier in the transport loop: see profiles/ */
 #endif
 
+#ifndef MQI_K_LATE_LUT
+#define MQI_K_LATE_LUT 1   /* delay the material LUT load behind the step's random numbers (see mqi_transport.cu) */
+#endif
+
 namespace mqib
 {
 struct Params;

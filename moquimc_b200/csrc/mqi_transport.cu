@@ -614,7 +614,50 @@ transport_kernel(const __grid_constant__ Params P) {
         const float ey0 = sm.ye[iy], ey1 = sm.ye[iy + 1];
         const float ez0 = sm.ze[iz], ez1 = sm.ze[iz + 1];
         const unsigned cnb = ((unsigned) iz * (unsigned) ny + (unsigned) iy) * (unsigned) nx + (unsigned) ix;
-        const MatEntry M   = P.g.lut[__ldg(P.g.mat + cnb)];
+        // material of the voxel: two dependent loads (index volume -> LUT entry); everything up to the
+        // first use of M (random numbers, kinematics, table rows, voxel exit distance) depends on the
+        // lane state alone
+#if MQI_K_LATE_LUT
+        const unsigned mat_idx = __ldg(P.g.mat + cnb);
+#else
+        const MatEntry M = P.g.lut[__ldg(P.g.mat + cnb)];
+#endif
+
+        // the per-step Philox block {u_mfp, u_a, u_b, u_phi}; consumed (blk advances) only if the step
+        // turns out to be a condensed-history step
+        uint32_t w[4];
+        philox4x32_10_rk(blk, 0u, h0, h1, P.rk, w);
+        const float u_mfp = u32_to_uniform(w[0]);
+        const float u_phi = u32_to_uniform(w[3]);
+        float z_loss, z_theta;
+        box_muller(u32_to_uniform(w[1]), u32_to_uniform(w[2]), z_loss, z_theta);
+
+        // relativistic quantities of vtx0.ke, base/mqi_relativistic_quantities.hpp:27-44
+        constexpr float MeMp = kMe / kMp;
+        const float Et       = ke + kMp;
+        const float gamma    = Et * (1.0f / kMp);
+        const float gamma_sq = gamma * gamma;
+        const float beta_sq  = 1.0f - 1.0f / gamma_sq;
+        const float Te_max   = (2.0f * kMe * beta_sq * gamma_sq) / (1.0f + 2.0f * gamma * MeMp + MeMp * MeMp);
+        // rows of vtx0.ke: one row of the p-ion grid serves the delta cross section, |dEdx| and the csda
+        // range; clamped rows make every lookup safe, out-of-table energies are masked by selects
+        const int    ia   = row_a(ke);
+        const float  ta   = ke - (0.1f + ia * 0.5f);
+        const float4 A0   = sm.a0[ia];
+        const float4 A1   = sm.a1[ia];
+        const bool   in_a = ke <= 299.6f;
+        const float  sp_w    = in_a ? fmaf(ta, A0.w, A0.z) : 0.f;
+        const float  cs1_ion = in_a ? fmaf(ta, A0.y, A0.x) : 0.f;
+        const int    ib   = row_b(ke);
+        const float2 Bs1  = sm.bs[ib];
+        const float  cs1_sum = cs1_ion + (ke <= 300.0f ? fmaf(ke - (0.5f + ib * 0.5f), Bs1.y, Bs1.x) : 0.f);
+
+#if MQI_K_LATE_LUT
+        // The LUT entry is addressed only now: the address takes the (always clear) sign bit of u_mfp as
+        // a data dependency, so that the in-order issue does not park the warp on the index load
+        // before the ~100 independent instructions above have been issued.
+        const MatEntry M = P.g.lut[mat_idx + (__float_as_uint(u_mfp) >> 31)];
+#endif
         float       d1x = dx, d1y = dy, d1z = dz;   // vtx1.dir: copy taken before intersect() zeroes tiny components
         const float tx = cell_tmax_axis(ex0, ex1, nx, px, dx, ix);
         const float ty = cell_tmax_axis(ey0, ey1, ny, py, dy, iy);
@@ -655,52 +698,17 @@ transport_kernel(const __grid_constant__ Params P) {
                 stopped = true;
             } else {
                 // ---------------- class-II condensed-history step, fippel_physics::stepping :95-216
-                // the per-step Philox block first: it only depends on the counter
-                uint32_t w[4];
-                philox4x32_10_rk(blk, 0u, h0, h1, P.rk, w);
                 blk += 1;
-                const float u_mfp = u32_to_uniform(w[0]);
-                const float u_phi = u32_to_uniform(w[3]);
-                float z_loss, z_theta;
-                box_muller(u32_to_uniform(w[1]), u32_to_uniform(w[2]), z_loss, z_theta);
-
-                // relativistic quantities of vtx0.ke, base/mqi_relativistic_quantities.hpp:27-44
-                const float Et       = ke + kMp;
-                const float gamma    = Et * (1.0f / kMp);
-                const float gamma_sq = gamma * gamma;
-                const float beta_sq  = 1.0f - 1.0f / gamma_sq;
-                constexpr float MeMp = kMe / kMp;
-                const float Te_max   = (2.0f * kMe * beta_sq * gamma_sq) / (1.0f + 2.0f * gamma * MeMp + MeMp * MeMp);
-
                 rsp0            = rsp_eval(M, ke);
                 const float cms = rsp0 * rho * (1.0f / kWaterRho);   // WEPL of the 1 mm max step
-                // one row of the p-ion grid serves the delta cross section, |dEdx| and the csda range
-                const int    ia  = row_a(ke);
-                const float  ta  = ke - (0.1f + ia * 0.5f);
-                const float4 A0  = sm.a0[ia];
-                const float4 A1  = sm.a1[ia];
-                const bool   in_a = ke <= 299.6f;   // ke > 0.5 here
-                const float  sp_w = in_a ? fmaf(ta, A0.w, A0.z) : 0.f;
-                const float cs1_ion = in_a ? fmaf(ta, A0.y, A0.x) : 0.f;
-                float       cs1_sum = cs1_ion;
-                if (ke <= 300.0f) {
-                    const int    ib = row_b(ke);
-                    const float2 b  = sm.bs[ib];
-                    cs1_sum += fmaf(ke - (0.5f + ib * 0.5f), b.y, b.x);
-                }
-                const float e2 = ke - cms * sp_w;   // energy after the largest possible CSDA loss
-                float       cs2_ion = 0.f, cs2_sum = 0.f;
-                if (e2 >= 0.1f) {   // e2 < ke <= 299.6 inside the table
-                    const int    i = row_a(e2);
-                    const float4 a = sm.a0[i];
-                    cs2_ion        = fmaf(e2 - (0.1f + i * 0.5f), a.y, a.x);
-                    cs2_sum        = cs2_ion;
-                    if (e2 >= 0.5f) {
-                        const int    j = row_b(e2);
-                        const float2 b = sm.bs[j];
-                        cs2_sum += fmaf(e2 - (0.5f + j * 0.5f), b.y, b.x);
-                    }
-                }
+                const float e2  = ke - cms * sp_w;   // energy after the largest possible CSDA loss
+                // cross sections at e2 (< ke, so inside the tables from above); zero below the grids
+                const int    i2  = row_a(e2);
+                const float4 a2  = sm.a0[i2];
+                const int    j2  = row_b(e2);
+                const float2 b2  = sm.bs[j2];
+                const float cs2_ion = e2 >= 0.1f ? fmaf(e2 - (0.1f + i2 * 0.5f), a2.y, a2.x) : 0.f;
+                const float cs2_sum = cs2_ion + (e2 >= 0.5f ? fmaf(e2 - (0.5f + j2 * 0.5f), b2.y, b2.x) : 0.f);
                 const bool  use1   = cs1_sum >= cs2_sum;
                 const float cs_sum = (use1 ? cs1_sum : cs2_sum) * rho;
                 const float c0     = (use1 ? cs1_ion : cs2_ion) * rho;   // delta-electron channel
@@ -714,45 +722,42 @@ transport_kernel(const __grid_constant__ Params P) {
                 // ---------------- along step (CSDA + straggling + MCS), mqi_p_ionization.hpp:298-420
                 {
                     const float liw = len * cms;
-                    float       dE;
-                    const float R0 = fmaf(ta, A1.y, A1.x);   // residual csda range in water
-                    if (R0 < liw) {
-                        dE = ke;
-                    } else {
-                        // do { if (r >= r_steps[n]) break; } while (--n > 0) from n = min(ia, 598): the
-                        // largest row n <= ia whose range does not exceed r (ranges increase with the row).
-                        // Same row, found from a first guess (the row of ke - liw |dEdx|, exact above
-                        // ~70 MeV) corrected against the table in both directions.
-                        const float r  = R0 - liw;
-                        const int   n0 = min(ia, kTableN - 2);
-                        int         n  = min(max((int) ((fmaf(-liw, sp_w, ke) - 0.1f) * 2.0f), 0), n0);
-                        float4      B  = sm.a1[n];
-                        while (n < n0) {
-                            const float4 Bn = sm.a1[n + 1];
-                            if (r < Bn.x) break;
-                            B = Bn;
-                            ++n;
-                        }
-                        while (n > 0 && r < B.x) B = sm.a1[--n];
-                        const float dE_mean = ke - fmaf(r - B.x, B.z, 0.1f + n * 0.5f);
-                        const float Te      = fminf(Te_max, 0.08511f);
-                        const float var     = P.dedx_term0 * rho * (1.0f / kWaterRho) * liw * (Te / beta_sq * (1.0f - 0.5f * beta_sq));
-                        dE                  = fabsf(fmaf(z_loss, sqrtf(var), dE_mean));
+                    const float R0  = fmaf(ta, A1.y, A1.x);   // residual csda range in water
+                    // do { if (r >= r_steps[n]) break; } while (--n > 0) from n = min(ia, 598): the
+                    // largest row n <= ia whose range does not exceed r (ranges increase with the row).
+                    // Same row, found from a first guess (the row of ke - liw |dEdx|, exact above
+                    // ~70 MeV) corrected against the table in both directions.  When the residual range
+                    // is shorter than the step (R0 < liw) all of ke is lost; r is clamped so that the
+                    // (discarded) inversion stays in the table.
+                    const float r  = fmaxf(R0 - liw, 0.f);
+                    const int   n0 = min(ia, kTableN - 2);
+                    int         n  = min(max((int) ((fmaf(-liw, sp_w, ke) - 0.1f) * 2.0f), 0), n0);
+                    float4      B  = sm.a1[n];
+                    while (n < n0) {
+                        const float4 Bn = sm.a1[n + 1];
+                        if (r < Bn.x) break;
+                        B = Bn;
+                        ++n;
                     }
-                    float r = 1.0f;
+                    while (n > 0 && r < B.x) B = sm.a1[--n];
+                    const float dE_mean = ke - fmaf(r - B.x, B.z, 0.1f + n * 0.5f);
+                    const float Te      = fminf(Te_max, 0.08511f);
+                    const float var     = P.dedx_term0 * rho * (1.0f / kWaterRho) * liw * (Te / beta_sq * (1.0f - 0.5f * beta_sq));
+                    const float dE      = R0 < liw ? ke : fabsf(fmaf(z_loss, sqrtf(var), dE_mean));
+                    float rr = 1.0f;
                     if (dE >= ke) {
-                        r       = ke / dE;
+                        rr      = ke / dE;
                         stopped = true;
                     }
                     const float P_sq  = Et * Et - kMpSq;
                     const float th_sq = (13.9f * 13.9f) / (P_sq * beta_sq) * len * M.inv_x0;
                     const float th    = fabsf(z_theta) * sqrtf(2.0f * th_sq);
                     rotate_direction(d1x, d1y, d1z, th, kTwoPi * u_phi);
-                    res.dE += dE * r;
-                    const float sl = r * len;
+                    res.dE += dE * rr;
+                    const float sl = rr * len;
                     p1x = fmaf(dx, sl, px); p1y = fmaf(dy, sl, py); p1z = fmaf(dz, sl, pz);
                     res.len = sl;
-                    ke1 -= dE * r;
+                    ke1 -= dE * rr;
                 }
                 // ---------------- discrete interaction at the end of the step, :156-197
                 if (discrete && ke1 > kTpCut) {

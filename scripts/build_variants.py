@@ -10,6 +10,7 @@ VARIANTS = {
     "b256_s0": (256, 4, 0), "b256_s1": (256, 4, 1), "b256_s2": (256, 4, 2),
     "b512_s0": (512, 2, 0), "b512_s1": (512, 2, 1), "b512_s2": (512, 2, 2),
     "b1024_s1": (1024, 1, 1), "b1024_s2": (1024, 1, 2),
+    "early_lut": (256, 4, 0, "-DMQI_K_LATE_LUT=0"), "base": (256, 4, 0),
 }
 
 def main(names):
@@ -19,8 +20,8 @@ def main(names):
     cu = [os.path.join(B.CSRC, f) for f in ("mqi_transport.cu", "mqi_capi.cu")]
     procs = []
     for n in names:
-        blk, mb, sync = VARIANTS[n]
-        cmd = [B.nvcc()] + B.NVCC_FLAGS + ["-DMQI_K_BLOCK=%d" % blk, "-DMQI_K_MIN_BLOCKS=%d" % mb, "-DMQI_K_SYNC=%d" % sync,
+        blk, mb, sync = VARIANTS[n][:3]
+        cmd = [B.nvcc()] + B.NVCC_FLAGS + list(VARIANTS[n][3:]) + ["-DMQI_K_BLOCK=%d" % blk, "-DMQI_K_MIN_BLOCKS=%d" % mb, "-DMQI_K_SYNC=%d" % sync,
                                            "-shared", "-o", os.path.join(out, "libmqi_%s.so" % n)] + cu + ["-ldl"]
         procs.append(subprocess.Popen(cmd))
     for p in procs:
