@@ -46,6 +46,8 @@ extern "C" {
 #define MQI_SCORER_LETD_DENOM 3  /* LETd_weight2             :117-137 */
 #define MQI_SCORER_DOSE_SQ 4     /* dose_to_water_square     :64-77  (stopping criterion) */
 #define MQI_SCORER_DIJ 5         /* dose_to_water keyed by (voxel, spot): sparse hash table */
+#define MQI_SCORER_LETT_NUMER 6  /* LETt_weight1             :141-158 */
+#define MQI_SCORER_LETT_DENOM 7  /* LETt_weight2             :161-177 */
 
 /* reference quirks that can be switched on for bug-for-bug comparisons (default: off) */
 #define MQI_QUIRK_B2_DOUBLE_SCORE 1u /* mqi_transport.hpp:204-225: scorers [0,n-2) scored twice when n >= 3 */
@@ -177,6 +179,11 @@ MQI_API int mqi_get_scorer_device_ptr(mqi_handle* h, int scorer, void** d_ptr, u
  * all-reduces these partial sums across ranks before forming the percentage. */
 MQI_API int mqi_stat_partial(mqi_handle* h, int scorer_sum, int scorer_sumsq, uint64_t n_histories,
                      double threshold_fraction, double max_mean_dose_or_negative, double out[3]);
+/* Same criterion on caller-owned device buffers (n_voxels doubles each), e.g. the all-reduced sum /
+ * sum-of-squares grids of a one-process-per-GPU deployment (moquimc_b200/parallel.py). */
+MQI_API int mqi_stat_partial_buffers(mqi_handle* h, const void* d_sum, const void* d_sumsq, uint64_t n_voxels,
+                             uint64_t n_histories, double threshold_fraction, double max_mean_dose_or_negative,
+                             double out[3]);
 /* calculate_average (mqi_variables.hpp:50-66): scale a dense scorer in place */
 MQI_API int mqi_scale_scorer(mqi_handle* h, int scorer, double factor);
 

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("MQI_B200_LIB") or os.path.join(HERE, "libmqi_b200.so"
 HEADER = os.path.join(HERE, "..", "include", "mqi_b200.h")
 
 PHYSICS_RELEASE, PHYSICS_DEBUG = 0, 1
-SCORER_DOSE, SCORER_EDEP, SCORER_LETD_NUMER, SCORER_LETD_DENOM, SCORER_DOSE_SQ, SCORER_DIJ = range(6)
+SCORER_DOSE, SCORER_EDEP, SCORER_LETD_NUMER, SCORER_LETD_DENOM, SCORER_DOSE_SQ, SCORER_DIJ, SCORER_LETT_NUMER, SCORER_LETT_DENOM = range(8)
 QUIRK_B2_DOUBLE_SCORE = 1
 ACCUM_ATOMIC, ACCUM_WARP_MATCH = 0, 1
 ENODEVICE = -2
@@ -83,6 +83,7 @@ def load():
         "mqi_get_sparse": [vp, i32, vp, vp, vp, u64, C.c_double],
         "mqi_get_scorer_device_ptr": [vp, i32, C.POINTER(vp), C.POINTER(u64)],
         "mqi_stat_partial": [vp, i32, i32, u64, C.c_double, C.c_double, C.POINTER(C.c_double)],
+        "mqi_stat_partial_buffers": [vp, vp, vp, u64, u64, C.c_double, C.c_double, C.POINTER(C.c_double)],
         "mqi_scale_scorer": [vp, i32, C.c_double],
         "mqi_dev_hu_to_density": [vp, vp, u64, f32, vp],
         "mqi_dev_rsp": [vp, vp, vp, u64, vp, vp],
@@ -281,6 +282,12 @@ class Engine:
     def stat_partial(self, s_sum, s_sq, n_histories, threshold, max_mean=-1.0):
         out = (C.c_double * 3)()
         self._check(self.L.mqi_stat_partial(self.h, s_sum, s_sq, n_histories, threshold, max_mean, out))
+        return out[0], out[1], out[2]
+
+    def stat_partial_buffers(self, d_sum_ptr, d_sumsq_ptr, n_voxels, n_histories, threshold, max_mean=-1.0):
+        out = (C.c_double * 3)()
+        self._check(self.L.mqi_stat_partial_buffers(self.h, C.c_void_p(d_sum_ptr), C.c_void_p(d_sumsq_ptr), n_voxels,
+                                                    n_histories, threshold, max_mean, out))
         return out[0], out[1], out[2]
 
     def scale_scorer(self, scorer, factor):

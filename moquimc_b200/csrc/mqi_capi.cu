@@ -473,7 +473,7 @@ mqi_set_grid_density(mqi_handle* h, const float* xe, int n_xe, const float* ye, 
 int
 mqi_add_scorer(mqi_handle* h, int kind, const char* name, uint64_t capacity) {
     if (!h) return fail(MQI_EINVAL, "null handle");
-    if (kind < MQI_SCORER_DOSE || kind > MQI_SCORER_DIJ) return fail(MQI_EINVAL, "unknown scorer kind");
+    if (kind < MQI_SCORER_DOSE || kind > MQI_SCORER_LETT_DENOM) return fail(MQI_EINVAL, "unknown scorer kind");
     if ((int) h->scorers.size() >= kMaxScorers) return fail(MQI_EINVAL, "too many scorers");
     if (kind == MQI_SCORER_DIJ && capacity == 0) return fail(MQI_EINVAL, "Dij scorer needs a capacity");
     HostScorer s;
@@ -782,6 +782,30 @@ mqi_stat_partial(mqi_handle* h, int scorer_sum, int scorer_sumsq, uint64_t n_his
         CU(cudaStreamSynchronize(h->stream));
     }
     CU(launch_stat_partial(sum, sq, nvox(h), (double) n_histories, threshold_fraction * max_mean, d.p, h->stream));
+    CU(cudaMemcpyAsync(out, d.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    out[2] = max_mean;
+    return MQI_OK;
+}
+
+int
+mqi_stat_partial_buffers(mqi_handle* h, const void* d_sum, const void* d_sumsq, uint64_t n_voxels, uint64_t n_histories,
+                         double threshold_fraction, double max_mean, double out[3]) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (!d_sum || !d_sumsq || !out || n_voxels == 0) return fail(MQI_EINVAL, "null buffer");
+    if (n_histories < 2) return fail(MQI_ESTATE, "stat buffers need at least two histories");
+    const double* sum = static_cast<const double*>(d_sum);
+    const double* sq  = static_cast<const double*>(d_sumsq);
+    DevBuf<double> d;
+    CU(d.alloc(3));
+    CU(cudaMemsetAsync(d.p, 0, 3 * sizeof(double), h->stream));
+    if (max_mean < 0.0) {
+        CU(launch_stat_max(sum, n_voxels, 1.0 / (double) n_histories, d.p + 2, h->stream));
+        CU(cudaMemcpyAsync(&max_mean, d.p + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    CU(launch_stat_partial(sum, sq, n_voxels, (double) n_histories, threshold_fraction * max_mean, d.p, h->stream));
     CU(cudaMemcpyAsync(out, d.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     out[2] = max_mean;

@@ -13,6 +13,8 @@
 #define MQI_K_LETD_DENOM 3
 #define MQI_K_DOSE_SQ 4
 #define MQI_K_DIJ 5
+#define MQI_K_LETT_NUMER 6
+#define MQI_K_LETT_DENOM 7
 
 #define MQI_K_QUIRK_B2 1u
 #define MQI_K_ACCUM_ATOMIC 0

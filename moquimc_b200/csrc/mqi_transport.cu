@@ -358,6 +358,14 @@ letd_hit(int kind, float dE, float len, float rho) {
     return kind == MQI_K_LETD_NUMER ? (double) dE * let : (double) dE;
 }
 
+// LETt_weight1/2: scorers/mqi_scorer_energy_deposit.hpp:141-177
+__device__ __noinline__ double
+lett_hit(int kind, float dE, float len, float rho) {
+    if (kind == MQI_K_LETT_DENOM) return (double) len;
+    const double let = (double) dE / (double) len / (double) (rho * 1000.0f);
+    return (double) len * let;
+}
+
 // one insert per scorer per step, keyed to the voxel occupied at step start: mqi_transport.hpp:204-225,
 // hit functions scorers/mqi_scorer_energy_deposit.hpp:14-137
 template<int VARIANT>
@@ -377,6 +385,7 @@ score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, 
         if (kind == MQI_K_DOSE || kind == MQI_K_DIJ) v = dose + dose_te;
         else if (kind == MQI_K_DOSE_SQ) v = dose * dose + dose_te * dose_te;
         else if (kind == MQI_K_EDEP) v = (double) (r.dE + r.local_dE) + (double) r.te_debug;
+        else if (kind == MQI_K_LETT_NUMER || kind == MQI_K_LETT_DENOM) { if (r.len > 0.f) v = lett_hit(kind, r.dE, r.len, M.rho); }
         else if (r.len > 0.f) v = letd_hit(kind, r.dE, r.len, M.rho);
         if (!(v > 0.0)) continue;   // insert_hashtable: value <= 0 -> skip
         // quirk B2: the reference's non-stat kernel scores scorers [0, n-2) twice when n >= 3

@@ -1,0 +1,67 @@
+// tps_env -- treatment-planning front end of the B200 proton transport path: same command line
+// (one optional argument, the input-parameter file, default ./moqui_tps.in), same input keys and the
+// same output files as the reference's tests/mc/tps/tps_env.cpp:25-43, over the C ABI of
+// libmqi_b200.so.  The RTPLAN / CT DICOM inputs are replaced by a text plan and an .mha volume
+// (mqi_tps_host.hpp explains why).  `--dry-run` parses everything and prints the beam source
+// (beamlets, histories per spot, CT edges) as JSON without touching a GPU: used by the CPU tests.
+#include "mqi_tps_host.hpp"
+
+static void
+dump_json(mqib::tps_env& env) {
+    printf("{\"seed\": %d, \"n_fractions\": %d, \"sim_type\": %d, \"beams\": [", env.master_seed, env.n_fractions, (int) env.sim_type);
+    for (size_t q = 0; q < env.beam_numbers.size(); ++q) {
+        const mqib::plan_beam& b = env.plan.beams[env.beam_numbers[q] - 1];
+        env.sid = b.snout + 50;
+        std::vector<mqi_beamlet> bl;
+        std::vector<uint64_t>    nh;
+        env.build_source(b, bl, nh);
+        printf("%s{\"name\": \"%s\", \"sid\": %.9g, \"spots\": [", q ? ", " : "", b.name.c_str(), env.sid);
+        for (size_t i = 0; i < bl.size(); ++i) {
+            printf("%s{\"histories\": %llu, \"energy\": %.9g, \"sigma_energy\": %.9g, \"mean\": [", i ? ", " : "",
+                   (unsigned long long) nh[i], bl[i].energy, bl[i].sigma_energy);
+            for (int k = 0; k < 6; ++k) printf("%s%.9g", k ? ", " : "", bl[i].mean[k]);
+            printf("], \"sigma\": [");
+            for (int k = 0; k < 6; ++k) printf("%s%.9g", k ? ", " : "", bl[i].sigma[k]);
+            printf("], \"rot\": [");
+            for (int k = 0; k < 9; ++k) printf("%s%.9g", k ? ", " : "", bl[i].rot[k]);
+            printf("], \"trans\": [%.9g, %.9g, %.9g]}", bl[i].trans[0], bl[i].trans[1], bl[i].trans[2]);
+        }
+        printf("]}");
+    }
+    printf("], \"grid\": {\"n\": [%d, %d, %d], \"xe\": [%.9g, %.9g], \"ye\": [%.9g, %.9g], \"ze\": [%.9g, %.9g]}}\n", env.ct.nx, env.ct.ny,
+           env.ct.nz, env.grid.xe.front(), env.grid.xe.back(), env.grid.ye.front(), env.grid.ye.back(), env.grid.ze.front(),
+           env.grid.ze.back());
+}
+
+int
+main(int argc, char* argv[]) {
+    auto        start      = std::chrono::high_resolution_clock::now();
+    std::string input_file = "./moqui_tps.in";
+    bool        dry_run    = false;
+    for (int i = 1; i < argc; ++i) {
+        if (std::string(argv[i]) == "--dry-run") dry_run = true;
+        else if (std::string(argv[i]) == "--npz-selftest" && i + 1 < argc) {
+            // writer self-test for the CPU suite: 3 spots x 10 voxels, entries in "slot order"
+            const std::vector<uint32_t> vox { 7, 2, 9, 2, 0, 5 }, spot { 2, 0, 2, 1, 0, 2 };
+            const std::vector<double>   val { 0.5, 1.5, 2.5, 3.5, 4.5, 5.5 };
+            mqib::save_csr_npz(argv[i + 1], 3, 10, vox, spot, val);
+            return 0;
+        } else input_file = argv[i];
+    }
+    try {
+        mqib::tps_env myenv(input_file);
+        if (dry_run) {
+            printf("DRYRUN ");
+            dump_json(myenv);
+            return 0;
+        }
+        myenv.initialize_and_run();
+    } catch (const std::exception& e) {
+        std::cerr << "tps_env: " << e.what() << std::endl;
+        return 1;
+    }
+    auto                                      stop     = std::chrono::high_resolution_clock::now();
+    std::chrono::duration<double, std::milli> duration = stop - start;
+    std::cout << "Time taken by MC engine: " << duration.count() << " milli-seconds\n";
+    return 0;
+}

@@ -1193,6 +1193,20 @@ compute_hit(const ctx_t* c, int kind, const track_t* trk, uint64_t cnb) {
         if (let >= 25.0) return 0;
         return kind == MQO_SCORER_LETD_NUMER ? trk->dE * let : trk->dE * 1.0;
     }
+    case MQO_SCORER_LETT_NUMER:
+    case MQO_SCORER_LETT_DENOM: { /* LETt_weight1/2 scorers/mqi_scorer_energy_deposit.hpp:141-177 */
+        float  density = g->rho[cnb];
+        double length, let;
+        density *= 1000.0;
+        length = (trk->vtx1.pos.x - trk->vtx0.pos.x) * (trk->vtx1.pos.x - trk->vtx0.pos.x);
+        length += (trk->vtx1.pos.y - trk->vtx0.pos.y) * (trk->vtx1.pos.y - trk->vtx0.pos.y);
+        length += (trk->vtx1.pos.z - trk->vtx0.pos.z) * (trk->vtx1.pos.z - trk->vtx0.pos.z);
+        length = sqrt(length);
+        if (length <= 0) return 0.0;
+        if (kind == MQO_SCORER_LETT_DENOM) return length;
+        let = trk->dE / length / density;
+        return length * let;
+    }
     default: return 0.0;
     }
 }

@@ -33,6 +33,8 @@ extern "C" {
 #define MQO_SCORER_LETD_DENOM 3 /* LETd_weight2   :117-137 */
 #define MQO_SCORER_DOSE_SQ 4    /* dose_to_water_square :64-77 */
 #define MQO_SCORER_DIJ 5        /* dose_to_water keyed by (voxel, spot), hashed */
+#define MQO_SCORER_LETT_NUMER 6 /* LETt_weight1   :141-158 */
+#define MQO_SCORER_LETT_DENOM 7 /* LETt_weight2   :161-177 */
 
 #define MQO_QUIRK_B2_DOUBLE_SCORE 1u /* mqi_transport.hpp:204-225 scores scorers [0,n-2) twice when n>=3 */
 

@@ -11,7 +11,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 TABLES = os.path.join(ROOT, "moquimc_b200", "data", "mqi_tables_v1.bin")
 
 VARIANT_RELEASE, VARIANT_DEBUG = 0, 1
-SCORER_DOSE, SCORER_EDEP, SCORER_LETD_NUMER, SCORER_LETD_DENOM, SCORER_DOSE_SQ, SCORER_DIJ = range(6)
+SCORER_DOSE, SCORER_EDEP, SCORER_LETD_NUMER, SCORER_LETD_DENOM, SCORER_DOSE_SQ, SCORER_DIJ, SCORER_LETT_NUMER, SCORER_LETT_DENOM = range(8)
 QUIRK_B2_DOUBLE_SCORE = 1
 EMPTY = 0xFFFFFFFF
 

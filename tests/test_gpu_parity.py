@@ -217,17 +217,19 @@ def test_transport_matches_oracle_same_streams(variant):
 
 
 def test_transport_slab_heterogeneity_matches_oracle():
-    """C2-style bone / lung slabs, 150 MeV, release physics, Dose + EnergyDeposition + LETd."""
+    """C2-style bone / lung slabs, 150 MeV, release physics, Dose + EnergyDeposition + LETd + LETt."""
     hu = np.zeros((350, 200, 200), dtype=np.int16)
     hu[350 - 70:350 - 50] = 1000     # bone 50-70 mm
     hu[350 - 100:350 - 70] = -741    # lung 70-100 mm
     n = 12000   # LETd numerator is dominated by a few end-of-range steps: needs the statistics
-    kinds = (capi.SCORER_DOSE, capi.SCORER_EDEP, capi.SCORER_LETD_NUMER, capi.SCORER_LETD_DENOM)
+    kinds = (capi.SCORER_DOSE, capi.SCORER_EDEP, capi.SCORER_LETD_NUMER, capi.SCORER_LETD_DENOM, capi.SCORER_LETT_NUMER,
+             capi.SCORER_LETT_DENOM)
     e = c1_engine(capi.PHYSICS_RELEASE, hu=hu, scorers=kinds)
     e.set_beamlets([c1_beamlet(150.0, 10.0)], [n])
     e.run(seed=5, first=0, count=n)
     outs, _ = oracle_c1(O.VARIANT_RELEASE, n, 5, hu=hu, energy=150.0, spot=10.0,
-                        kinds=(O.SCORER_DOSE, O.SCORER_EDEP, O.SCORER_LETD_NUMER, O.SCORER_LETD_DENOM))
+                        kinds=(O.SCORER_DOSE, O.SCORER_EDEP, O.SCORER_LETD_NUMER, O.SCORER_LETD_DENOM, O.SCORER_LETT_NUMER,
+                               O.SCORER_LETT_DENOM))
     for s, od in enumerate(outs):
         d = e.get_dense(s)
         assert abs(d.sum() / od.sum() - 1.0) < 5e-3, s
@@ -236,8 +238,45 @@ def test_transport_slab_heterogeneity_matches_oracle():
     dose = e.get_dense(0)
     assert abs(M.r80_mm(dose.sum(axis=(1, 2))) - M.r80_mm(outs[0].sum(axis=(1, 2)))) < 0.15
     # voxel 0 is never scored (B1)
-    for s in range(4):
+    for s in range(len(kinds)):
         assert e.get_dense(s).ravel()[0] == 0.0
+
+
+def test_stopping_criterion_kernel_matches_numpy_and_buffer_entry_point():
+    """calculate_standard_deviation + calculate_stat (mqi_variables.hpp:20-48, mqi_tps_env.hpp:1409-1425) fused on
+    the device, through scorer ids and through caller-owned device buffers."""
+    n = 6000
+    e = c1_engine(capi.PHYSICS_RELEASE, scorers=(capi.SCORER_DOSE, capi.SCORER_DOSE_SQ))
+    e.set_beamlets([c1_beamlet(120.0, 4.0)], [n])
+    e.run(9, 0, n)
+    s, q = e.get_dense(0).ravel(), e.get_dense(1).ravel()
+    mean = s / n
+    var = (q / n - mean * mean) / (n - 1.0)
+    sel = mean > 0.5 * mean.max()
+    ref = (np.sqrt(np.maximum(var[sel], 0.0)) / mean[sel]).sum()
+    a = e.stat_partial(0, 1, n, 0.5)
+    np.testing.assert_allclose(a[0], ref, rtol=1e-10)
+    assert a[1] == sel.sum() and a[2] == mean.max()
+    (p0, n0), (p1, n1) = e.scorer_device_ptr(0), e.scorer_device_ptr(1)
+    assert n0 == n1 == s.size
+    b = e.stat_partial_buffers(p0, p1, n0, n, 0.5)
+    assert a == b
+
+
+def test_density_scaling_shortens_the_range():
+    """DensityScaling (robust scenarios, mqi_tps_env.hpp:768): rho *= s for every voxel.  In water the linear
+    stopping power follows rho * rsp(rho, E): +3.5 % density -> about -2.6 % range."""
+    r80 = {}
+    for sc in (1.0, 1.035, 0.965):
+        e = capi.Engine(0, physics=capi.PHYSICS_RELEASE)
+        xe, ye, ze = capi.uniform_edges(-50, 50, 200), capi.uniform_edges(-50, 50, 200), capi.uniform_edges(-350, 0, 350)
+        e.set_grid_hu(xe, ye, ze, np.zeros((350, 200, 200), dtype=np.int16), density_scale=sc)
+        e.add_scorer(capi.SCORER_DOSE, "Dose")
+        e.set_beamlets([c1_beamlet(150.0, 5.0)], [20000])
+        e.run(1, 0, 20000)
+        r80[sc] = M.r80_mm(e.get_dense(0).sum(axis=(1, 2)))
+    assert 0.970 < r80[1.035] / r80[1.0] < 0.978
+    assert 1.024 < r80[0.965] / r80[1.0] < 1.031
 
 
 def test_quirk_b2_double_scoring_and_accumulation_modes():

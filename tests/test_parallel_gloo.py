@@ -1,0 +1,145 @@
+"""Host-side multi-GPU logic (moquimc_b200/parallel.py) with two gloo ranks on CPU.
+
+The compute stand-in is the ORACLE (tests only): history h draws the same counter-based stream
+whoever transports it, so two ranks that shard a history range and sum-reduce their dense grids must
+reproduce the single-process grid to fp64 summation order -- the property the NCCL path of bench.py
+and tps_env relies on.  Also covered: whole-spot sharding for Dij (disjoint rows), the 21 robust
+scenarios round-robin, and the statistical stopping loop with per-pass all-reduces.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from moquimc_b200 import parallel as P  # noqa: E402
+
+NX, NY, NZ = 20, 20, 60
+N_HIST = 600
+
+
+def small_setup():
+    import oracle_lib as O
+    xe, ye, ze = O.uniform_edges(-20, 20, NX), O.uniform_edges(-20, 20, NY), O.uniform_edges(-120, 0, NZ)
+    rho = np.full(NX * NY * NZ, O.hu_to_density(np.array([0]))[0], dtype=np.float32)
+    g, keep = O.make_grid(xe, ye, ze, rho)
+    beamlets = [O.make_beamlet(90.0, [x0, 0, 0.5, 0, 0, -1], [3, 3, 0, 0, 0, 0], uniform=True) for x0 in (-8.0, 0.0, 8.0)]
+    return O, g, keep, beamlets, [N_HIST // 3] * 3
+
+
+def numpy_criterion(total_sum, total_sq, n, threshold=0.5):
+    """calculate_standard_deviation + calculate_stat (mqi_variables.hpp:20-48, mqi_tps_env.hpp:1409-1425)"""
+    s, q = total_sum.numpy(), total_sq.numpy()
+    mean = s / n
+    var = (q / n - mean * mean) / (n - 1.0)
+    sel = (mean > threshold * mean.max()) & (mean > 0)
+    return float((np.sqrt(np.maximum(var[sel], 0.0)) / mean[sel]).sum()), int(sel.sum())
+
+
+def worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        O, g, keep, beamlets, hps = small_setup()
+        nvox = NX * NY * NZ
+        # ---- dense scorer: shard the history range, one reduce
+        first, count = P.history_shard(N_HIST, rank, world)
+        (d,), _ = O.transport(g, O.VARIANT_RELEASE, beamlets, hps, seed=11, h0=first, n=count, kinds=[O.SCORER_DOSE])
+        grid = torch.from_numpy(np.ascontiguousarray(d.reshape(-1)))
+        P.reduce_dense(grid, dst=0)
+        if rank == 0:
+            np.save(os.path.join(out_dir, "dense.npy"), grid.numpy())
+        # ---- Dij: whole spots per rank, no reduction; rank r's rows are spots [s0, s0 + ns)
+        s0, ns, h0, nh = P.spot_shard(hps, rank, world)
+        outs, _ = O.transport(g, O.VARIANT_RELEASE, beamlets, hps, seed=11, h0=h0, n=nh, kinds=[O.SCORER_DIJ], per_spot=True,
+                              dij_capacity=400_009)
+        k1, k2, v = outs[0]["key1"], outs[0]["key2"], outs[0]["value"]
+        assert len(k2) and k2.min() >= s0 and k2.max() < s0 + ns
+        np.savez(os.path.join(out_dir, "dij_%d.npz" % rank), k1=k1, k2=k2, v=v)
+        # ---- statistical stopping: fresh streams per pass, per-pass all-reduce, identical decision on all ranks
+
+        def transport_pass(k, pass_sum, pass_sq):
+            (a, b), _ = O.transport(g, O.VARIANT_RELEASE, beamlets, hps, seed=100 + k, h0=first, n=count,
+                                    kinds=[O.SCORER_DOSE, O.SCORER_DOSE_SQ])
+            pass_sum += torch.from_numpy(np.ascontiguousarray(a.reshape(-1)))
+            pass_sq += torch.from_numpy(np.ascontiguousarray(b.reshape(-1)))
+            return count
+        z = lambda: torch.zeros(nvox, dtype=torch.float64)   # noqa: E731
+        loop = P.StoppingLoop(60.0, transport_pass, numpy_criterion, max_passes=6)
+        ts, tq = z(), z()
+        tracked, current, passes = loop.run(z(), z(), ts, tq)
+        np.save(os.path.join(out_dir, "stat_%d.npy" % rank), np.array([tracked, current, passes] + loop.history))
+        if rank == 0:
+            np.save(os.path.join(out_dir, "stat_sum.npy"), ts.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.fixture(scope="module")
+def two_rank_outputs(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("gloo"))
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(worker, args=(2, port, out), nprocs=2, join=True)
+    return out
+
+
+def test_shard_helpers():
+    for n, w in ((10, 3), (7, 8), (10**9 + 7, 8)):
+        parts = [P.history_shard(n, r, w) for r in range(w)]
+        assert parts[0][0] == 0 and sum(c for _, c in parts) == n
+        assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+    hps = [5, 0, 7, 3, 9]
+    parts = [P.spot_shard(hps, r, 2) for r in range(2)]
+    assert parts == [(0, 2, 0, 5), (2, 3, 5, 19)]
+    sc = P.robust_scenarios()
+    assert len(sc) == 21 and sc[0] == {"XShift": 0.0, "YShift": 0.0, "ZShift": 0.0, "DensityScaling": 1.0}
+    assert sorted(sum((P.scenario_shard(21, r, 8) for r in range(8)), [])) == list(range(21))
+    assert max(len(P.scenario_shard(21, r, 8)) for r in range(8)) == 3
+
+
+def test_sharded_dense_dose_equals_single_process(two_rank_outputs):
+    O, g, keep, beamlets, hps = small_setup()
+    (d,), _ = O.transport(g, O.VARIANT_RELEASE, beamlets, hps, seed=11, h0=0, n=N_HIST, kinds=[O.SCORER_DOSE])
+    got = np.load(os.path.join(two_rank_outputs, "dense.npy"))
+    assert d.sum() > 0
+    np.testing.assert_allclose(got, d.reshape(-1), rtol=1e-12, atol=d.max() * 1e-14)
+
+
+def test_spot_sharded_dij_rows_are_disjoint_and_complete(two_rank_outputs):
+    O, g, keep, beamlets, hps = small_setup()
+    outs, _ = O.transport(g, O.VARIANT_RELEASE, beamlets, hps, seed=11, h0=0, n=N_HIST, kinds=[O.SCORER_DIJ], per_spot=True,
+                          dij_capacity=400_009)
+    k1, k2, v = outs[0]["key1"], outs[0]["key2"], outs[0]["value"]
+    ref = {(int(a), int(b)): float(c) for a, b, c in zip(k1, k2, v)}
+    got = {}
+    for r in range(2):
+        z = np.load(os.path.join(two_rank_outputs, "dij_%d.npz" % r))
+        for a, b, c in zip(z["k1"], z["k2"], z["v"]):
+            assert (int(a), int(b)) not in got           # disjoint: concatenation, no reduction
+            got[(int(a), int(b))] = float(c)
+    assert got.keys() == ref.keys()
+    np.testing.assert_allclose([got[k] for k in sorted(ref)], [ref[k] for k in sorted(ref)], rtol=1e-12)
+
+
+def test_stopping_loop_is_consistent_across_ranks(two_rank_outputs):
+    a = np.load(os.path.join(two_rank_outputs, "stat_0.npy"))
+    b = np.load(os.path.join(two_rank_outputs, "stat_1.npy"))
+    np.testing.assert_array_equal(a, b)                  # same totals => same decision on every rank
+    tracked, current, passes = a[:3]
+    hist = a[3:]
+    assert passes == len(hist) >= 1 and tracked == passes * N_HIST
+    assert (current <= 60.0) or passes == 6
+    assert all(x >= y * 0.8 for x, y in zip(hist, hist[1:]))
+    # the running total equals a single-process accumulation of the same passes
+    O, g, keep, beamlets, hps = small_setup()
+    tot = np.zeros(NX * NY * NZ)
+    for k in range(int(passes)):
+        (d,), _ = O.transport(g, O.VARIANT_RELEASE, beamlets, hps, seed=100 + k, h0=0, n=N_HIST, kinds=[O.SCORER_DOSE])
+        tot += d.reshape(-1)
+    np.testing.assert_allclose(np.load(os.path.join(two_rank_outputs, "stat_sum.npy")), tot, rtol=1e-12, atol=tot.max() * 1e-14)

@@ -1,0 +1,177 @@
+"""Host side of the treatment-planning front end (moquimc_b200/bin/tps_env, csrc/mqi_tps_host.hpp),
+checked on CPU through `tps_env --dry-run`, which parses the input-parameter file, the .mha CT, the
+generic PBS beam-model file and the text plan and prints the resulting beam source as JSON.
+
+The expected values are a numpy restatement of the reference's formulas (file:line under
+/root/reference/moqui) -- the reference's own tps_env cannot be built here (GDCM missing, SURVEY.md
+section 8c), so this part of the boundary is pinned by restatement only:
+  pbs::characterize_beamlet   base/mqi_treatment_machine_pbs.hpp:238-276 (fp32, intpl :94-96)
+  pbs::characterize_history   :134-143
+  beam_starting_position      base/mqi_treatment_machine_ion.hpp:324-333
+  coordinate_transform        base/mqi_coordinate_transform.hpp:52-58, create_coordinate_transform tmi:42-70
+  CT edges                    base/environments/mqi_tps_env.hpp:468-531
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from moquimc_b200 import synthetic as S  # noqa: E402
+
+EXE = os.path.join(ROOT, "moquimc_b200", "bin", "tps_env")
+f32 = np.float32
+
+
+def dry_run(inp, expect_fail=False):
+    r = subprocess.run([EXE, "--dry-run", inp], capture_output=True, text=True, timeout=120)
+    if expect_fail:
+        assert r.returncode != 0, r.stdout
+        return r.stderr
+    assert r.returncode == 0, r.stderr
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("DRYRUN ")][-1]
+    return json.loads(line[len("DRYRUN "):])
+
+
+def intpl(x, x0, x1, y0, y1):
+    x, x0, x1, y0, y1 = map(f32, (x, x0, x1, y0, y1))
+    return y0 if x1 == x0 else f32(y0 + f32(f32(f32(x - x0) * f32(y1 - y0)) / f32(x1 - x0)))
+
+
+def expected_spot(rows, spot, sid, sad, pph):
+    """rows: beam-model [spot] table; spot = (e, x, y, meterset)"""
+    e, x, y, w = map(f32, spot)
+    keys = [f32(r[0]) for r in rows]
+    up = next(i for i, k in enumerate(keys) if k >= e)          # std::map::lower_bound
+    up = max(up, 1)
+    dn = up - 1
+    D, U = [f32(v) for v in rows[dn]], [f32(v) for v in rows[up]]
+    mid_e = intpl(e, D[0], U[0], D[1], U[1])                      # x axis = nominal energies
+    mids = [intpl(e, D[1], U[1], D[c], U[c]) for c in (2, 3, 4, 5, 6)]   # x axis = down.E / up.E (as the reference)
+    ratio = intpl(e, D[0], U[0], D[7], U[7])
+    z = f32(sid)
+    bx = f32(f32(x * f32(f32(sad[0]) - z)) / f32(sad[0]))
+    by = f32(f32(y * f32(f32(sad[1]) - z)) / f32(sad[1]))
+    d = np.array([x - bx, y - by, f32(0) - z], dtype=f32)
+    d = d / f32(np.sqrt(f32(d[0] * d[0] + d[1] * d[1] + d[2] * d[2])))
+    return {"energy": mid_e, "sigma_energy": mids[0], "mean": [bx, by, z, d[0], d[1], d[2]],
+            "sigma": [mids[1], mids[2], 0, mids[3], mids[4], 0], "histories": int(f32(f32(w * ratio) / f32(pph)))}
+
+
+def rot_matrix(collimator, gantry, couch):
+    """iec2dicom(90 deg about x) * couch(about z, sign flipped) * gantry(about y) * collimator(about z),
+    each mat3x3(a, b, c) = identity rotated about x, y, z (mqi_matrix.hpp:69-76, 214-273)"""
+    def rx(a):
+        c, s = np.cos(a), np.sin(a)
+        return np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
+
+    def ry(a):
+        c, s = np.cos(a), np.sin(a)
+        return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+
+    def rz(a):
+        c, s = np.cos(a), np.sin(a)
+        return np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])
+    d = np.pi / 180.0
+    return rx(90 * d) @ rz(-couch * d) @ ry(gantry * d) @ rz(collimator * d)
+
+
+@pytest.fixture(scope="module")
+def case(tmp_path_factory):
+    root = str(tmp_path_factory.mktemp("tps"))
+    inp = S.make_case(root, beams=2, ParticlesPerHistory=2.5e4, XShift=1.5, YShift=-2.0, ZShift=0.25)
+    return root, inp
+
+
+def test_beam_source_matches_reference_formulas(case):
+    root, inp = case
+    out = dry_run(inp)
+    rows = S.beam_model_rows()
+    assert [b["name"] for b in out["beams"]] == ["G000", "G090"]
+    for bi, beam in enumerate(out["beams"]):
+        spots = S.spot_list(n_layers=4, pitch=10.0, half_width=20.0, seed=1 + bi)
+        assert beam["sid"] == 300.0 and len(beam["spots"]) == len(spots)
+        R = rot_matrix(0.0, 90.0 * bi, 0.0)
+        for got, sp in zip(beam["spots"], spots):
+            sp = tuple(float("%.6g" % v) for v in sp[:3]) + (float("%.8g" % sp[3]),)   # as written to the plan file
+            exp = expected_spot(rows, sp, 300.0, (2000.0, 1800.0), 2.5e4)
+            assert got["histories"] == exp["histories"]
+            np.testing.assert_allclose(got["energy"], exp["energy"], rtol=3e-7)
+            np.testing.assert_allclose(got["sigma_energy"], exp["sigma_energy"], rtol=3e-6)
+            np.testing.assert_allclose(got["mean"], exp["mean"], rtol=3e-6, atol=1e-6)
+            np.testing.assert_allclose(got["sigma"], exp["sigma"], rtol=3e-6)
+            np.testing.assert_allclose(np.array(got["rot"]).reshape(3, 3), R, atol=2e-7)
+            assert got["trans"] == [0.0, 0.0, 0.0]
+
+
+def test_ct_edges_follow_the_reference_rule(case):
+    root, inp = case
+    g = dry_run(inp)["grid"]
+    assert g["n"] == [64, 64, 40]
+    # origin = centre of voxel 0; first edge = centre - spacing / 2 + shift; last = first + n * spacing (fp32)
+    x0 = f32(f32(-(64 - 1) / 2.0 * 4.0) - f32(4.0) / 2.0) + f32(1.5)
+    y0 = f32(f32(-(64 - 1) / 2.0 * 4.0) - f32(4.0) / 2.0) + f32(-2.0)
+    z0 = f32(f32(-(40 - 1) / 2.0 * 6.0) - f32(6.0) / 2.0) + f32(0.25)
+    np.testing.assert_allclose(g["xe"], [x0, x0 + 64 * 4.0], rtol=1e-6)
+    np.testing.assert_allclose(g["ye"], [y0, y0 + 64 * 4.0], rtol=1e-6)
+    np.testing.assert_allclose(g["ze"], [z0, z0 + 40 * 6.0], rtol=1e-6)
+
+
+def write_variant(root, name, **kw):
+    p = os.path.join(root, name)
+    S.write_input(p, root, os.path.join(root, "out_" + name), **kw)
+    return p
+
+
+def test_parser_semantics(case):
+    root, _ = case
+    # keys are case-insensitive, text after '#' is dropped, vectors split on commas
+    p = os.path.join(root, "mixed.in")
+    with open(p, "w") as f:
+        f.write("# comment line\n\ngpuid 0\nRANDOMSEED 77 # trailing comment\nParentDir %s\nDicomDir .\nCTVolumeName ct.mha\n"
+                "PlanFile plan.txt\nscorer Dose , LETd\nMachine pbs:machine.txt\nOutputDir %s\nOverwriteResults TRUE\n"
+                "ParticlesPerHistory 1e5\nBeamNumbers 2\n" % (root, os.path.join(root, "o1")))
+    out = dry_run(p)
+    assert out["seed"] == 77 and out["n_fractions"] == 30 and [b["name"] for b in out["beams"]] == ["G090"]
+    # Dij forces per-spot simulation and cannot be combined (mqi_tps_env.hpp:213-220)
+    assert dry_run(write_variant(root, "dij.in", Scorer="Dij", UnitWeights=100))["sim_type"] == 1
+    assert "Dij cannot be scored" in dry_run(write_variant(root, "dij2.in", Scorer="Dose,Dij"), expect_fail=True)
+    assert "Unrecognized scorer name" in dry_run(write_variant(root, "bad.in", Scorer="Fluence"), expect_fail=True)
+    assert "Valid machine is not available" in dry_run(write_variant(root, "m.in", Machine="gtr1:x"), expect_fail=True)
+    assert "threshold cannot be zero" in dry_run(write_variant(root, "st.in", StoppingStatistics="true", StoppingCriteria=1.0),
+                                                 expect_fail=True)
+    assert "no GDCM" in dry_run(write_variant(root, "rs.in", ReadStructure="true"), expect_fail=True)
+    # UnitWeights overrides the histories of every spot in a per-spot run (:1488-1491)
+    out = dry_run(write_variant(root, "uw.in", Scorer="Dij", UnitWeights=321))
+    assert {s["histories"] for s in out["beams"][0]["spots"]} == {321}
+
+
+def test_output_directory_guard(case):
+    root, _ = case
+    od = os.path.join(root, "exists")
+    os.makedirs(od, exist_ok=True)
+    p = os.path.join(root, "guard.in")
+    S.write_input(p, root, od, OverwriteResults="false")
+    assert "Output directory exists" in dry_run(p, expect_fail=True)
+
+
+def test_npz_writer_is_a_scipy_csr(tmp_path):
+    import scipy.sparse as sp
+    path = str(tmp_path / "dij.npz")
+    subprocess.run([EXE, "--npz-selftest", path], check=True, timeout=60)
+    z = np.load(path)
+    assert sorted(z.files) == ["data", "format", "indices", "indptr", "shape"]
+    assert z["indices"].dtype == np.uint32 and z["indptr"].dtype == np.uint32 and z["shape"].dtype == np.uint32
+    assert z["data"].dtype == np.float64 and z["format"].tobytes() == b"csr"
+    assert z["shape"].tolist() == [3, 10] and z["indptr"].tolist() == [0, 2, 3, 6]
+    # columns inside a row keep the table-slot order of the triplets, like the reference's single scan
+    assert z["indices"].tolist() == [2, 0, 2, 7, 9, 5]
+    m = sp.load_npz(path)
+    dense = np.zeros((3, 10))
+    for v, s, x in zip([7, 2, 9, 2, 0, 5], [2, 0, 2, 1, 0, 2], [0.5, 1.5, 2.5, 3.5, 4.5, 5.5]):
+        dense[s, v] += x
+    np.testing.assert_array_equal(m.toarray(), dense)
