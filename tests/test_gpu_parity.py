@@ -449,6 +449,52 @@ def test_c1_dose_against_reference_golden(golden_dir, variant):
         < 3e-3 * gold["water_dE_total_reb"].max()
 
 
+@pytest.mark.parametrize("energy", [70, 150, 230])
+def test_c2_slabs_dose_and_letd_against_reference_golden(golden_dir, energy):
+    """Config C2: bone / lung slabs, energy sweep, Dose + LETd, release physics, against the reference's own CPU
+    run (tests/golden/c2_slabs<E>_release.npz from oracle/ref_harness.cpp, 1e6 histories).  The reference scores
+    Dose twice per step when three scorers are attached (quirk B2): reproduced with MQI_QUIRK_B2_DOUBLE_SCORE."""
+    path = os.path.join(golden_dir, "c2_slabs%d_release.npz" % energy)
+    if not os.path.exists(path):
+        pytest.skip("golden not generated")
+    gold = np.load(path)
+    hu = np.zeros((350, 200, 200), dtype=np.int16)
+    hu[350 - 70:350 - 50] = 1000
+    hu[350 - 100:350 - 70] = -741
+    kinds = (capi.SCORER_DOSE, capi.SCORER_LETD_NUMER, capi.SCORER_LETD_DENOM)
+    e = c1_engine(capi.PHYSICS_RELEASE, hu=hu, scorers=kinds, quirks=capi.QUIRK_B2_DOUBLE_SCORE)
+    n_total, n_batches = 4_000_000, 8
+    per = n_total // n_batches
+    e.set_beamlets([c1_beamlet(float(energy), 10.0)], [n_total])
+    idd = {k: [] for k in range(3)}
+    xz = np.zeros((350, 200))
+    for b in range(n_batches):
+        e.clear_scorers()
+        e.run(31337, b * per, per)
+        for k in range(3):
+            d = e.get_dense(k) / per
+            idd[k].append(d.sum(axis=(1, 2)))
+            if k == 0:
+                xz += d.sum(axis=1) / n_batches
+    mean = {k: np.mean(idd[k], axis=0) for k in idd}
+    se = {k: np.std(idd[k], axis=0, ddof=1) / np.sqrt(n_batches) for k in idd}
+    g_idd = gold["Dose_idd"]
+    assert abs(M.r80_mm(mean[0]) - M.r80_mm(g_idd)) < 0.1
+    assert abs(mean[0].sum() / float(gold["Dose_total"]) - 1.0) < 3e-3
+    rate, _, _ = M.gamma_1d(g_idd, mean[0], 1.0)
+    assert rate >= 0.99, rate
+    rate, _, _ = M.gamma_2d(gold["Dose_xz"], xz, (1.0, 0.5))
+    assert rate >= 0.99, rate
+    frac, _ = M.fraction_within_sigma(g_idd, gold["Dose_idd_se"], mean[0], se[0])
+    assert frac >= 0.90, frac
+    # dose-averaged LET per depth = numer / denom where the beam deposits (above 5 % of the denominator's maximum)
+    gn, gd = gold["LETd_numer_idd"], gold["LETd_denom_idd"]
+    m = gd > 0.05 * gd.max()
+    let_ref, let_gpu = gn[m] / gd[m], mean[1][m] / mean[2][m]
+    assert np.abs(let_gpu / let_ref - 1.0).max() < 0.03, np.abs(let_gpu / let_ref - 1.0).max()
+    assert abs(mean[2].sum() / float(gold["LETd_denom_total"]) - 1.0) < 3e-3
+
+
 def test_history_partition_is_reproducible_and_additive():
     """Multi-GPU contract (subsystem 5): disjoint history ranges are independent streams, so two
     half-runs accumulate to the same dose as one full run (up to fp64 summation order)."""

@@ -31,3 +31,31 @@ def test_oracle_transport_matches_reference_golden_dose(golden_dir, name, varian
     # with __PHYSICS_DEBUG__ (delta daughters are separate steps), ~388 without
     assert abs(st.steps / n - (446.3 if name == "debug" else 388.0)) < 3.0
     assert d.ravel()[0] == 0.0   # voxel 0 is never scored (B1)
+
+
+def test_oracle_slab_transport_and_letd_match_reference_golden(golden_dir):
+    """Config C2 at 150 MeV (bone / lung slabs, release physics, Dose + LETd with the reference's double scoring
+    of Dose, quirk B2): restatement vs the reference's own CPU run (tests/golden/c2_slabs150_release.npz)."""
+    gold = np.load(os.path.join(golden_dir, "c2_slabs150_release.npz"))
+    xe, ye, ze = O.uniform_edges(-50, 50, 200), O.uniform_edges(-50, 50, 200), O.uniform_edges(-350, 0, 350)
+    hu = np.zeros((350, 200, 200), dtype=np.int64)
+    hu[350 - 70:350 - 50] = 1000
+    hu[350 - 100:350 - 70] = -741
+    rho = O.hu_to_density(np.arange(-1000, 2996))[hu.ravel() + 1000].astype(np.float32)
+    g, keep = O.make_grid(xe, ye, ze, rho)
+    b = O.make_beamlet(150.0, [0, 0, 0.5, 0, 0, -1], [10, 10, 0, 0, 0, 0], uniform=True)
+    n = 20000
+    (d, num, den), st = O.transport(g, O.VARIANT_RELEASE, [b], [n], seed=8, h0=0, n=n, quirks=O.QUIRK_B2_DOUBLE_SCORE,
+                                    kinds=[O.SCORER_DOSE, O.SCORER_LETD_NUMER, O.SCORER_LETD_DENOM])
+    idd = d.reshape(350, 200, 200).sum(axis=(1, 2)) / n
+    assert abs(M.r80_mm(idd) - M.r80_mm(gold["Dose_idd"])) < 0.15
+    assert abs(idd.sum() / float(gold["Dose_total"]) - 1.0) < 5e-3
+    rate, _, _ = M.gamma_1d(gold["Dose_idd"], idd, 1.0)
+    assert rate >= 0.99
+    ni, di = num.reshape(350, -1).sum(axis=1) / n, den.reshape(350, -1).sum(axis=1) / n
+    # dose-averaged LET in 10 mm depth bins (2e4 histories: single 1 mm bins are dominated by a few high-LET steps)
+    gn, gd = gold["LETd_numer_idd"], gold["LETd_denom_idd"]
+    r10 = lambda a: a.reshape(35, 10).sum(axis=1)   # noqa: E731
+    m = r10(gd) > 0.2 * r10(gd).max()
+    assert np.abs((r10(ni)[m] / r10(di)[m]) / (r10(gn)[m] / r10(gd)[m]) - 1.0).max() < 0.04
+    assert abs(di.sum() / float(gold["LETd_denom_total"]) - 1.0) < 5e-3
