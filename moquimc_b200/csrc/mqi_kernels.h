@@ -24,11 +24,7 @@
 #define MQI_K_BLOCK 256
 #endif
 #ifndef MQI_K_MIN_BLOCKS
-#define MQI_K_MIN_BLOCKS 4   /* 64 registers/thread: measured best of 2/3/4 on B200 (profiles/) */
-#endif
-
-#ifndef MQI_K_SYNC
-#define MQI_K_SYNC 0   /* per-iteration CTA (1) / sub-partition (2) barrier in the transport loop: see profiles/ */
+#define MQI_K_MIN_BLOCKS 3   /* <= 85 registers/thread, 24 warps/SM: measured best of 2/3/4 CTAs of 256 and 8 of 128 on B200 (profiles/r1_experiments.md) */
 #endif
 
 #ifndef MQI_K_LATE_LUT

@@ -401,8 +401,9 @@ score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, 
 // locate the start cell (index(p, dir) or entry intersect), mqi_transport.hpp:146-190
 // ---------------------------------------------------------------------------------------------
 struct LaneIO {
-    float    px, py, pz, dx, dy, dz, ke, ke1_off, dE_pre;
+    float    px, py, pz, dx, dy, dz, ke;
     int      ix, iy, iz;
+    int      recoil;   // debug recoil daughter before its first step: vtx1.ke = 0 and trk.dE = vtx0.ke
     uint32_t spot_ind, h0, h1, blk;
     int      sp;
     unsigned n_done;
@@ -427,11 +428,13 @@ rearm_lane(const Params& P, Secondary* stack, LaneIO& L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int  nx = P.g.nx, ny = P.g.ny, nz = P.g.nz;
     const Smem sm = smem_view(smem_raw, nx, ny);
-    float px, py, pz, dx, dy, dz, ke, ke1_off, dE_pre;
+    float px, py, pz, dx, dy, dz, ke;
+    bool  recoil;
     if (L.sp > 0) {
         const Secondary& s = stack[--L.sp];
         px = s.px; py = s.py; pz = s.pz; dx = s.dx; dy = s.dy; dz = s.dz;
-        ke = s.ke0; ke1_off = s.ke1_off; dE_pre = s.dE_pre;
+        ke = s.ke0;
+        recoil = s.ke1_off != 0.f;   // pushed as (ke0, -ke0, ke0) by the debug variant only
     } else {
         const unsigned long long i = atomicAdd(P.counters + C_NEXT, 1ull);
         if (i >= P.count) return REARM_EXIT;
@@ -459,8 +462,7 @@ rearm_lane(const Params& P, Secondary* stack, LaneIO& L) {
         dx = v.dir[0]; dy = v.dir[1]; dz = v.dir[2];
         ke = v.ke;
         L.spot_ind = P.per_spot ? spot : kEmptyKey32;
-        ke1_off    = 0.f;
-        dE_pre     = 0.f;
+        recoil     = false;
         ++L.n_done;
     }
     // world -> node frame, mqi_transport.hpp:165-170
@@ -506,9 +508,8 @@ rearm_lane(const Params& P, Secondary* stack, LaneIO& L) {
             px = __fadd_rn(px, __fmul_rn(d[0], dist));
             py = __fadd_rn(py, __fmul_rn(d[1], dist));
             pz = __fadd_rn(pz, __fmul_rn(d[2], dist));
-            ke += ke1_off;
-            ke1_off = 0.f;
-            dE_pre  = 0.f;
+            if (recoil) ke = 0.f;   // vtx0.ke := vtx1.ke, and the carried energy is dropped by move()
+            recoil = false;
             if (d[0] == dx && d[1] == dy && d[2] == dz) {
                 ix = c[0]; iy = c[1]; iz = c[2];
             } else {
@@ -520,15 +521,17 @@ rearm_lane(const Params& P, Secondary* stack, LaneIO& L) {
         }
     }
     L.px = px; L.py = py; L.pz = pz; L.dx = dx; L.dy = dy; L.dz = dz;
-    L.ke = ke; L.ke1_off = ke1_off; L.dE_pre = dE_pre;
+    L.ke = ke; L.recoil = recoil ? 1 : 0;
     L.ix = ix; L.iy = iy; L.iz = iz;
     return alive ? REARM_ALIVE : REARM_MISSED;
 }
 
 // further tries of the delta-electron energy rejection loop (about one event in ten needs them):
 // (n, accept) pairs from Philox2x32-10, counter = (block, history_lo), one block number per pair
-__device__ __noinline__ float
-delta_retry(uint32_t& blk, uint32_t h0, uint32_t key2, float T_cut, float Tmax1, float b1_sq, float inv_2Et_sq) {
+// returns {Te, next block number} in registers (a reference parameter would pin the lane's block
+// counter to local memory for the whole loop)
+__device__ __noinline__ float2
+delta_retry(uint32_t blk, uint32_t h0, uint32_t key2, float T_cut, float Tmax1, float b1_sq, float inv_2Et_sq) {
     const float inv_Tmax1 = 1.0f / Tmax1;
     while (true) {
         uint32_t wn, wa;
@@ -536,7 +539,7 @@ delta_retry(uint32_t& blk, uint32_t h0, uint32_t key2, float T_cut, float Tmax1,
         blk += 1;
         const float n  = u32_to_uniform(wn);
         const float Te = T_cut * Tmax1 / ((1.0f - n) * Tmax1 + n * T_cut);
-        if (u32_to_uniform(wa) < 1.0f - b1_sq * Te * inv_Tmax1 + Te * Te * inv_2Et_sq) return Te;
+        if (u32_to_uniform(wa) < 1.0f - b1_sq * Te * inv_Tmax1 + Te * Te * inv_2Et_sq) return make_float2(Te, __uint_as_float(blk));
     }
 }
 
@@ -571,7 +574,8 @@ transport_kernel(const __grid_constant__ Params P) {
     int       sp = 0;
 
     // lane state
-    float    px = 0, py = 0, pz = 0, dx = 0, dy = 0, dz = 0, ke = 0, ke1_off = 0, dE_pre = 0;
+    float    px = 0, py = 0, pz = 0, dx = 0, dy = 0, dz = 0, ke = 0;
+    bool     recoil = false;   // see LaneIO::recoil (always false in the release variant)
     int      ix = 0, iy = 0, iz = 0;
     bool     alive = false;
     uint32_t spot_ind = kEmptyKey32;
@@ -579,43 +583,31 @@ transport_kernel(const __grid_constant__ Params P) {
     const uint32_t k0 = (uint32_t) P.seed, k1 = (uint32_t) (P.seed >> 32);
     unsigned n_steps = 0, n_done = 0, n_sec = 0, n_ovf = 0;
 
-#if MQI_K_SYNC
+    // Warp-level reconvergence.  The re-arm below is executed by the few lanes whose track just ended;
+    // without an explicit join the compiler only reconverges them at the END of the iteration, i.e. the
+    // whole step body ran twice per re-arm (once for the re-armed lane alone: 13 % of all issue slots in
+    // ncu).  The full-warp vote after the re-arm is the join: every lane executes it once per turn, and
+    // the warp leaves the loop together once all of its lanes found the history counter exhausted.
     bool done = false;   // this lane found the history counter exhausted
-#endif
     while (true) {
-#if MQI_K_SYNC == 1
-        // keep the warps of the CTA on the same stretch of the loop body (instruction-cache locality)
-        if (__syncthreads_and(done)) break;
-        if (done) continue;
-#elif MQI_K_SYNC == 2
-        // same, but only among the warps that share an SM sub-partition (warp id mod 4)
-        {
-            unsigned all_done;
-            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbarrier.red.and.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(all_done) : "r"((unsigned) done), "r"(1u + ((threadIdx.x >> 5) & 3u)), "r"((unsigned) (MQI_K_BLOCK / 4)) : "memory");
-            if (all_done) break;
-        }
-        if (done) continue;
-#endif
         // ------------------------------------------------------------------ re-arm the lane
-        if (!alive) {
+        if (!alive && !done) {
             LaneIO L;
             L.sp = sp; L.h0 = h0; L.h1 = h1; L.blk = blk; L.spot_ind = spot_ind; L.n_done = 0;
             const int rc = rearm_lane(P, stack, L);
             sp = L.sp;
             n_done += L.n_done;
-#if MQI_K_SYNC
-            if (rc == REARM_EXIT) { done = true; continue; }
-#else
-            if (rc == REARM_EXIT) break;
-#endif
-            h0 = L.h0; h1 = L.h1; blk = L.blk; spot_ind = L.spot_ind;
-            px = L.px; py = L.py; pz = L.pz; dx = L.dx; dy = L.dy; dz = L.dz;
-            ke = L.ke; ke1_off = L.ke1_off; dE_pre = L.dE_pre;
-            ix = L.ix; iy = L.iy; iz = L.iz;
-            alive = rc == REARM_ALIVE;
-            if (!alive) continue;
+            done = rc == REARM_EXIT;
+            if (!done) {
+                h0 = L.h0; h1 = L.h1; blk = L.blk; spot_ind = L.spot_ind;
+                px = L.px; py = L.py; pz = L.pz; dx = L.dx; dy = L.dy; dz = L.dz;
+                ke = L.ke; recoil = VARIANT == MQI_K_DEBUG && L.recoil != 0;
+                ix = L.ix; iy = L.iy; iz = L.iz;
+                alive = rc == REARM_ALIVE;   // REARM_MISSED: the track never enters the grid, fetch again next turn
+            }
         }
+        if (__all_sync(0xffffffffu, done)) break;
+        if (!alive) continue;   // taken after the join: the lane idles this turn, the others are converged
 
         // ------------------------------------------------------------------ one voxel step
         ++n_steps;
@@ -677,19 +669,19 @@ transport_kernel(const __grid_constant__ Params P) {
         // (rho > 99.9: mqi_fippel_physics.hpp:81-85): the track ends without scoring
         if (!(d2b > 0.f) || rho > 99.9f) {
             alive = false;
-            continue;
+            continue;   // rare; the lane rejoins at the ballot of the next turn
         }
 
         bool  stopped = false;
         float p1x, p1y, p1z;              // vtx1.pos
-        float ke1 = ke + ke1_off;         // vtx1.ke
+        float ke1 = recoil ? 0.f : ke;    // vtx1.ke
 
         if (rho < 1.0e-7f) {
             // vacuum: move to the boundary, nothing to score (mqi_fippel_physics.hpp:77-80)
             p1x = px + dx * d2b; p1y = py + dy * d2b; p1z = pz + dz * d2b;
         } else {
             StepResult res;
-            res.dE = dE_pre; res.local_dE = 0.f; res.te_debug = 0.f; res.len = 0.f;
+            res.dE = recoil ? ke : 0.f; res.local_dE = 0.f; res.te_debug = 0.f; res.len = 0.f;
             float rsp0;
             if (ke <= kTpCut) {
                 // below the tracking cut: dump the energy, :86-94 + last_step mqi_p_ionization.hpp:482-490
@@ -785,8 +777,11 @@ transport_kernel(const __grid_constant__ Params P) {
                         const float inv_2Et_sq = 0.5f / (Et1 * Et1);
                         const float n  = fminf(u / c0, 1.0f);
                         float       Te = T_cut * Tmax1 / ((1.0f - n) * Tmax1 + n * T_cut);
-                        if (!(spare_bytes_to_uniform(w[0], w[1], w[2]) < 1.0f - b1_sq * Te / Tmax1 + Te * Te * inv_2Et_sq))
-                            Te = delta_retry(blk, h0, k0 ^ (k1 * 0x85EBCA6Bu) ^ (h1 * 0xC2B2AE35u), T_cut, Tmax1, b1_sq, inv_2Et_sq);
+                        if (!(spare_bytes_to_uniform(w[0], w[1], w[2]) < 1.0f - b1_sq * Te / Tmax1 + Te * Te * inv_2Et_sq)) {
+                            const float2 rt = delta_retry(blk, h0, k0 ^ (k1 * 0x85EBCA6Bu) ^ (h1 * 0xC2B2AE35u), T_cut, Tmax1, b1_sq, inv_2Et_sq);
+                            Te  = rt.x;
+                            blk = __float_as_uint(rt.y);
+                        }
                         if (VARIANT == MQI_K_DEBUG) res.te_debug = Te;   // carried by a zero-energy daughter
                         else res.dE += Te;
                         ke1 -= Te;
@@ -836,8 +831,7 @@ transport_kernel(const __grid_constant__ Params P) {
             px = p1x; py = p1y; pz = p1z;
             dx = d1x; dy = d1y; dz = d1z;
             ke = ke1;
-            ke1_off = 0.f;
-            dE_pre  = 0.f;
+            recoil = false;
             if ((unsigned) ix >= (unsigned) nx || (unsigned) iy >= (unsigned) ny || (unsigned) iz >= (unsigned) nz) alive = false;
         }
     }

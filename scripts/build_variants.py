@@ -7,9 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from moquimc_b200 import build as B
 
 VARIANTS = {
-    "b256_s0": (256, 4, 0), "b256_s1": (256, 4, 1), "b256_s2": (256, 4, 2),
-    "b512_s0": (512, 2, 0), "b512_s1": (512, 2, 1), "b512_s2": (512, 2, 2),
-    "b1024_s1": (1024, 1, 1), "b1024_s2": (1024, 1, 2),
+    "b256": (256, 4, 0), "b512": (512, 2, 0), "b128": (128, 8, 0), "b256_3": (256, 3, 0),
     "early_lut": (256, 4, 0, "-DMQI_K_LATE_LUT=0"), "base": (256, 4, 0),
 }
 
@@ -21,7 +19,7 @@ def main(names):
     procs = []
     for n in names:
         blk, mb, sync = VARIANTS[n][:3]
-        cmd = [B.nvcc()] + B.NVCC_FLAGS + list(VARIANTS[n][3:]) + ["-DMQI_K_BLOCK=%d" % blk, "-DMQI_K_MIN_BLOCKS=%d" % mb, "-DMQI_K_SYNC=%d" % sync,
+        cmd = [B.nvcc()] + B.NVCC_FLAGS + list(VARIANTS[n][3:]) + ["-DMQI_K_BLOCK=%d" % blk, "-DMQI_K_MIN_BLOCKS=%d" % mb, 
                                            "-shared", "-o", os.path.join(out, "libmqi_%s.so" % n)] + cu + ["-ldl"]
         procs.append(subprocess.Popen(cmd))
     for p in procs:

@@ -492,7 +492,12 @@ def test_c2_slabs_dose_and_letd_against_reference_golden(golden_dir, energy):
     gn, gd = gold["LETd_numer_idd"], gold["LETd_denom_idd"]
     m = gd > 0.10 * gd.max()
     let_ref, let_gpu = gn[m] / gd[m], mean[1][m] / mean[2][m]
-    assert np.abs(let_gpu / let_ref - 1.0).max() < 0.03, np.abs(let_gpu / let_ref - 1.0).max()
+    # 3 %, or 4 sigma of the numerators' batch errors where a single depth bin is noisier than that (the LETd
+    # numerator is heavy-tailed: a few delta-electron steps dominate a bin)
+    rel_sigma = np.sqrt((gold["LETd_numer_idd_se"][m] / gn[m]) ** 2 + (se[1][m] / mean[1][m]) ** 2)
+    dev = np.abs(let_gpu / let_ref - 1.0)
+    assert (dev < np.maximum(0.03, 4.0 * rel_sigma)).all(), (dev.max(), rel_sigma[dev.argmax()])
+    assert np.median(dev) < 0.005
     assert abs(mean[2].sum() / float(gold["LETd_denom_total"]) - 1.0) < 3e-3
 
 
