@@ -129,6 +129,25 @@ MQI_API int mqi_add_scorer(mqi_handle* h, int kind, const char* name, uint64_t c
 /* Let a dense scorer accumulate into caller-owned device memory (nvox doubles), e.g. a torch tensor
  * that is then reduced with NCCL.  The buffer is NOT cleared. */
 MQI_API int mqi_bind_scorer_buffer(mqi_handle* h, int scorer, void* d_buffer);
+/* Region of interest of a scorer: roi_t(CONTOUR) built by mask_reader::mask_to_roi from the summed 0/1
+ * mask volumes (moqui/base/mqi_file_handler.hpp:107-113,176-217; mqi_roi.hpp:48-58,127-137; used by
+ * ScoringMask / StatROIMaskFilename, mqi_tps_env.hpp:776-812).  mask_total: host pointer, one byte per
+ * voxel of the scored grid ([nz][ny][nx]); a step is scored only if its voxel lies inside a run of the
+ * mask.  NULL restores roi_t(DIRECT) (every voxel but voxel 0).  roi_size (optional)
+ * receives get_mask_size().  Must be called after mqi_set_grid_*; a new grid drops the roi. */
+MQI_API int mqi_set_scorer_roi(mqi_handle* h, int scorer, const uint8_t* mask_total, uint64_t n_voxels,
+                       uint64_t* roi_size);
+/* Beamline children of the world in front of the scored grid, in transport order: the range shifter
+ * slab and the voxelised aperture of create_rangeshifter / create_voxelized_aperture
+ * (mqi_tps_env.hpp:1605-1736), traversed by the c_ind loop of transport_particles_patient
+ * (mqi_transport.hpp:162-240) before the patient grid.  rho: raw mass densities in g/mm^3
+ * ([nz][ny][nx]; 1e-8 = open, 100 = closed aperture voxel: stepping stops the track at rho > 99.9,
+ * mqi_fippel_physics.hpp:77-85); rot = rotation_matrix_fwd (row-major) or NULL, trans =
+ * translation_vector or NULL.  Beamline nodes carry no scorers (mqi_tps_env.hpp:751).  Returns the
+ * node index (>= 0) or a negative error; mqi_clear_beamline removes them all. */
+MQI_API int mqi_add_beamline_node(mqi_handle* h, const float* xe, int n_xe, const float* ye, int n_ye, const float* ze,
+                          int n_ze, const float* rho, const float* rot, const float* trans);
+MQI_API int mqi_clear_beamline(mqi_handle* h);
 MQI_API int mqi_clear_scorers(mqi_handle* h);
 MQI_API int mqi_set_accumulation(mqi_handle* h, int mode);
 

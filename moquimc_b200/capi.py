@@ -69,6 +69,9 @@ def load():
         "mqi_set_grid_density": [vp, fp, i32, fp, i32, fp, i32, fp, fp, fp],
         "mqi_add_scorer": [vp, i32, C.c_char_p, u64],
         "mqi_bind_scorer_buffer": [vp, i32, vp],
+        "mqi_set_scorer_roi": [vp, i32, vp, u64, C.POINTER(u64)],
+        "mqi_add_beamline_node": [vp, fp, i32, fp, i32, fp, i32, fp, fp, fp],
+        "mqi_clear_beamline": [vp],
         "mqi_clear_scorers": [vp],
         "mqi_set_accumulation": [vp, i32],
         "mqi_set_beamlets": [vp, C.POINTER(Beamlet), u32, C.POINTER(u64)],
@@ -200,6 +203,20 @@ class Engine:
                                                 _fp(rho), _fp(r), _fp(t)))
         self.shape = (len(ze) - 1, len(ye) - 1, len(xe) - 1)
 
+    def add_beamline_node(self, xe, ye, ze, rho, rot=None, trans=None):
+        """A child of the world in front of the scored grid (range shifter slab, voxelised aperture),
+        create_rangeshifter / create_voxelized_aperture mqi_tps_env.hpp:1605-1736.  rho in g/mm^3."""
+        xe, ye, ze = _f32(xe), _f32(ye), _f32(ze)
+        rho = _f32(rho)
+        assert rho.size == (len(xe) - 1) * (len(ye) - 1) * (len(ze) - 1)
+        r = _f32(rot).ravel() if rot is not None else None
+        t = _f32(trans) if trans is not None else None
+        return self._check(self.L.mqi_add_beamline_node(self.h, _fp(xe), len(xe), _fp(ye), len(ye), _fp(ze), len(ze),
+                                                        _fp(rho), _fp(r), _fp(t)))
+
+    def clear_beamline(self):
+        self._check(self.L.mqi_clear_beamline(self.h))
+
     @property
     def nvox(self):
         return int(np.prod(self.shape))
@@ -209,6 +226,17 @@ class Engine:
         i = self._check(self.L.mqi_add_scorer(self.h, kind, name.encode(), capacity))
         self.scorers.append((kind, name))
         return i
+
+    def set_scorer_roi(self, scorer, mask_total):
+        """CONTOUR roi from the summed 0/1 mask volume (mask_reader::mask_to_roi); None = DIRECT roi.
+        Returns the roi size (get_mask_size)."""
+        n = C.c_uint64()
+        if mask_total is None:
+            self._check(self.L.mqi_set_scorer_roi(self.h, scorer, None, 0, C.byref(n)))
+        else:
+            m = np.ascontiguousarray(mask_total, dtype=np.uint8).ravel()
+            self._check(self.L.mqi_set_scorer_roi(self.h, scorer, m.ctypes.data, m.size, C.byref(n)))
+        return n.value
 
     def bind_scorer_buffer(self, scorer, device_ptr):
         self._check(self.L.mqi_bind_scorer_buffer(self.h, scorer, C.c_void_p(device_ptr)))

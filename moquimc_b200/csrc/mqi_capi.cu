@@ -7,6 +7,7 @@
 #include "../../include/mqi_b200.h"
 #include "mqi_device.cuh"
 #include "mqi_kernels.h"
+#include "mqi_roi.hpp"
 
 #include <dlfcn.h>
 
@@ -46,6 +47,21 @@ struct HostScorer {
     double*     d_dense  = nullptr;
     bool        external = false;
     DijSlot*    d_table  = nullptr;
+    uint32_t*   d_roi    = nullptr;   // CONTOUR roi as one bit per voxel, nullptr = DIRECT roi
+    uint64_t    roi_size = 0;         // voxels inside the roi (get_mask_size)
+};
+
+// one child of the world in front of the scored grid (range shifter, aperture)
+struct HostNode {
+    int                nx = 0, ny = 0, nz = 0;
+    std::vector<float> edges;   // xe | ye | ze
+    uint16_t*          d_mat = nullptr;
+    MatEntry*          d_lut = nullptr;
+    int                lut_size = 0;
+    float              rot[9]   = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    float              trans[3] = { 0, 0, 0 };
+    int                identity = 1;
+    float              inv_w[3] = { 0, 0, 0 };
 };
 
 const float* table_ptr(int t) { return reinterpret_cast<const float*>(k_tables_blob + 16) + 600 * t; }
@@ -155,6 +171,13 @@ struct mqi_handle {
     float     trans[3] = { 0, 0, 0 };
     int       identity = 1;
     float     inv_w[3] = { 0, 0, 0 };
+    std::vector<float> edges_host;
+    // beamline children in transport order (multi-node launches), and their device mirror
+    std::vector<HostNode> beamline;
+    GridDev*  d_nodes = nullptr;
+    float*    d_edges_all = nullptr;
+    int       n_edge_floats_all = 0;
+    bool      nodes_dirty = true;
     // source
     BeamletDev*         d_beamlets = nullptr;
     unsigned long long* d_cum      = nullptr;
@@ -200,18 +223,23 @@ set_grid_common(mqi_handle* h, const float* xe, int n_xe, const float* ye, int n
     for (int i = 1; i < n_xe; ++i) if (!(xe[i] > xe[i - 1])) return fail(MQI_EINVAL, "x edges must increase");
     for (int i = 1; i < n_ye; ++i) if (!(ye[i] > ye[i - 1])) return fail(MQI_EINVAL, "y edges must increase");
     for (int i = 1; i < n_ze; ++i) if (!(ze[i] > ze[i - 1])) return fail(MQI_EINVAL, "z edges must increase");
-    if (transport_smem_bytes(n_xe - 1, n_ye - 1, n_ze - 1) > 200 * 1024) return fail(MQI_EINVAL, "too many grid edges for shared memory");
+    if (transport_smem_bytes(n_xe + n_ye + n_ze, 1) > 200 * 1024) return fail(MQI_EINVAL, "too many grid edges for shared memory");
     // scorers are sized by the grid: drop dense accumulators of a previous grid
     for (auto& s : h->scorers) {
         if (s.d_dense && !s.external) cudaFree(s.d_dense);
         if (!s.external) s.d_dense = nullptr;
+        cudaFree(s.d_roi);   // a region of interest belongs to the grid it was defined on
+        s.d_roi    = nullptr;
+        s.roi_size = 0;
     }
     free_grid(h);
+    h->nodes_dirty = true;
     h->nx = n_xe - 1; h->ny = n_ye - 1; h->nz = n_ze - 1;
     std::vector<float> e;
     e.insert(e.end(), xe, xe + n_xe);
     e.insert(e.end(), ye, ye + n_ye);
     e.insert(e.end(), ze, ze + n_ze);
+    h->edges_host = e;
     CU(cudaMalloc(&h->d_edges, e.size() * sizeof(float)));
     CU(cudaMemcpyAsync(h->d_edges, e.data(), e.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -268,6 +296,18 @@ fill_params(const mqi_handle* h, Params& p) {
     std::memcpy(p.g.rot_fwd, h->rot, sizeof(h->rot));
     std::memcpy(p.g.trans, h->trans, sizeof(h->trans));
     std::memcpy(p.g.inv_w, h->inv_w, sizeof(h->inv_w));
+    p.g.edge_off = 0;
+    if (h->beamline.empty()) {
+        p.nodes         = nullptr;
+        p.n_nodes       = 1;
+        p.edges_all     = h->d_edges;
+        p.n_edge_floats = h->nx + h->ny + h->nz + 3;
+    } else {   // mirror built by sync_nodes()
+        p.nodes         = h->d_nodes;
+        p.n_nodes       = (int) h->beamline.size() + 1;
+        p.edges_all     = h->d_edges_all;
+        p.n_edge_floats = h->n_edge_floats_all;
+    }
     p.src.beamlets = h->d_beamlets;
     p.src.cum      = h->d_cum;
     p.src.n_spots  = h->n_spots;
@@ -279,6 +319,7 @@ fill_params(const mqi_handle* h, Params& p) {
         p.sc[i].dense    = h->scorers[i].d_dense;
         p.sc[i].table    = h->scorers[i].d_table;
         p.sc[i].capacity = h->scorers[i].capacity;
+        p.sc[i].roi      = h->scorers[i].d_roi;
     }
     p.quirks      = h->quirks;
     p.accum_mode  = h->accum;
@@ -292,6 +333,75 @@ fill_params(const mqi_handle* h, Params& p) {
     p.counters    = h->d_counters;
 }
 
+// raw densities -> 16-bit material indices + LUT of the distinct values
+int
+build_density_lut(const float* rho, size_t nv, int variant, std::vector<uint16_t>& mat, std::vector<MatEntry>& lut) {
+    std::map<uint32_t, uint16_t> dict;
+    mat.resize(nv);
+    lut.clear();
+    for (size_t i = 0; i < nv; ++i) {
+        uint32_t bits;
+        std::memcpy(&bits, &rho[i], 4);
+        auto it = dict.find(bits);
+        if (it == dict.end()) {
+            if (lut.size() >= 65536) return fail(MQI_EINVAL, "more than 65536 distinct densities; pass HU instead");
+            it = dict.emplace(bits, (uint16_t) lut.size()).first;
+            lut.push_back(make_mat_entry(rho[i], variant));
+        }
+        mat[i] = it->second;
+    }
+    return MQI_OK;
+}
+
+void
+free_beamline(mqi_handle* h) {
+    for (auto& n : h->beamline) {
+        cudaFree(n.d_mat);
+        cudaFree(n.d_lut);
+    }
+    h->beamline.clear();
+    cudaFree(h->d_nodes);
+    cudaFree(h->d_edges_all);
+    h->d_nodes     = nullptr;
+    h->d_edges_all = nullptr;
+    h->nodes_dirty = true;
+}
+
+// device mirror of the world's children for multi-node launches: descriptors + all edges back to back
+int
+sync_nodes(mqi_handle* h) {
+    if (h->beamline.empty() || !h->nodes_dirty) return MQI_OK;
+    std::vector<GridDev> nodes;
+    std::vector<float>   edges;
+    auto add = [&](int nx, int ny, int nz, const std::vector<float>& e, const uint16_t* mat, const MatEntry* lut, int lut_size,
+                   const float* rot, const float* trans, int identity, const float* inv_w) {
+        GridDev g;
+        std::memset(&g, 0, sizeof(g));
+        g.nx = nx; g.ny = ny; g.nz = nz;
+        g.edges = nullptr;
+        g.mat = mat; g.lut = lut; g.lut_size = lut_size; g.identity = identity;
+        std::memcpy(g.rot_fwd, rot, 9 * sizeof(float));
+        std::memcpy(g.trans, trans, 3 * sizeof(float));
+        std::memcpy(g.inv_w, inv_w, 3 * sizeof(float));
+        g.edge_off = (int) edges.size();
+        edges.insert(edges.end(), e.begin(), e.end());
+        nodes.push_back(g);
+    };
+    for (auto& n : h->beamline) add(n.nx, n.ny, n.nz, n.edges, n.d_mat, n.d_lut, n.lut_size, n.rot, n.trans, n.identity, n.inv_w);
+    add(h->nx, h->ny, h->nz, h->edges_host, h->d_mat, h->d_lut, h->lut_size, h->rot, h->trans, h->identity, h->inv_w);
+    cudaFree(h->d_nodes);
+    cudaFree(h->d_edges_all);
+    h->d_nodes = nullptr; h->d_edges_all = nullptr;
+    CU(cudaMalloc(&h->d_nodes, nodes.size() * sizeof(GridDev)));
+    CU(cudaMalloc(&h->d_edges_all, edges.size() * sizeof(float)));
+    CU(cudaMemcpyAsync(h->d_nodes, nodes.data(), nodes.size() * sizeof(GridDev), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_edges_all, edges.data(), edges.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->n_edge_floats_all = (int) edges.size();
+    h->nodes_dirty       = false;
+    return MQI_OK;
+}
+
 template<typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -301,6 +411,8 @@ struct DevBuf {
 }   // namespace
 
 extern "C" {
+static int collect_run(mqi_handle* h);
+static int collect_run_fwd(mqi_handle* h) { return collect_run(h); }
 
 const char* mqi_last_error(void) { return g_err.c_str(); }
 const char* mqi_version(void) { return "moquimc_b200 0.1 (sm_100a)"; }
@@ -376,9 +488,11 @@ mqi_destroy(mqi_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     free_grid(h);
+    free_beamline(h);
     for (auto& s : h->scorers) {
         if (s.d_dense && !s.external) cudaFree(s.d_dense);
         cudaFree(s.d_table);
+        cudaFree(s.d_roi);
     }
     cudaFree(h->d_tab_a0); cudaFree(h->d_tab_a1); cudaFree(h->d_tab_bs); cudaFree(h->d_tab_n0); cudaFree(h->d_tab_n1); cudaFree(h->d_correction); cudaFree(h->d_counters);
     cudaFree(h->d_beamlets); cudaFree(h->d_cum); cudaFree(h->d_vertices); cudaFree(h->d_spot_ids);
@@ -445,21 +559,10 @@ mqi_set_grid_density(mqi_handle* h, const float* xe, int n_xe, const float* ye, 
     rc = set_grid_common(h, xe, n_xe, ye, n_ye, ze, n_ze, rot, trans);
     if (rc) return rc;
     const size_t nv = nvox(h);
-    // dictionary of distinct densities (bit patterns) -> 16-bit material index
-    std::map<uint32_t, uint16_t> dict;
-    std::vector<uint16_t>        mat(nv);
-    std::vector<MatEntry>        lut;
-    for (size_t i = 0; i < nv; ++i) {
-        uint32_t bits;
-        std::memcpy(&bits, &rho[i], 4);
-        auto it = dict.find(bits);
-        if (it == dict.end()) {
-            if (lut.size() >= 65536) return fail(MQI_EINVAL, "more than 65536 distinct densities; pass HU instead");
-            it = dict.emplace(bits, (uint16_t) lut.size()).first;
-            lut.push_back(make_mat_entry(rho[i], h->variant));
-        }
-        mat[i] = it->second;
-    }
+    std::vector<uint16_t> mat;
+    std::vector<MatEntry> lut;
+    rc = build_density_lut(rho, nv, h->variant, mat, lut);
+    if (rc) return rc;
     CU(cudaMalloc(&h->d_mat, nv * sizeof(uint16_t)));
     CU(cudaMalloc(&h->d_lut, lut.size() * sizeof(MatEntry)));
     CU(cudaMemcpyAsync(h->d_mat, mat.data(), nv * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
@@ -492,6 +595,83 @@ mqi_bind_scorer_buffer(mqi_handle* h, int scorer, void* d_buffer) {
     if (s.d_dense && !s.external) cudaFree(s.d_dense);
     s.d_dense  = static_cast<double*>(d_buffer);
     s.external = d_buffer != nullptr;
+    return MQI_OK;
+}
+
+int
+mqi_set_scorer_roi(mqi_handle* h, int scorer, const uint8_t* mask_total, uint64_t n_voxels, uint64_t* roi_size) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (scorer < 0 || scorer >= (int) h->scorers.size()) return fail(MQI_EINVAL, "bad scorer index");
+    if (!h->has_grid) return fail(MQI_ESTATE, "set the grid before a region of interest");
+    HostScorer& s = h->scorers[scorer];
+    rc = collect_run_fwd(h);
+    if (rc) return rc;
+    cudaFree(s.d_roi);
+    s.d_roi    = nullptr;
+    s.roi_size = 0;
+    if (!mask_total) {   // back to roi_t(DIRECT)
+        if (roi_size) *roi_size = nvox(h);
+        return MQI_OK;
+    }
+    if (n_voxels != nvox(h)) return fail(MQI_EINVAL, "mask size differs from the grid");
+    const RoiRuns               runs = mask_to_roi(mask_total, n_voxels);
+    const std::vector<uint32_t> bits = runs.bitmask();
+    CU(cudaMalloc(&s.d_roi, std::max<size_t>(bits.size(), 1) * sizeof(uint32_t)));
+    CU(cudaMemcpyAsync(s.d_roi, bits.data(), bits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    s.roi_size = runs.size();
+    if (roi_size) *roi_size = s.roi_size;
+    return MQI_OK;
+}
+
+int
+mqi_add_beamline_node(mqi_handle* h, const float* xe, int n_xe, const float* ye, int n_ye, const float* ze, int n_ze,
+                      const float* rho, const float* rot, const float* trans) {
+    int rc = activate(h);
+    if (rc) return rc;
+    if (!xe || !ye || !ze || n_xe < 2 || n_ye < 2 || n_ze < 2 || !rho) return fail(MQI_EINVAL, "bad beamline node");
+    for (int i = 1; i < n_xe; ++i) if (!(xe[i] > xe[i - 1])) return fail(MQI_EINVAL, "x edges must increase");
+    for (int i = 1; i < n_ye; ++i) if (!(ye[i] > ye[i - 1])) return fail(MQI_EINVAL, "y edges must increase");
+    for (int i = 1; i < n_ze; ++i) if (!(ze[i] > ze[i - 1])) return fail(MQI_EINVAL, "z edges must increase");
+    if ((int) h->beamline.size() >= 7) return fail(MQI_EINVAL, "too many beamline nodes");
+    rc = collect_run_fwd(h);
+    if (rc) return rc;
+    HostNode n;
+    n.nx = n_xe - 1; n.ny = n_ye - 1; n.nz = n_ze - 1;
+    n.edges.insert(n.edges.end(), xe, xe + n_xe);
+    n.edges.insert(n.edges.end(), ye, ye + n_ye);
+    n.edges.insert(n.edges.end(), ze, ze + n_ze);
+    n.inv_w[0] = (float) n.nx / (xe[n_xe - 1] - xe[0]);
+    n.inv_w[1] = (float) n.ny / (ye[n_ye - 1] - ye[0]);
+    n.inv_w[2] = (float) n.nz / (ze[n_ze - 1] - ze[0]);
+    const float I[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    std::memcpy(n.rot, rot ? rot : I, sizeof(I));
+    for (int k = 0; k < 3; ++k) n.trans[k] = trans ? trans[k] : 0.f;
+    n.identity = (std::memcmp(n.rot, I, sizeof(I)) == 0 && n.trans[0] == 0.f && n.trans[1] == 0.f && n.trans[2] == 0.f) ? 1 : 0;
+    const size_t          nv = (size_t) n.nx * n.ny * n.nz;
+    std::vector<uint16_t> mat;
+    std::vector<MatEntry> lut;
+    rc = build_density_lut(rho, nv, h->variant, mat, lut);
+    if (rc) return rc;
+    CU(cudaMalloc(&n.d_mat, nv * sizeof(uint16_t)));
+    CU(cudaMalloc(&n.d_lut, lut.size() * sizeof(MatEntry)));
+    CU(cudaMemcpyAsync(n.d_mat, mat.data(), nv * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(n.d_lut, lut.data(), lut.size() * sizeof(MatEntry), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    n.lut_size = (int) lut.size();
+    h->beamline.push_back(n);
+    h->nodes_dirty = true;
+    return (int) h->beamline.size() - 1;
+}
+
+int
+mqi_clear_beamline(mqi_handle* h) {
+    int rc = activate(h);
+    if (rc) return rc;
+    rc = collect_run_fwd(h);
+    if (rc) return rc;
+    free_beamline(h);
     return MQI_OK;
 }
 
@@ -605,6 +785,8 @@ mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t cou
     if (rc) return rc;
     rc = ensure_scorer_buffers(h);
     if (rc) return rc;
+    rc = sync_nodes(h);
+    if (rc) return rc;
     std::memset(&h->stats, 0, sizeof(h->stats));
     if (count == 0) return MQI_OK;
     Params p;
@@ -621,9 +803,10 @@ mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t cou
         p.src.vertices = h->d_vertices + first_history;
         p.src.spot_ids = h->d_spot_ids ? h->d_spot_ids + first_history : nullptr;
     }
-    const size_t smem = transport_smem_bytes(h->nx, h->ny, h->nz);
+    const size_t smem = transport_smem_bytes(p.n_edge_floats, p.n_nodes);
+    if (smem > 200 * 1024) return fail(MQI_EINVAL, "the world's grid edges do not fit into shared memory");
     int          bps  = 0;
-    CU(transport_occupancy(h->variant, transport_is_simple(p), smem, &bps));
+    CU(transport_occupancy(p, h->variant, smem, &bps));
     if (bps < 1) return fail(MQI_ECUDA, "transport kernel does not fit on an SM");
     if (h->blocks_per_sm_override > 0) bps = std::min(bps, h->blocks_per_sm_override);
     // persistent grid: a whole number of CTAs per SM, never more lanes than histories

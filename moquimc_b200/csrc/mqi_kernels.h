@@ -38,9 +38,9 @@ struct MatEntry;
 struct BeamletDev;
 struct VertexDev;
 
-size_t      transport_smem_bytes(int nx, int ny, int nz);
+size_t      transport_smem_bytes(int n_edge_floats, int n_nodes);
 bool        transport_is_simple(const Params& p);
-cudaError_t transport_occupancy(int variant, bool simple, size_t smem, int* blocks_per_sm);
+cudaError_t transport_occupancy(const Params& p, int variant, size_t smem, int* blocks_per_sm);
 cudaError_t launch_transport(const Params& p, int variant, int grid, size_t smem, cudaStream_t st);
 
 // HU volume -> 16-bit material index volume (index = clamp(hu) + 1000)

@@ -17,16 +17,53 @@ namespace mqib
 {
 
 // ---------------------------------------------------------------------------------------------
-// shared-memory view of the physics tables and grid edges
+// shared-memory layout: physics tables | grid edges of every node | node descriptors (multi-node
+// launches) | per-warp queues of pre-sampled primaries
 // ---------------------------------------------------------------------------------------------
 struct Smem {
     const float4* a0;   // {cs_p_ion, slope, restricted stopping power, slope}   per 0.5 MeV row, Ei = 0.1
     const float4* a1;   // {csda range, slope, dE/drange (inverse slope), 0}
     const float2* bs;   // {cs_pp + cs_pO_el + cs_pO_inel, slope}                  Ei = 0.5
-    const float*  xe;
-    const float*  ye;
-    const float*  ze;
+    const float*  edges;   // node k: xe | ye | ze at edges + nodes[k].edge_off (single node: offset 0)
+    const GridDev* nodes;  // multi-node launches only
+    uint32_t*     queue;   // kQueueWords words per warp
 };
+
+// queue of pre-sampled primaries, one per warp, structure of arrays: field f of entry e at
+// [f * kQueueCap + e].  Filled 32 entries at a time by the whole warp (refill_queue), drained by the
+// lanes whose track ended.
+constexpr int kQueueCap    = 64;
+enum QueueField { Q_PX = 0, Q_PY, Q_PZ, Q_DX, Q_DY, Q_DZ, Q_KE, Q_IX, Q_IY, Q_IZ, Q_H0, Q_H1, Q_SPOT, Q_NODE, Q_FIELDS };
+constexpr int kQueueWords  = Q_FIELDS * kQueueCap;
+constexpr size_t kTableBytes = kTableN * (2 * sizeof(float4) + sizeof(float2));
+
+__host__ __device__ __forceinline__ size_t
+smem_nodes_offset(int n_edge_floats) { return (kTableBytes + (size_t) n_edge_floats * sizeof(float) + 15) & ~(size_t) 15; }
+__host__ __device__ __forceinline__ size_t
+smem_queue_offset(int n_edge_floats, int n_nodes) {
+    return smem_nodes_offset(n_edge_floats) + ((n_nodes > 1 ? (size_t) n_nodes * sizeof(GridDev) : 0) + 15 & ~(size_t) 15);
+}
+
+__device__ __forceinline__ Smem
+smem_view(unsigned char* raw, int n_edge_floats, int n_nodes) {
+    Smem sm;
+    float4* a0 = reinterpret_cast<float4*>(raw);
+    float4* a1 = a0 + kTableN;
+    float2* bs = reinterpret_cast<float2*>(a1 + kTableN);
+    sm.a0 = a0; sm.a1 = a1; sm.bs = bs;
+    sm.edges = reinterpret_cast<float*>(bs + kTableN);
+    sm.nodes = reinterpret_cast<const GridDev*>(raw + smem_nodes_offset(n_edge_floats));
+    sm.queue = reinterpret_cast<uint32_t*>(raw + smem_queue_offset(n_edge_floats, n_nodes));
+    return sm;
+}
+
+// the node a lane is in: a shared-memory descriptor in multi-node launches, else the kernel parameter
+template<bool MULTI>
+__device__ __forceinline__ const GridDev&
+node_ref(const Params& P, const Smem& sm, int node) {
+    if (MULTI) return sm.nodes[node];
+    return P.g;
+}
 
 // Cross sections [mm^2/g]: delta production on the p-ion grid plus the three nuclear channels
 // (pre-summed for the mean free path: linear interpolation commutes with the sum), mqi_p_ionization.hpp:
@@ -103,11 +140,12 @@ struct NucIO {
     float c1, c2, c3;               // nuclear channel cross sections (filled by nuclear_event)
     int   stopped;
     int   sp;                       // stack pointer, in/out
+    int   node;                     // node the interaction happens in (multi-node launches)
     unsigned n_sec, n_ovf;          // counters, out
     RngBuf rb;
 };
 
-template<int VARIANT>
+template<int VARIANT, bool MULTI>
 __device__ __forceinline__ void
 push_secondary(const Params& P, Secondary* stack, NucIO& io, float x, float y, float z, float ux, float uy,
                float uz, float ke0, float ke1_off, float dE_pre) {
@@ -116,13 +154,16 @@ push_secondary(const Params& P, Secondary* stack, NucIO& io, float x, float y, f
         ++io.n_ovf;
         return;
     }
-    if (!P.g.identity) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem     sm = smem_view(smem_raw, P.n_edge_floats, P.n_nodes);
+    const GridDev& G  = node_ref<MULTI>(P, sm, io.node);
+    if (!G.identity) {
         // daughters are mapped with Rfwd * (x - T) + T, mqi_pp_elastic.hpp:188-195
-        const float* R  = P.g.rot_fwd;
-        const float  qx = x - P.g.trans[0], qy = y - P.g.trans[1], qz = z - P.g.trans[2];
-        x = R[0] * qx + R[1] * qy + R[2] * qz + P.g.trans[0];
-        y = R[3] * qx + R[4] * qy + R[5] * qz + P.g.trans[1];
-        z = R[6] * qx + R[7] * qy + R[8] * qz + P.g.trans[2];
+        const float* R  = G.rot_fwd;
+        const float  qx = x - G.trans[0], qy = y - G.trans[1], qz = z - G.trans[2];
+        x = R[0] * qx + R[1] * qy + R[2] * qz + G.trans[0];
+        y = R[3] * qx + R[4] * qy + R[5] * qz + G.trans[1];
+        z = R[6] * qx + R[7] * qy + R[8] * qz + G.trans[2];
         const float ex = ux, ey = uy, ez = uz;
         ux = R[0] * ex + R[1] * ey + R[2] * ez;
         uy = R[3] * ex + R[4] * ey + R[5] * ez;
@@ -136,7 +177,7 @@ push_secondary(const Params& P, Secondary* stack, NucIO& io, float x, float y, f
 
 // p-p elastic, p-O elastic and p-O inelastic post-step interactions (0.5 events per 200 MeV history):
 // out of line so that the voxel-step loop stays small.
-template<int VARIANT>
+template<int VARIANT, bool MULTI>
 __device__ __noinline__ void
 nuclear_event(const Params& P, Secondary* stack, NucIO& io) {
     RngBuf& rb = io.rb;
@@ -177,14 +218,14 @@ nuclear_event(const Params& P, Secondary* stack, NucIO& io) {
         // recoil proton: direction rotated from the already scattered primary direction
         float sx = io.d1x, sy = io.d1y, sz = io.d1z;
         rotate_direction(sx, sy, sz, th4, phi);
-        push_secondary<VARIANT>(P, stack, io, io.p1x, io.p1y, io.p1z, sx, sy, sz, dE, 0.f, 0.f);
+        push_secondary<VARIANT, MULTI>(P, stack, io, io.p1x, io.p1y, io.p1z, sx, sy, sz, dE, 0.f, 0.f);
     } else if (io.u < io.c1 + io.c2) {
         // p-O elastic, po_elastic::post_step mqi_po_elastic.hpp:97-217
         const Rel r1 = rel_make(io.ke1);
         if (r1.Ek <= 5.5f) {
             const float dE = r1.Ek;
             if (VARIANT == MQI_K_DEBUG)
-                push_secondary<VARIANT>(P, stack, io, io.p1x, io.p1y, io.p1z, io.d1x, io.d1y, io.d1z, dE, -dE, dE);
+                push_secondary<VARIANT, MULTI>(P, stack, io, io.p1x, io.p1y, io.p1z, io.d1x, io.d1y, io.d1z, dE, -dE, dE);
             else io.local_dE += dE;
             io.ke1 -= dE;
             io.stopped = 1;
@@ -203,7 +244,7 @@ nuclear_event(const Params& P, Secondary* stack, NucIO& io) {
             const float th3 = acosf(cos_th3);
             const float phi = kTwoPi * rb_uniform(rb);
             if (VARIANT == MQI_K_DEBUG)   // daughter starts at the parent's PRE-step vertex
-                push_secondary<VARIANT>(P, stack, io, io.px, io.py, io.pz, io.dx, io.dy, io.dz, dE, -dE, dE);
+                push_secondary<VARIANT, MULTI>(P, stack, io, io.px, io.py, io.pz, io.dx, io.dy, io.dz, dE, -dE, dE);
             else io.local_dE += dE;
             io.ke1 -= dE;
             rotate_direction(io.d1x, io.d1y, io.d1z, th3, phi);
@@ -232,11 +273,11 @@ nuclear_event(const Params& P, Secondary* stack, NucIO& io) {
                 const float phi = kTwoPi * rb_uniform(rb);
                 float sx = io.d1x, sy = io.d1y, sz = io.d1z;
                 rotate_direction(sx, sy, sz, th, phi);
-                push_secondary<VARIANT>(P, stack, io, io.p1x, io.p1y, io.p1z, sx, sy, sz, dE, 0.f, 0.f);
+                push_secondary<VARIANT, MULTI>(P, stack, io, io.p1x, io.p1y, io.p1z, sx, sy, sz, dE, 0.f, 0.f);
             } else if (zeta < prob_long) {
                 // neutral / long-range: energy leaves
             } else if (VARIANT == MQI_K_DEBUG) {
-                push_secondary<VARIANT>(P, stack, io, io.px, io.py, io.pz, io.dx, io.dy, io.dz, dE, -dE, dE);
+                push_secondary<VARIANT, MULTI>(P, stack, io, io.px, io.py, io.pz, io.dx, io.dy, io.dz, dE, -dE, dE);
             }   // release: short-range energy dropped (:273-275, B4)
             Eb *= 0.65f;
         }
@@ -372,7 +413,6 @@ template<int VARIANT>
 __device__ __forceinline__ void
 score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, float inv_vol, float rsp0,
            const StepResult& r) {
-    if ((int) cnb <= 0) return;   // roi_->idx(cnb) > 0 with a DIRECT roi: voxel 0 is never scored (B1)
     // dose_to_water: (dE + local_dE) * 1.60218e-10 / (V * rho * rsp(rho, vtx0.ke))
     const float  kdose   = 1.60218e-10f * inv_vol * M.inv_rho;
     const double dose    = (double) ((r.dE + r.local_dE) * kdose / rsp0);
@@ -381,6 +421,10 @@ score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, 
 #pragma unroll 1
     for (int s = 0; s < n; ++s) {
         const int kind = P.sc[s].kind;
+        // roi_->idx(cnb) > 0 (mqi_transport.hpp:205,216): a DIRECT roi returns cnb, so voxel 0 is never
+        // scored (B1); a CONTOUR roi (mask_to_roi) accepts the voxels inside its runs
+        const uint32_t* roi = P.sc[s].roi;
+        if (roi ? !((__ldg(roi + (cnb >> 5)) >> (cnb & 31u)) & 1u) : (int) cnb <= 0) continue;
         double    v    = 0.0;
         if (kind == MQI_K_DOSE || kind == MQI_K_DIJ) v = dose + dose_te;
         else if (kind == MQI_K_DOSE_SQ) v = dose * dose + dose_te * dose_te;
@@ -396,53 +440,172 @@ score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// re-arming a lane (out of line: executed once per track, keeps the voxel-step loop compact for the
-// instruction cache): pop a secondary or fetch + sample the next primary, world -> node frame,
-// locate the start cell (index(p, dir) or entry intersect), mqi_transport.hpp:146-190
+// starting a track: world -> node frame, locate the start cell (index(p, dir) or entry intersect),
+// mqi_transport.hpp:162-190.  Out of the voxel-step loop (keeps it compact for the instruction cache).
+// Primaries are started 32 at a time by the whole warp (refill_queue) and parked in a per-warp
+// shared-memory queue; secondaries and node-to-node transitions are started by the lane that owns
+// them (restart_lane).
 // ---------------------------------------------------------------------------------------------
-struct LaneIO {
-    float    px, py, pz, dx, dy, dz, ke;
-    int      ix, iy, iz;
-    int      recoil;   // debug recoil daughter before its first step: vtx1.ke = 0 and trk.dE = vtx0.ke
-    uint32_t spot_ind, h0, h1, blk;
-    int      sp;
-    unsigned n_done;
+struct TrackIO {
+    float px, py, pz, dx, dy, dz, ke;
+    int   ix, iy, iz;
+    int   recoil;   // debug recoil daughter before its first step: vtx1.ke = 0 and trk.dE = vtx0.ke
+    int   node;     // in: first child to try, out: child entered
+    int   sp;       // stack pointer (restart_lane)
 };
 
-__device__ __forceinline__ Smem
-smem_view(unsigned char* raw, int nx, int ny) {
-    Smem sm;
-    float4* a0 = reinterpret_cast<float4*>(raw);
-    float4* a1 = a0 + kTableN;
-    float2* bs = reinterpret_cast<float2*>(a1 + kTableN);
-    float*  e  = reinterpret_cast<float*>(bs + kTableN);
-    sm.a0 = a0; sm.a1 = a1; sm.bs = bs;
-    sm.xe = e; sm.ye = e + nx + 1; sm.ze = e + nx + 1 + ny + 1;
-    return sm;
+// Try the world's children in order from T.node (the reference's c_ind loop): a child the track misses
+// hands it back in the world frame to the next one, :176-185.  Returns false if no child is entered.
+template<bool MULTI>
+__device__ __forceinline__ bool
+enter_nodes(const Params& P, const Smem& sm, TrackIO& T) {
+    const int n_nodes = MULTI ? P.n_nodes : 1;
+    float     px = T.px, py = T.py, pz = T.pz, dx = T.dx, dy = T.dy, dz = T.dz, ke = T.ke;
+    bool      recoil = T.recoil != 0;
+#pragma unroll 1
+    for (int node = MULTI ? T.node : 0; node < n_nodes; ++node) {
+        const GridDev& G  = node_ref<MULTI>(P, sm, node);
+        const int      nx = G.nx, ny = G.ny, nz = G.nz;
+        const float*   xe = sm.edges + (MULTI ? G.edge_off : 0);
+        const float*   ye = xe + nx + 1;
+        const float*   ze = ye + ny + 1;
+        // world -> node frame, mqi_transport.hpp:165-170
+        if (!G.identity) {
+            const float* R  = G.rot_fwd;   // inverse = transpose
+            const float  qx = px - G.trans[0], qy = py - G.trans[1], qz = pz - G.trans[2];
+            px = R[0] * qx + R[3] * qy + R[6] * qz;
+            py = R[1] * qx + R[4] * qy + R[7] * qz;
+            pz = R[2] * qx + R[5] * qy + R[8] * qz;
+            const float ex = dx, ey = dy, ez = dz;
+            dx = R[0] * ex + R[3] * ey + R[6] * ez;
+            dy = R[1] * ex + R[4] * ey + R[7] * ez;
+            dz = R[2] * ex + R[5] * ey + R[8] * ez;
+        }
+        {
+            const float n = rsqrtf(dx * dx + dy * dy + dz * dz);
+            dx *= n; dy *= n; dz *= n;
+        }
+        // locate: index(p, dir) or entry intersect, :171-190.  A point farther than the geometry
+        // tolerance outside the bounding box has no valid index on that axis: skip the search.
+        int ix, iy, iz;
+        if (px < xe[0] - 2.f * kGeomTol || px > xe[nx] + 2.f * kGeomTol || py < ye[0] - 2.f * kGeomTol ||
+            py > ye[ny] + 2.f * kGeomTol || pz < ze[0] - 2.f * kGeomTol || pz > ze[nz] + 2.f * kGeomTol) {
+            ix = iy = iz = -1;
+        } else {
+            ix = index_axis_guess(xe, nx, px, dx, G.inv_w[0]);
+            iy = index_axis_guess(ye, ny, py, dy, G.inv_w[1]);
+            iz = index_axis_guess(ze, nz, pz, dz, G.inv_w[2]);
+        }
+        bool  alive = true;
+        float d[3]  = { dx, dy, dz };
+        if (ix < 0 || iy < 0 || iz < 0 || ix >= nx || iy >= ny || iz >= nz) {
+            const float p[3] = { px, py, pz };
+            int         c[3];
+            const float inv_w[3] = { G.inv_w[0], G.inv_w[1], G.inv_w[2] };
+            const float dist = grid_entry(xe, ye, ze, nx, ny, nz, inv_w, p, d, c);
+            if (dist < 0.f) {
+                alive = false;
+            } else {
+                // update_post_vertex_position uses the (possibly zeroed) direction, move() then
+                // restores the un-zeroed copy held in vtx1.dir; vtx1.ke becomes vtx0.ke.  The cell
+                // of the moved point is the one intersect() already looked up (same point, same d
+                // up to the zeroed components, which only matter exactly on an edge).
+                px = __fadd_rn(px, __fmul_rn(d[0], dist));
+                py = __fadd_rn(py, __fmul_rn(d[1], dist));
+                pz = __fadd_rn(pz, __fmul_rn(d[2], dist));
+                if (recoil) ke = 0.f;   // vtx0.ke := vtx1.ke, and the carried energy is dropped by move()
+                recoil = false;
+                if (d[0] == dx && d[1] == dy && d[2] == dz) {
+                    ix = c[0]; iy = c[1]; iz = c[2];
+                } else {
+                    ix = index_axis_guess(xe, nx, px, dx, G.inv_w[0]);
+                    iy = index_axis_guess(ye, ny, py, dy, G.inv_w[1]);
+                    iz = index_axis_guess(ze, nz, pz, dz, G.inv_w[2]);
+                }
+                if (ix < 0 || iy < 0 || iz < 0 || ix >= nx || iy >= ny || iz >= nz) alive = false;
+            }
+        }
+        if (alive) {
+            T.px = px; T.py = py; T.pz = pz; T.dx = dx; T.dy = dy; T.dz = dz;
+            T.ke = ke; T.recoil = recoil ? 1 : 0;
+            T.ix = ix; T.iy = iy; T.iz = iz;
+            T.node = node;
+            return true;
+        }
+        if (!MULTI) break;
+        // missed this child: node -> world frame with the direction intersect() left behind (tiny
+        // components zeroed in place), :176-185, and on to the next child
+        dx = d[0]; dy = d[1]; dz = d[2];
+        if (!G.identity) {
+            const float* R  = G.rot_fwd;
+            const float  qx = px, qy = py, qz = pz;
+            px = R[0] * qx + R[1] * qy + R[2] * qz + G.trans[0];
+            py = R[3] * qx + R[4] * qy + R[5] * qz + G.trans[1];
+            pz = R[6] * qx + R[7] * qy + R[8] * qz + G.trans[2];
+            const float ex = dx, ey = dy, ez = dz;
+            dx = R[0] * ex + R[1] * ey + R[2] * ez;
+            dy = R[3] * ex + R[4] * ey + R[5] * ez;
+            dz = R[6] * ex + R[7] * ey + R[8] * ez;
+        }
+    }
+    return false;
 }
 
-enum { REARM_EXIT = 0, REARM_ALIVE = 1, REARM_MISSED = 2 };
-
-__device__ __noinline__ int
-rearm_lane(const Params& P, Secondary* stack, LaneIO& L) {
+// A lane whose track ended continues with (a) the same track in the next child of the world, if it
+// left its node alive (multi-node launches: local -> world, mqi_transport.hpp:234-239, then the c_ind
+// loop goes on), or (b) the secondary on top of its stack, which starts at child 0 again (:160-162).
+template<bool MULTI>
+__device__ __noinline__ bool
+restart_lane(const Params& P, const Secondary* stack, TrackIO& T, int advance) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int  nx = P.g.nx, ny = P.g.ny, nz = P.g.nz;
-    const Smem sm = smem_view(smem_raw, nx, ny);
-    float px, py, pz, dx, dy, dz, ke;
-    bool  recoil;
-    if (L.sp > 0) {
-        const Secondary& s = stack[--L.sp];
-        px = s.px; py = s.py; pz = s.pz; dx = s.dx; dy = s.dy; dz = s.dz;
-        ke = s.ke0;
-        recoil = s.ke1_off != 0.f;   // pushed as (ke0, -ke0, ke0) by the debug variant only
+    const Smem sm = smem_view(smem_raw, P.n_edge_floats, P.n_nodes);
+    if (MULTI && advance) {
+        const GridDev& G = sm.nodes[T.node];
+        if (!G.identity) {
+            const float* R  = G.rot_fwd;
+            const float  qx = T.px, qy = T.py, qz = T.pz;
+            T.px = R[0] * qx + R[1] * qy + R[2] * qz + G.trans[0];
+            T.py = R[3] * qx + R[4] * qy + R[5] * qz + G.trans[1];
+            T.pz = R[6] * qx + R[7] * qy + R[8] * qz + G.trans[2];
+            const float ex = T.dx, ey = T.dy, ez = T.dz;
+            T.dx = R[0] * ex + R[1] * ey + R[2] * ez;
+            T.dy = R[3] * ex + R[4] * ey + R[5] * ez;
+            T.dz = R[6] * ex + R[7] * ey + R[8] * ez;
+        }
+        T.node += 1;   // the caller only advances when a next child exists
     } else {
-        const unsigned long long i = atomicAdd(P.counters + C_NEXT, 1ull);
-        if (i >= P.count) return REARM_EXIT;
+        const Secondary& s = stack[--T.sp];
+        T.px = s.px; T.py = s.py; T.pz = s.pz; T.dx = s.dx; T.dy = s.dy; T.dz = s.dz;
+        T.ke     = s.ke0;
+        T.recoil = s.ke1_off != 0.f;   // pushed as (ke0, -ke0, ke0) by the debug variant only
+        T.node   = 0;
+    }
+    return enter_nodes<MULTI>(P, sm, T);
+}
+
+// The whole warp fetches the next 32 history ids with one atomic, samples (or loads) their primary
+// vertices, locates them and appends the ones that enter the geometry to the warp's queue.  Every lane
+// works on its own history: the source sampling and the cell search, which cost about as much as one
+// voxel step, run at full SIMT width instead of once per lane and history.  Returns the new queue
+// length | source exhausted << 16 | this lane fetched a history << 17.
+template<bool MULTI>
+__device__ __noinline__ int
+refill_queue(const Params& P, uint32_t* q, int q_n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem sm   = smem_view(smem_raw, P.n_edge_floats, P.n_nodes);
+    const int  lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(P.counters + C_NEXT, 32ull);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const unsigned long long i    = base + lane;
+    const bool               have = i < P.count;
+    bool     alive = false;
+    TrackIO  T;
+    uint32_t spot = 0, h0 = 0, h1 = 0;
+    if (have) {
         const unsigned long long h = P.first + i;
-        L.h0  = (uint32_t) h;
-        L.h1  = (uint32_t) (h >> 32);
-        L.blk = 0;
-        uint32_t spot = 0;
+        h0 = (uint32_t) h;
+        h1 = (uint32_t) (h >> 32);
         VertexDev v;
         if (P.src.vertices) {
             v    = P.src.vertices[i];
@@ -456,74 +619,29 @@ rearm_lane(const Params& P, Secondary* stack, LaneIO& L) {
             }
             spot = min(lo, P.src.n_spots - 1);
             sample_vertex(P.src.beamlets[spot], P.seed, h, v);
-            L.blk = 2;
         }
-        px = v.pos[0]; py = v.pos[1]; pz = v.pos[2];
-        dx = v.dir[0]; dy = v.dir[1]; dz = v.dir[2];
-        ke = v.ke;
-        L.spot_ind = P.per_spot ? spot : kEmptyKey32;
-        recoil     = false;
-        ++L.n_done;
+        T.px = v.pos[0]; T.py = v.pos[1]; T.pz = v.pos[2];
+        T.dx = v.dir[0]; T.dy = v.dir[1]; T.dz = v.dir[2];
+        T.ke = v.ke;
+        T.recoil = 0;
+        T.node   = 0;
+        alive    = enter_nodes<MULTI>(P, sm, T);
     }
-    // world -> node frame, mqi_transport.hpp:165-170
-    if (!P.g.identity) {
-        const float* R  = P.g.rot_fwd;   // inverse = transpose
-        const float  qx = px - P.g.trans[0], qy = py - P.g.trans[1], qz = pz - P.g.trans[2];
-        px = R[0] * qx + R[3] * qy + R[6] * qz;
-        py = R[1] * qx + R[4] * qy + R[7] * qz;
-        pz = R[2] * qx + R[5] * qy + R[8] * qz;
-        const float ex = dx, ey = dy, ez = dz;
-        dx = R[0] * ex + R[3] * ey + R[6] * ez;
-        dy = R[1] * ex + R[4] * ey + R[7] * ez;
-        dz = R[2] * ex + R[5] * ey + R[8] * ez;
+    const unsigned m = __ballot_sync(0xffffffffu, alive);
+    if (alive) {
+        uint32_t* e = q + q_n + __popc(m & ((1u << lane) - 1u));
+        e[Q_PX * kQueueCap] = __float_as_uint(T.px); e[Q_PY * kQueueCap] = __float_as_uint(T.py);
+        e[Q_PZ * kQueueCap] = __float_as_uint(T.pz); e[Q_DX * kQueueCap] = __float_as_uint(T.dx);
+        e[Q_DY * kQueueCap] = __float_as_uint(T.dy); e[Q_DZ * kQueueCap] = __float_as_uint(T.dz);
+        e[Q_KE * kQueueCap] = __float_as_uint(T.ke);
+        e[Q_IX * kQueueCap] = (uint32_t) T.ix; e[Q_IY * kQueueCap] = (uint32_t) T.iy; e[Q_IZ * kQueueCap] = (uint32_t) T.iz;
+        e[Q_H0 * kQueueCap] = h0; e[Q_H1 * kQueueCap] = h1;
+        e[Q_SPOT * kQueueCap] = P.per_spot ? spot : kEmptyKey32;
+        e[Q_NODE * kQueueCap] = (uint32_t) T.node;
     }
-    {
-        const float n = rsqrtf(dx * dx + dy * dy + dz * dz);
-        dx *= n; dy *= n; dz *= n;
-    }
-    // locate: index(p, dir) or entry intersect, :171-190.  A point farther than the geometry
-    // tolerance outside the bounding box has no valid index on that axis: skip the search.
-    int ix, iy, iz;
-    if (px < sm.xe[0] - 2.f * kGeomTol || px > sm.xe[nx] + 2.f * kGeomTol || py < sm.ye[0] - 2.f * kGeomTol ||
-        py > sm.ye[ny] + 2.f * kGeomTol || pz < sm.ze[0] - 2.f * kGeomTol || pz > sm.ze[nz] + 2.f * kGeomTol) {
-        ix = iy = iz = -1;
-    } else {
-        ix = index_axis_guess(sm.xe, nx, px, dx, P.g.inv_w[0]);
-        iy = index_axis_guess(sm.ye, ny, py, dy, P.g.inv_w[1]);
-        iz = index_axis_guess(sm.ze, nz, pz, dz, P.g.inv_w[2]);
-    }
-    bool alive = true;
-    if (ix < 0 || iy < 0 || iz < 0 || ix >= nx || iy >= ny || iz >= nz) {
-        const float p[3] = { px, py, pz };
-        float       d[3] = { dx, dy, dz };
-        int         c[3];
-        const float dist = grid_entry(sm.xe, sm.ye, sm.ze, nx, ny, nz, P.g.inv_w, p, d, c);
-        if (dist < 0.f) {
-            alive = false;
-        } else {
-            // update_post_vertex_position uses the (possibly zeroed) direction, move() then
-            // restores the un-zeroed copy held in vtx1.dir; vtx1.ke becomes vtx0.ke.  The cell
-            // of the moved point is the one intersect() already looked up (same point, same d
-            // up to the zeroed components, which only matter exactly on an edge).
-            px = __fadd_rn(px, __fmul_rn(d[0], dist));
-            py = __fadd_rn(py, __fmul_rn(d[1], dist));
-            pz = __fadd_rn(pz, __fmul_rn(d[2], dist));
-            if (recoil) ke = 0.f;   // vtx0.ke := vtx1.ke, and the carried energy is dropped by move()
-            recoil = false;
-            if (d[0] == dx && d[1] == dy && d[2] == dz) {
-                ix = c[0]; iy = c[1]; iz = c[2];
-            } else {
-                ix = index_axis_guess(sm.xe, nx, px, dx, P.g.inv_w[0]);
-                iy = index_axis_guess(sm.ye, ny, py, dy, P.g.inv_w[1]);
-                iz = index_axis_guess(sm.ze, nz, pz, dz, P.g.inv_w[2]);
-            }
-            if (ix < 0 || iy < 0 || iz < 0 || ix >= nx || iy >= ny || iz >= nz) alive = false;
-        }
-    }
-    L.px = px; L.py = py; L.pz = pz; L.dx = dx; L.dy = dy; L.dz = dz;
-    L.ke = ke; L.recoil = recoil ? 1 : 0;
-    L.ix = ix; L.iy = iy; L.iz = iz;
-    return alive ? REARM_ALIVE : REARM_MISSED;
+    __syncwarp();
+    const int exhausted = base + 32ull >= P.count ? 1 : 0;
+    return (q_n + __popc(m)) | (exhausted << 16) | ((have ? 1 : 0) << 17);
 }
 
 // further tries of the delta-electron energy rejection loop (about one event in ten needs them):
@@ -546,13 +664,15 @@ delta_retry(uint32_t blk, uint32_t h0, uint32_t key2, float T_cut, float Tmax1, 
 // ---------------------------------------------------------------------------------------------
 // the transport kernel
 // ---------------------------------------------------------------------------------------------
-// SIMPLE: exactly one dense Dose scorer (phantom_env, and the tps "Dose" case): the scorer loop and
-// the other hit functions are compiled out of the voxel-step loop.
-template<int VARIANT, bool SIMPLE>
+// SIMPLE: exactly one dense Dose scorer with a DIRECT roi (phantom_env, and the tps "Dose" case): the
+// scorer loop and the other hit functions are compiled out of the voxel-step loop.
+// MULTI: the world has beamline children (range shifter, aperture) in front of the scored grid; every
+// lane carries the index of the child it is in and reads that child's descriptor from shared memory.
+template<int VARIANT, bool SIMPLE, bool MULTI>
 __global__ void __launch_bounds__(MQI_K_BLOCK, MQI_K_MIN_BLOCKS)
 transport_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nx = P.g.nx, ny = P.g.ny, nz = P.g.nz;
+    const Smem sm = smem_view(smem_raw, P.n_edge_floats, P.n_nodes);
     {
         float4* s_a0    = reinterpret_cast<float4*>(smem_raw);
         float4* s_a1    = s_a0 + kTableN;
@@ -563,10 +683,14 @@ transport_kernel(const __grid_constant__ Params P) {
             s_a1[i] = P.tab_a1[i];
             s_bs[i] = P.tab_bs[i];
         }
-        for (int i = threadIdx.x; i < nx + ny + nz + 3; i += blockDim.x) s_edges[i] = P.g.edges[i];
+        for (int i = threadIdx.x; i < P.n_edge_floats; i += blockDim.x) s_edges[i] = P.edges_all[i];
+        if (MULTI) {
+            uint32_t*       dst = reinterpret_cast<uint32_t*>(smem_raw + smem_nodes_offset(P.n_edge_floats));
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(P.nodes);
+            for (int i = threadIdx.x; i < P.n_nodes * (int) (sizeof(GridDev) / 4); i += blockDim.x) dst[i] = src[i];
+        }
     }
     __syncthreads();
-    const Smem sm = smem_view(smem_raw, nx, ny);
 
     constexpr float T_cut = (VARIANT == MQI_K_DEBUG) ? 0.08511f : 0.0815f;   // mqi_interaction.hpp:24-28
     constexpr int   DEPTH = StackCfg<VARIANT>::depth;
@@ -575,53 +699,101 @@ transport_kernel(const __grid_constant__ Params P) {
 
     // lane state
     float    px = 0, py = 0, pz = 0, dx = 0, dy = 0, dz = 0, ke = 0;
-    bool     recoil = false;   // see LaneIO::recoil (always false in the release variant)
+    bool     recoil = false;   // see TrackIO::recoil (always false in the release variant)
     int      ix = 0, iy = 0, iz = 0;
     bool     alive = false;
+    int      node = 0;          // child of the world the lane's track is in (MULTI)
+    bool     advance = false;   // the track left `node` alive and a next child exists (MULTI)
     uint32_t spot_ind = kEmptyKey32;
     uint32_t h0 = 0, h1 = 0, blk = 0;   // Philox counter of the current history
     const uint32_t k0 = (uint32_t) P.seed, k1 = (uint32_t) (P.seed >> 32);
     unsigned n_steps = 0, n_done = 0, n_sec = 0, n_ovf = 0;
 
-    // Warp-level reconvergence.  The re-arm below is executed by the few lanes whose track just ended;
+    // the warp's queue of pre-sampled primaries
+    const int lane      = threadIdx.x & 31;
+    uint32_t* q         = sm.queue + (threadIdx.x >> 5) * kQueueWords;
+    int       q_n       = 0;       // entries in the queue (warp-uniform)
+    bool      src_empty = false;   // the history counter is exhausted (warp-uniform)
+
+    // Warp-level reconvergence.  Restarting a lane is executed by the few lanes whose track just ended;
     // without an explicit join the compiler only reconverges them at the END of the iteration, i.e. the
-    // whole step body ran twice per re-arm (once for the re-armed lane alone: 13 % of all issue slots in
-    // ncu).  The full-warp vote after the re-arm is the join: every lane executes it once per turn, and
-    // the warp leaves the loop together once all of its lanes found the history counter exhausted.
-    bool done = false;   // this lane found the history counter exhausted
+    // whole step body ran twice per restart (once for the restarted lane alone: 13 % of all issue slots in
+    // ncu).  The full-warp votes below are the join: every lane executes them once per turn, and the
+    // warp leaves the loop together once all of its lanes found the source exhausted.
+    bool done = false;   // this lane found the queue empty and the history counter exhausted
     while (true) {
-        // ------------------------------------------------------------------ re-arm the lane
+        // ------------------------------------------------------------------ restart the lane
+        bool need = false;   // the lane needs a new primary
         if (!alive && !done) {
-            LaneIO L;
-            L.sp = sp; L.h0 = h0; L.h1 = h1; L.blk = blk; L.spot_ind = spot_ind; L.n_done = 0;
-            const int rc = rearm_lane(P, stack, L);
-            sp = L.sp;
-            n_done += L.n_done;
-            done = rc == REARM_EXIT;
-            if (!done) {
-                h0 = L.h0; h1 = L.h1; blk = L.blk; spot_ind = L.spot_ind;
-                px = L.px; py = L.py; pz = L.pz; dx = L.dx; dy = L.dy; dz = L.dz;
-                ke = L.ke; recoil = VARIANT == MQI_K_DEBUG && L.recoil != 0;
-                ix = L.ix; iy = L.iy; iz = L.iz;
-                alive = rc == REARM_ALIVE;   // REARM_MISSED: the track never enters the grid, fetch again next turn
+            if ((MULTI && advance) || sp > 0) {
+                TrackIO T;
+                T.px = px; T.py = py; T.pz = pz; T.dx = dx; T.dy = dy; T.dz = dz; T.ke = ke;
+                T.recoil = 0; T.node = node; T.sp = sp;
+                alive = restart_lane<MULTI>(P, stack, T, MULTI && advance ? 1 : 0);
+                sp      = T.sp;
+                advance = false;
+                if (alive) {
+                    px = T.px; py = T.py; pz = T.pz; dx = T.dx; dy = T.dy; dz = T.dz;
+                    ke = T.ke; recoil = VARIANT == MQI_K_DEBUG && T.recoil != 0;
+                    ix = T.ix; iy = T.iy; iz = T.iz;
+                    if (MULTI) node = T.node;
+                }   // else: the track never enters the geometry, try again next turn
+            } else {
+                need = true;
             }
+        }
+        const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+        if (need_mask) {
+            const int n_need = __popc(need_mask);
+            if (q_n < n_need && !src_empty) {   // warp-uniform: every lane helps to refill
+                const int r = refill_queue<MULTI>(P, q, q_n);
+                q_n       = r & 0xffff;
+                src_empty = ((r >> 16) & 1) != 0;
+                n_done += (unsigned) (r >> 17) & 1u;
+            }
+            if (need) {
+                const int e = q_n - 1 - __popc(need_mask & ((1u << lane) - 1u));
+                if (e >= 0) {
+                    const uint32_t* qe = q + e;
+                    px = __uint_as_float(qe[Q_PX * kQueueCap]); py = __uint_as_float(qe[Q_PY * kQueueCap]);
+                    pz = __uint_as_float(qe[Q_PZ * kQueueCap]); dx = __uint_as_float(qe[Q_DX * kQueueCap]);
+                    dy = __uint_as_float(qe[Q_DY * kQueueCap]); dz = __uint_as_float(qe[Q_DZ * kQueueCap]);
+                    ke = __uint_as_float(qe[Q_KE * kQueueCap]);
+                    ix = (int) qe[Q_IX * kQueueCap]; iy = (int) qe[Q_IY * kQueueCap]; iz = (int) qe[Q_IZ * kQueueCap];
+                    h0 = qe[Q_H0 * kQueueCap]; h1 = qe[Q_H1 * kQueueCap];
+                    spot_ind = qe[Q_SPOT * kQueueCap];
+                    if (MULTI) node = (int) qe[Q_NODE * kQueueCap];
+                    blk    = P.src.vertices ? 0u : 2u;   // blocks 0-1 belong to the source sampling
+                    recoil = false;
+                    alive  = true;
+                } else if (src_empty) {
+                    done = true;
+                }
+            }
+            __syncwarp();   // the queue slots just read may be overwritten by the next refill
+            q_n = max(q_n - n_need, 0);
         }
         if (__all_sync(0xffffffffu, done)) break;
         if (!alive) continue;   // taken after the join: the lane idles this turn, the others are converged
 
         // ------------------------------------------------------------------ one voxel step
         ++n_steps;
-        const float ex0 = sm.xe[ix], ex1 = sm.xe[ix + 1];
-        const float ey0 = sm.ye[iy], ey1 = sm.ye[iy + 1];
-        const float ez0 = sm.ze[iz], ez1 = sm.ze[iz + 1];
+        const GridDev& G  = node_ref<MULTI>(P, sm, node);
+        const int      nx = G.nx, ny = G.ny, nz = G.nz;
+        const float*   xe = sm.edges + (MULTI ? G.edge_off : 0);
+        const float*   ye = xe + nx + 1;
+        const float*   ze = ye + ny + 1;
+        const float ex0 = xe[ix], ex1 = xe[ix + 1];
+        const float ey0 = ye[iy], ey1 = ye[iy + 1];
+        const float ez0 = ze[iz], ez1 = ze[iz + 1];
         const unsigned cnb = ((unsigned) iz * (unsigned) ny + (unsigned) iy) * (unsigned) nx + (unsigned) ix;
         // material of the voxel: two dependent loads (index volume -> LUT entry); everything up to the
         // first use of M (random numbers, kinematics, table rows, voxel exit distance) depends on the
         // lane state alone
 #if MQI_K_LATE_LUT
-        const unsigned mat_idx = __ldg(P.g.mat + cnb);
+        const unsigned mat_idx = __ldg(G.mat + cnb);
 #else
-        const MatEntry M = P.g.lut[__ldg(P.g.mat + cnb)];
+        const MatEntry M = G.lut[__ldg(G.mat + cnb)];
 #endif
 
         // the per-step Philox block {u_mfp, u_a, u_b, u_phi}; consumed (blk advances) only if the step
@@ -657,7 +829,7 @@ transport_kernel(const __grid_constant__ Params P) {
         // The LUT entry is addressed only now: the address takes the (always clear) sign bit of u_mfp as
         // a data dependency, so that the in-order issue does not park the warp on the index load
         // before the ~100 independent instructions above have been issued.
-        const MatEntry M = P.g.lut[mat_idx + (__float_as_uint(u_mfp) >> 31)];
+        const MatEntry M = G.lut[mat_idx + (__float_as_uint(u_mfp) >> 31)];
 #endif
         float       d1x = dx, d1y = dy, d1z = dz;   // vtx1.dir: copy taken before intersect() zeroes tiny components
         const float tx = cell_tmax_axis(ex0, ex1, nx, px, dx, ix);
@@ -793,9 +965,9 @@ transport_kernel(const __grid_constant__ Params P) {
                         io.ke1 = ke1; io.dE = res.dE; io.local_dE = res.local_dE;
                         io.u = u - c0; io.e_cs = use1 ? ke : e2; io.rho = rho;
                         io.stopped = stopped ? 1 : 0;
-                        io.sp = sp; io.n_sec = 0; io.n_ovf = 0;
+                        io.sp = sp; io.node = node; io.n_sec = 0; io.n_ovf = 0;
                         io.rb.blk = blk; io.rb.pos = 4; io.rb.h0 = h0; io.rb.h1 = h1; io.rb.k0 = k0; io.rb.k1 = k1;
-                        nuclear_event<VARIANT>(P, stack, io);
+                        nuclear_event<VARIANT, MULTI>(P, stack, io);
                         d1x = io.d1x; d1y = io.d1y; d1z = io.d1z;
                         ke1 = io.ke1; res.dE = io.dE; res.local_dE = io.local_dE;
                         stopped = io.stopped != 0;
@@ -807,7 +979,9 @@ transport_kernel(const __grid_constant__ Params P) {
 
             // -------------------------------------------------------------- scoring, :204-225
             const float inv_vol = 1.0f / ((ex1 - ex0) * (ey1 - ey0) * (ez1 - ez0));
-            if (SIMPLE) {
+            if (MULTI && node != P.n_nodes - 1) {
+                // beamline children carry no scorers (n_scorers = 0, mqi_tps_env.hpp:751)
+            } else if (SIMPLE) {
                 // dose_to_water: (dE + local_dE) * 1.60218e-10 / (V * rho * rsp(rho, vtx0.ke)); voxel 0 is
                 // never scored (roi_->idx(cnb) > 0, B1); insert_hashtable skips value <= 0.  The debug
                 // variant's zero-energy delta daughter scores its own hit with rsp(rho, 0).
@@ -832,7 +1006,10 @@ transport_kernel(const __grid_constant__ Params P) {
             dx = d1x; dy = d1y; dz = d1z;
             ke = ke1;
             recoil = false;
-            if ((unsigned) ix >= (unsigned) nx || (unsigned) iy >= (unsigned) ny || (unsigned) iz >= (unsigned) nz) alive = false;
+            if ((unsigned) ix >= (unsigned) nx || (unsigned) iy >= (unsigned) ny || (unsigned) iz >= (unsigned) nz) {
+                alive = false;
+                if (MULTI) advance = node + 1 < P.n_nodes;   // the c_ind loop hands the track to the next child
+            }
         }
     }
 
@@ -1099,26 +1276,27 @@ static inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
 }
 
 size_t
-transport_smem_bytes(int nx, int ny, int nz) {
-    return kTableN * (2 * sizeof(float4) + sizeof(float2)) + (size_t) (nx + ny + nz + 3) * sizeof(float);
+transport_smem_bytes(int n_edge_floats, int n_nodes) {
+    return smem_queue_offset(n_edge_floats, n_nodes) + (size_t) (MQI_K_BLOCK / 32) * kQueueWords * sizeof(uint32_t);
 }
 
 typedef void (*transport_fn)(const Params);
 static transport_fn
-pick_transport(int variant, bool simple) {
-    if (variant == MQI_K_DEBUG) return simple ? transport_kernel<MQI_K_DEBUG, true> : transport_kernel<MQI_K_DEBUG, false>;
-    return simple ? transport_kernel<MQI_K_RELEASE, true> : transport_kernel<MQI_K_RELEASE, false>;
+pick_transport(int variant, bool simple, bool multi) {
+    if (multi) return variant == MQI_K_DEBUG ? transport_kernel<MQI_K_DEBUG, false, true> : transport_kernel<MQI_K_RELEASE, false, true>;
+    if (variant == MQI_K_DEBUG) return simple ? transport_kernel<MQI_K_DEBUG, true, false> : transport_kernel<MQI_K_DEBUG, false, false>;
+    return simple ? transport_kernel<MQI_K_RELEASE, true, false> : transport_kernel<MQI_K_RELEASE, false, false>;
 }
 
-// one dense Dose scorer -> the specialised kernel
+// one dense Dose scorer with a DIRECT roi on a single-node world -> the specialised kernel
 bool
 transport_is_simple(const Params& p) {
-    return p.n_scorers == 1 && p.sc[0].kind == MQI_K_DOSE && !(p.quirks & MQI_K_QUIRK_B2);
+    return p.n_nodes == 1 && p.n_scorers == 1 && p.sc[0].kind == MQI_K_DOSE && !p.sc[0].roi && !(p.quirks & MQI_K_QUIRK_B2);
 }
 
 cudaError_t
-transport_occupancy(int variant, bool simple, size_t smem, int* blocks_per_sm) {
-    transport_fn f = pick_transport(variant, simple);
+transport_occupancy(const Params& p, int variant, size_t smem, int* blocks_per_sm) {
+    transport_fn f = pick_transport(variant, transport_is_simple(p), p.n_nodes > 1);
     cudaError_t  e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, f, MQI_K_BLOCK, smem);
@@ -1126,7 +1304,7 @@ transport_occupancy(int variant, bool simple, size_t smem, int* blocks_per_sm) {
 
 cudaError_t
 launch_transport(const Params& p, int variant, int grid, size_t smem, cudaStream_t st) {
-    pick_transport(variant, transport_is_simple(p))<<<grid, MQI_K_BLOCK, smem, st>>>(p);
+    pick_transport(variant, transport_is_simple(p), p.n_nodes > 1)<<<grid, MQI_K_BLOCK, smem, st>>>(p);
     return cudaGetLastError();
 }
 

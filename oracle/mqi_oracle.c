@@ -1251,29 +1251,86 @@ mqo_insert(mqo_scorer* s, const uint32_t* key1, const uint32_t* key2, const doub
 /* ------------------------------------------------------------------------------------------- */
 /* transport_particles_patient mqi_transport.hpp:113-250                                         */
 /* ------------------------------------------------------------------------------------------- */
+static void
+ctx_set_node(ctx_t* c, const mqo_grid* g) {
+    c->g = g;
+    c->rot_fwd.xx = g->rot_fwd[0]; c->rot_fwd.xy = g->rot_fwd[1]; c->rot_fwd.xz = g->rot_fwd[2];
+    c->rot_fwd.yx = g->rot_fwd[3]; c->rot_fwd.yy = g->rot_fwd[4]; c->rot_fwd.yz = g->rot_fwd[5];
+    c->rot_fwd.zx = g->rot_fwd[6]; c->rot_fwd.zy = g->rot_fwd[7]; c->rot_fwd.zz = g->rot_fwd[8];
+    /* inverse() is the transpose: mqi_matrix.hpp:291-295 */
+    c->rot_inv.xx = c->rot_fwd.xx; c->rot_inv.xy = c->rot_fwd.yx; c->rot_inv.xz = c->rot_fwd.zx;
+    c->rot_inv.yx = c->rot_fwd.xy; c->rot_inv.yy = c->rot_fwd.yy; c->rot_inv.yz = c->rot_fwd.zy;
+    c->rot_inv.zx = c->rot_fwd.xz; c->rot_inv.zy = c->rot_fwd.yz; c->rot_inv.zz = c->rot_fwd.zz;
+    c->trans = v3_make(g->trans[0], g->trans[1], g->trans[2]);
+}
+
+/* roi_t::idx(cnb) > 0 (mqi_transport.hpp:205,216; mqi_roi.hpp:48-58,127-137): a DIRECT roi returns cnb
+ * itself (voxel 0 is never scored, B1); a CONTOUR roi (mask_reader::mask_to_roi, mqi_file_handler.hpp:
+ * 176-217) returns 1 inside a run of the mask and -1 outside.  The mask here is the run-length ROI
+ * expanded back to one byte per voxel (mqo_mask_to_roi). */
+static inline int
+roi_accepts(const uint8_t* mask, uint64_t cnb) {
+    if (!mask) return (int32_t) (uint32_t) cnb > 0;
+    return mask[cnb] != 0;
+}
+
+/* mask_reader::mask_to_roi mqi_file_handler.hpp:176-217 restated on the summed mask volume
+ * (read_mask_files adds the 0/1 masks of all files, :107-113): a run starts at a voxel whose sum is
+ * exactly 1 while no run is open and ends at the next voxel whose sum is 0.  Voxels with a sum >= 2
+ * neither open nor close a run.  A run still open at the end of the volume has no stride in the
+ * reference (uninitialised read); it is closed at the volume end here.  Returns the number of runs;
+ * start/stride (capacity max_runs each) and the expanded 0/1 membership are written when non-NULL. */
+uint32_t
+mqo_mask_to_roi(const uint8_t* mask_total, uint64_t n, uint32_t* start, uint32_t* stride, uint32_t max_runs,
+                uint8_t* member) {
+    uint32_t runs = 0;
+    int      open = 0;
+    uint64_t i, s0 = 0;
+    if (member) memset(member, 0, n);
+    for (i = 0; i < n; ++i) {
+        if (mask_total[i] == 1 && !open) {
+            open = 1;
+            s0   = i;
+        }
+        if (mask_total[i] == 0 && open) {
+            open = 0;
+            if (runs < max_runs) {
+                if (start) start[runs] = (uint32_t) s0;
+                if (stride) stride[runs] = (uint32_t) (i - s0);
+            }
+            if (member) memset(member + s0, 1, i - s0);
+            ++runs;
+        }
+    }
+    if (open) {
+        if (runs < max_runs) {
+            if (start) start[runs] = (uint32_t) s0;
+            if (stride) stride[runs] = (uint32_t) (n - s0);
+        }
+        if (member) memset(member + s0, 1, n - s0);
+        ++runs;
+    }
+    return runs;
+}
+
+/* The world's children in order (beamline objects first, the patient / phantom grid last:
+ * mqi_tps_env.hpp:732-758); scorers belong to the LAST node (beamline nodes have n_scorers = 0, :751).
+ * roi_masks[s] (may be NULL as a whole or per scorer) is the expanded CONTOUR roi of scorer s. */
 int
-mqo_transport(const mqo_grid* g, int variant, uint32_t quirks, const mqo_beamlet* beamlets,
-              const uint64_t* cum_histories, uint32_t n_beamlets, const mqo_vertex* vertices,
-              const uint32_t* spot_ids, int per_spot, uint64_t seed, uint64_t h0, uint64_t n,
-              mqo_scorer* scorers, int n_scorers, mqo_stats* stats) {
+mqo_transport_nodes(const mqo_grid* nodes, int n_nodes, int variant, uint32_t quirks, const mqo_beamlet* beamlets,
+                    const uint64_t* cum_histories, uint32_t n_beamlets, const mqo_vertex* vertices,
+                    const uint32_t* spot_ids, int per_spot, uint64_t seed, uint64_t h0, uint64_t n,
+                    mqo_scorer* scorers, int n_scorers, const uint8_t* const* roi_masks, mqo_stats* stats) {
     ctx_t     c;
     rng_t     rng;
     tstack_t* stk;
     uint64_t  i;
     if (!g_tables_loaded) return -1;
+    if (n_nodes < 1) return -4;
     stk = (tstack_t*) malloc(sizeof(tstack_t));
     if (!stk) return -2;
     memset(&c, 0, sizeof(c));
-    c.g       = g;
     c.variant = variant;
-    c.rot_fwd.xx = g->rot_fwd[0]; c.rot_fwd.xy = g->rot_fwd[1]; c.rot_fwd.xz = g->rot_fwd[2];
-    c.rot_fwd.yx = g->rot_fwd[3]; c.rot_fwd.yy = g->rot_fwd[4]; c.rot_fwd.yz = g->rot_fwd[5];
-    c.rot_fwd.zx = g->rot_fwd[6]; c.rot_fwd.zy = g->rot_fwd[7]; c.rot_fwd.zz = g->rot_fwd[8];
-    /* inverse() is the transpose: mqi_matrix.hpp:291-295 */
-    c.rot_inv.xx = c.rot_fwd.xx; c.rot_inv.xy = c.rot_fwd.yx; c.rot_inv.xz = c.rot_fwd.zx;
-    c.rot_inv.yx = c.rot_fwd.xy; c.rot_inv.yy = c.rot_fwd.yy; c.rot_inv.yz = c.rot_fwd.zy;
-    c.rot_inv.zx = c.rot_fwd.xz; c.rot_inv.zy = c.rot_fwd.yz; c.rot_inv.zz = c.rot_fwd.zz;
-    c.trans = v3_make(g->trans[0], g->trans[1], g->trans[2]);
     c.T_cut = (variant == MQO_VARIANT_DEBUG) ? 0.08511 * 1.0f : 0.0815 * 1.0f;
     c.rng   = &rng;
     c.stk   = stk;
@@ -1315,73 +1372,101 @@ mqo_transport(const mqo_grid* g, int variant, uint32_t quirks, const mqo_beamlet
 
         while (stk->idx != 0) {
             track_t track = stk->tracks[--stk->idx];
-            float   p[3], d[3];
-            int     checker[3];
-            /* single child node (the patient / phantom grid): world -> local :165-170 */
-            track.vtx0.pos = m33_mul(&c.rot_inv, v3_sub(track.vtx0.pos, c.trans));
-            track.vtx0.dir = v3_normalize(m33_mul(&c.rot_inv, track.vtx0.dir));
-            track.vtx1.pos = track.vtx0.pos;
-            track.vtx1.dir = track.vtx0.dir;
-            p[0] = track.vtx0.pos.x; p[1] = track.vtx0.pos.y; p[2] = track.vtx0.pos.z;
-            d[0] = track.vtx0.dir.x; d[1] = track.vtx0.dir.y; d[2] = track.vtx0.dir.z;
-            mqo_grid_index(g, p, d, checker);
-            if (!grid_is_valid(g, checker)) {
-                int   ecell[3];
-                float dist = mqo_grid_intersect_entry(g, p, d, ecell);
-                track.vtx0.dir = v3_make(d[0], d[1], d[2]); /* intersect() zeroes tiny components in place */
-                track.its_dist = dist;
-                if (dist < 0) { continue; }
-                track.vtx1.pos = v3_add(track.vtx0.pos, v3_scale(track.vtx0.dir, dist));
-                track.vtx0     = track.vtx1; /* move(): note vtx1.dir still holds the un-zeroed copy */
-                track.dE       = 0;
-                track.local_dE = 0;
+            int     c_ind;
+            for (c_ind = 0; c_ind < n_nodes; ++c_ind) { /* :162 */
+                const mqo_grid* g = &nodes[c_ind];
+                const int nb_of_scorers = (c_ind == n_nodes - 1) ? n_scorers : 0;
+                float   p[3], d[3];
+                int     checker[3];
+                ctx_set_node(&c, g);
+                /* world -> local :165-170 */
+                track.vtx0.pos = m33_mul(&c.rot_inv, v3_sub(track.vtx0.pos, c.trans));
+                track.vtx0.dir = v3_normalize(m33_mul(&c.rot_inv, track.vtx0.dir));
+                track.vtx1.pos = track.vtx0.pos;
+                track.vtx1.dir = track.vtx0.dir;
                 p[0] = track.vtx0.pos.x; p[1] = track.vtx0.pos.y; p[2] = track.vtx0.pos.z;
                 d[0] = track.vtx0.dir.x; d[1] = track.vtx0.dir.y; d[2] = track.vtx0.dir.z;
-                mqo_grid_index(g, p, d, track.cell);
-            } else {
-                track.its_dist = 0.0;
-                track.cell[0] = checker[0]; track.cell[1] = checker[1]; track.cell[2] = checker[2];
-            }
-            while (grid_is_valid(g, track.cell) && !track.stopped) {
-                uint64_t cnb = (uint64_t) track.cell[2] * g->nx * g->ny + (uint64_t) track.cell[1] * g->nx + track.cell[0];
-                int      s, pass;
-                p[0] = track.vtx0.pos.x; p[1] = track.vtx0.pos.y; p[2] = track.vtx0.pos.z;
-                d[0] = track.vtx0.dir.x; d[1] = track.vtx0.dir.y; d[2] = track.vtx0.dir.z;
-                track.its_dist = mqo_grid_intersect_cell(g, p, d, track.cell);
-                track.vtx0.dir = v3_make(d[0], d[1], d[2]);
-                if (stats) stats->steps++;
-                if (track.its_dist < 0) {
-                    /* the reference still calls stepping() with a negative distance (which poisons
-                     * the track with NaN) and then breaks without scoring: :195-202 */
-                    break;
-                }
-                stepping(&c, &track, g->rho[cnb], track.its_dist);
-                /* scoring :204-225; roi_->idx(cnb) > 0 with a DIRECT roi means voxel 0 is never scored */
-                for (pass = 0; pass < 2; ++pass) {
-                    int s_end = n_scorers;
-                    if (pass == 0) {
-                        if (!(quirks & MQO_QUIRK_B2_DOUBLE_SCORE)) continue;
-                        s_end = n_scorers - 2;
+                mqo_grid_index(g, p, d, checker);
+                if (!grid_is_valid(g, checker)) {
+                    int   ecell[3];
+                    float dist = mqo_grid_intersect_entry(g, p, d, ecell);
+                    track.vtx0.dir = v3_make(d[0], d[1], d[2]); /* intersect() zeroes tiny components in place */
+                    track.its_dist = dist;
+                    if (dist < 0) { /* :176-185: back to the world frame, next child */
+                        track.vtx0.pos = v3_add(m33_mul(&c.rot_fwd, track.vtx0.pos), c.trans);
+                        track.vtx0.dir = m33_mul(&c.rot_fwd, track.vtx0.dir);
+                        track.vtx1.pos = track.vtx0.pos;
+                        track.vtx1.dir = track.vtx0.dir;
+                        continue;
                     }
-                    for (s = 0; s < s_end; ++s) {
-                        if ((int32_t) (uint32_t) cnb > 0) {
-                            insert_scorer(&scorers[s], (uint32_t) cnb, spot_ind,
-                                          compute_hit(&c, scorers[s].kind, &track, cnb));
-                        }
-                    }
-                }
-                if (!track.stopped) {
-                    float q[3] = { track.vtx1.pos.x, track.vtx1.pos.y, track.vtx1.pos.z };
-                    float e[3] = { track.vtx1.dir.x, track.vtx1.dir.y, track.vtx1.dir.z };
-                    mqo_grid_index_update(g, q, e, track.cell);
-                    track.vtx0     = track.vtx1;
+                    track.vtx1.pos = v3_add(track.vtx0.pos, v3_scale(track.vtx0.dir, dist));
+                    track.vtx0     = track.vtx1; /* move(): note vtx1.dir still holds the un-zeroed copy */
                     track.dE       = 0;
                     track.local_dE = 0;
+                    p[0] = track.vtx0.pos.x; p[1] = track.vtx0.pos.y; p[2] = track.vtx0.pos.z;
+                    d[0] = track.vtx0.dir.x; d[1] = track.vtx0.dir.y; d[2] = track.vtx0.dir.z;
+                    mqo_grid_index(g, p, d, track.cell);
+                } else {
+                    track.its_dist = 0.0;
+                    track.cell[0] = checker[0]; track.cell[1] = checker[1]; track.cell[2] = checker[2];
                 }
+                while (grid_is_valid(g, track.cell) && !track.stopped) {
+                    uint64_t cnb = (uint64_t) track.cell[2] * g->nx * g->ny + (uint64_t) track.cell[1] * g->nx + track.cell[0];
+                    int      s, pass;
+                    p[0] = track.vtx0.pos.x; p[1] = track.vtx0.pos.y; p[2] = track.vtx0.pos.z;
+                    d[0] = track.vtx0.dir.x; d[1] = track.vtx0.dir.y; d[2] = track.vtx0.dir.z;
+                    track.its_dist = mqo_grid_intersect_cell(g, p, d, track.cell);
+                    track.vtx0.dir = v3_make(d[0], d[1], d[2]);
+                    if (stats) stats->steps++;
+                    if (track.its_dist < 0) {
+                        /* the reference still calls stepping() with a negative distance (which poisons
+                         * the track with NaN) and then breaks without scoring: :195-202.  The poisoned
+                         * track fails every later index / intersect test, i.e. it is lost. */
+                        track.stopped = 1;
+                        break;
+                    }
+                    stepping(&c, &track, g->rho[cnb], track.its_dist);
+                    /* scoring :204-225 */
+                    for (pass = 0; pass < 2; ++pass) {
+                        int s_end = nb_of_scorers;
+                        if (pass == 0) {
+                            if (!(quirks & MQO_QUIRK_B2_DOUBLE_SCORE)) continue;
+                            s_end = nb_of_scorers - 2;
+                        }
+                        for (s = 0; s < s_end; ++s) {
+                            if (roi_accepts(roi_masks ? roi_masks[s] : NULL, cnb)) {
+                                insert_scorer(&scorers[s], (uint32_t) cnb, spot_ind,
+                                              compute_hit(&c, scorers[s].kind, &track, cnb));
+                            }
+                        }
+                    }
+                    if (!track.stopped) {
+                        float q[3] = { track.vtx1.pos.x, track.vtx1.pos.y, track.vtx1.pos.z };
+                        float e[3] = { track.vtx1.dir.x, track.vtx1.dir.y, track.vtx1.dir.z };
+                        mqo_grid_index_update(g, q, e, track.cell);
+                        track.vtx0     = track.vtx1;
+                        track.dE       = 0;
+                        track.local_dE = 0;
+                    }
+                }
+                /* local -> world :234-239 */
+                track.vtx0.pos = v3_add(m33_mul(&c.rot_fwd, track.vtx0.pos), c.trans);
+                track.vtx0.dir = m33_mul(&c.rot_fwd, track.vtx0.dir);
+                track.vtx1.pos = track.vtx0.pos;
+                track.vtx1.dir = track.vtx0.dir;
             }
         }
         if (stats) stats->histories++;
     }
     free(stk);
     return 0;
+}
+
+int
+mqo_transport(const mqo_grid* g, int variant, uint32_t quirks, const mqo_beamlet* beamlets,
+              const uint64_t* cum_histories, uint32_t n_beamlets, const mqo_vertex* vertices,
+              const uint32_t* spot_ids, int per_spot, uint64_t seed, uint64_t h0, uint64_t n,
+              mqo_scorer* scorers, int n_scorers, mqo_stats* stats) {
+    return mqo_transport_nodes(g, 1, variant, quirks, beamlets, cum_histories, n_beamlets, vertices, spot_ids,
+                               per_spot, seed, h0, n, scorers, n_scorers, NULL, stats);
 }

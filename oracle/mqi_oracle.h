@@ -117,6 +117,16 @@ int mqo_transport(const mqo_grid* g, int variant, uint32_t quirks, const mqo_bea
                   const uint32_t* spot_ids, int per_spot, uint64_t seed, uint64_t h0, uint64_t n,
                   mqo_scorer* scorers, int n_scorers, mqo_stats* stats);
 
+/* Multi-node world (beamline children first, patient grid last, mqi_tps_env.hpp:732-758) and per-scorer
+ * CONTOUR regions of interest (expanded masks, see mqo_mask_to_roi); scorers belong to the last node. */
+int mqo_transport_nodes(const mqo_grid* nodes, int n_nodes, int variant, uint32_t quirks, const mqo_beamlet* beamlets,
+                        const uint64_t* cum_histories, uint32_t n_beamlets, const mqo_vertex* vertices,
+                        const uint32_t* spot_ids, int per_spot, uint64_t seed, uint64_t h0, uint64_t n,
+                        mqo_scorer* scorers, int n_scorers, const uint8_t* const* roi_masks, mqo_stats* stats);
+/* mask_reader::mask_to_roi (mqi_file_handler.hpp:176-217) on the summed mask volume */
+uint32_t mqo_mask_to_roi(const uint8_t* mask_total, uint64_t n, uint32_t* start, uint32_t* stride, uint32_t max_runs,
+                         uint8_t* member);
+
 #ifdef __cplusplus
 }
 #endif

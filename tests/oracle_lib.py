@@ -155,11 +155,32 @@ def insert(kind, key1, key2, value, capacity=0, nvox=0):
     return tab
 
 
-def transport(grid, variant, beamlets, histories_per_spot, seed, h0, n, kinds, quirks=0, per_spot=False,
-              dij_capacity=0, vertices=None, spot_ids=None):
-    """Run the oracle; returns (list of outputs per scorer, Stats).  Dense scorers -> float64[nvox];
-    Dij -> structured array of occupied slots (key1, key2, value)."""
+def mask_to_roi(mask_total):
+    """mask_reader::mask_to_roi restated: returns (start, stride, member) of the run-length CONTOUR roi."""
     L = lib()
+    m = np.ascontiguousarray(mask_total, dtype=np.uint8).ravel()
+    member = np.zeros(m.size, dtype=np.uint8)
+    L.mqo_mask_to_roi.restype = C.c_uint32
+    u8 = C.POINTER(C.c_uint8)
+    u32 = C.POINTER(C.c_uint32)
+    n = L.mqo_mask_to_roi(m.ctypes.data_as(u8), C.c_uint64(m.size), None, None, C.c_uint32(0), member.ctypes.data_as(u8))
+    start = np.zeros(max(n, 1), dtype=np.uint32)
+    stride = np.zeros(max(n, 1), dtype=np.uint32)
+    L.mqo_mask_to_roi(m.ctypes.data_as(u8), C.c_uint64(m.size), start.ctypes.data_as(u32), stride.ctypes.data_as(u32),
+                      C.c_uint32(n), None)
+    return start[:n], stride[:n], member
+
+
+def transport(grid, variant, beamlets, histories_per_spot, seed, h0, n, kinds, quirks=0, per_spot=False,
+              dij_capacity=0, vertices=None, spot_ids=None, roi_members=None):
+    """Run the oracle; returns (list of outputs per scorer, Stats).  Dense scorers -> float64[nvox];
+    Dij -> structured array of occupied slots (key1, key2, value).  `grid` is one Grid or a list of
+    Grids (beamline nodes first, the scored patient grid last); roi_members is an optional list (one
+    entry per scorer, None = DIRECT roi) of expanded CONTOUR roi memberships (mask_to_roi()[2])."""
+    L = lib()
+    nodes = list(grid) if isinstance(grid, (list, tuple)) else [grid]
+    grid = nodes[-1]
+    narr = (Grid * len(nodes))(*nodes)
     nvox = grid.nx * grid.ny * grid.nz
     nb = len(beamlets)
     barr = (Beamlet * max(nb, 1))(*beamlets)
@@ -188,12 +209,24 @@ def transport(grid, variant, beamlets, histories_per_spot, seed, h0, n, kinds, q
         if spot_ids is not None:
             spot_ids = np.ascontiguousarray(spot_ids, dtype=np.uint32)
             sptr = spot_ids.ctypes.data_as(C.POINTER(C.c_uint32))
-    rc = L.mqo_transport(C.byref(grid), C.c_int(variant), C.c_uint32(quirks), barr,
-                         cum.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_uint32(nb), vptr, sptr,
-                         C.c_int(1 if per_spot else 0), C.c_uint64(seed), C.c_uint64(h0), C.c_uint64(n),
-                         sc, C.c_int(len(kinds)), C.byref(st))
+    rptr = None
+    if roi_members is not None:
+        assert len(roi_members) == len(kinds)
+        rarr = (C.POINTER(C.c_uint8) * len(kinds))()
+        for i, m in enumerate(roi_members):
+            if m is not None:
+                m = np.ascontiguousarray(m, dtype=np.uint8).ravel()
+                assert m.size == nvox
+                keep.append(m)
+                rarr[i] = m.ctypes.data_as(C.POINTER(C.c_uint8))
+        rptr = rarr
+    L.mqo_transport_nodes.restype = C.c_int
+    rc = L.mqo_transport_nodes(narr, C.c_int(len(nodes)), C.c_int(variant), C.c_uint32(quirks), barr,
+                               cum.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_uint32(nb), vptr, sptr,
+                               C.c_int(1 if per_spot else 0), C.c_uint64(seed), C.c_uint64(h0), C.c_uint64(n),
+                               sc, C.c_int(len(kinds)), rptr, C.byref(st))
     if rc != 0:
-        raise RuntimeError("mqo_transport rc=%d" % rc)
+        raise RuntimeError("mqo_transport_nodes rc=%d" % rc)
     outs = []
     for k, a in zip(kinds, keep):
         if k == SCORER_DIJ:
