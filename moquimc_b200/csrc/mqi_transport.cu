@@ -587,7 +587,7 @@ restart_lane(const Params& P, const Secondary* stack, TrackIO& T, int advance) {
 // vertices, locates them and appends the ones that enter the geometry to the warp's queue.  Every lane
 // works on its own history: the source sampling and the cell search, which cost about as much as one
 // voxel step, run at full SIMT width instead of once per lane and history.  Returns the new queue
-// length | source exhausted << 16 | this lane fetched a history << 17.
+// length | source exhausted << 16.
 template<bool MULTI>
 __device__ __noinline__ int
 refill_queue(const Params& P, uint32_t* q, int q_n) {
@@ -628,6 +628,8 @@ refill_queue(const Params& P, uint32_t* q, int q_n) {
         alive    = enter_nodes<MULTI>(P, sm, T);
     }
     const unsigned m = __ballot_sync(0xffffffffu, alive);
+    const unsigned fetched = __ballot_sync(0xffffffffu, have);
+    if (lane == 0 && fetched) atomicAdd(P.counters + C_DONE, (unsigned long long) __popc(fetched));   // :245 tracked_particles
     if (alive) {
         uint32_t* e = q + q_n + __popc(m & ((1u << lane) - 1u));
         e[Q_PX * kQueueCap] = __float_as_uint(T.px); e[Q_PY * kQueueCap] = __float_as_uint(T.py);
@@ -641,7 +643,7 @@ refill_queue(const Params& P, uint32_t* q, int q_n) {
     }
     __syncwarp();
     const int exhausted = base + 32ull >= P.count ? 1 : 0;
-    return (q_n + __popc(m)) | (exhausted << 16) | ((have ? 1 : 0) << 17);
+    return (q_n + __popc(m)) | (exhausted << 16);
 }
 
 // further tries of the delta-electron energy rejection loop (about one event in ten needs them):
@@ -707,13 +709,11 @@ transport_kernel(const __grid_constant__ Params P) {
     uint32_t spot_ind = kEmptyKey32;
     uint32_t h0 = 0, h1 = 0, blk = 0;   // Philox counter of the current history
     const uint32_t k0 = (uint32_t) P.seed, k1 = (uint32_t) (P.seed >> 32);
-    unsigned n_steps = 0, n_done = 0, n_sec = 0, n_ovf = 0;
+    unsigned n_steps = 0;
 
-    // the warp's queue of pre-sampled primaries
-    const int lane      = threadIdx.x & 31;
-    uint32_t* q         = sm.queue + (threadIdx.x >> 5) * kQueueWords;
-    int       q_n       = 0;       // entries in the queue (warp-uniform)
-    bool      src_empty = false;   // the history counter is exhausted (warp-uniform)
+    // the warp's queue of pre-sampled primaries: entries in the queue | history counter exhausted << 16
+    // (warp-uniform; one register)
+    int q_state = 0;
 
     // Warp-level reconvergence.  Restarting a lane is executed by the few lanes whose track just ended;
     // without an explicit join the compiler only reconverges them at the END of the iteration, i.e. the
@@ -745,12 +745,11 @@ transport_kernel(const __grid_constant__ Params P) {
         const unsigned need_mask = __ballot_sync(0xffffffffu, need);
         if (need_mask) {
             const int n_need = __popc(need_mask);
-            if (q_n < n_need && !src_empty) {   // warp-uniform: every lane helps to refill
-                const int r = refill_queue<MULTI>(P, q, q_n);
-                q_n       = r & 0xffff;
-                src_empty = ((r >> 16) & 1) != 0;
-                n_done += (unsigned) (r >> 17) & 1u;
-            }
+            const int lane   = threadIdx.x & 31;
+            uint32_t* q      = sm.queue + (threadIdx.x >> 5) * kQueueWords;
+            if (q_state < n_need) q_state = refill_queue<MULTI>(P, q, q_state);   // warp-uniform (not exhausted, too few entries): every lane helps
+            const int  q_n       = q_state & 0xffff;
+            const bool src_empty = (q_state >> 16) != 0;
             if (need) {
                 const int e = q_n - 1 - __popc(need_mask & ((1u << lane) - 1u));
                 if (e >= 0) {
@@ -771,7 +770,7 @@ transport_kernel(const __grid_constant__ Params P) {
                 }
             }
             __syncwarp();   // the queue slots just read may be overwritten by the next refill
-            q_n = max(q_n - n_need, 0);
+            q_state = max(q_n - n_need, 0) | (q_state & 0x10000);
         }
         if (__all_sync(0xffffffffu, done)) break;
         if (!alive) continue;   // taken after the join: the lane idles this turn, the others are converged
@@ -971,7 +970,9 @@ transport_kernel(const __grid_constant__ Params P) {
                         d1x = io.d1x; d1y = io.d1y; d1z = io.d1z;
                         ke1 = io.ke1; res.dE = io.dE; res.local_dE = io.local_dE;
                         stopped = io.stopped != 0;
-                        sp = io.sp; n_sec += io.n_sec; n_ovf += io.n_ovf;
+                        sp = io.sp;
+                        if (io.n_sec) atomicAdd(P.counters + C_SECONDARIES, (unsigned long long) io.n_sec);
+                        if (io.n_ovf) atomicAdd(P.counters + C_OVERFLOW, (unsigned long long) io.n_ovf);
                         blk = io.rb.blk;
                     }
                 }
@@ -1013,11 +1014,8 @@ transport_kernel(const __grid_constant__ Params P) {
         }
     }
 
-    // per-lane counters -> global (one atomic per lane per launch)
-    if (n_done) atomicAdd(P.counters + C_DONE, (unsigned long long) n_done);
+    // per-lane step counter -> global (one atomic per lane per launch)
     if (n_steps && P.count_steps) atomicAdd(P.counters + C_STEPS, (unsigned long long) n_steps);
-    if (n_sec) atomicAdd(P.counters + C_SECONDARIES, (unsigned long long) n_sec);
-    if (n_ovf) atomicAdd(P.counters + C_OVERFLOW, (unsigned long long) n_ovf);
 }
 
 

@@ -9,6 +9,9 @@
 #      (compile error in the non-CUDA branch)       -> print a constant string.
 #   2. moqui/base/mqi_p_ionization.hpp:318-320       uint16 wrap-around in the range-table
 #      walk (out-of-bounds read -> SEGV)            -> stop the walk at n == 0.
+#   3. moqui/base/mqi_file_handler.hpp (scratch copy, used by ref_harness only): the include of
+#      mqi_beam_module_ion.hpp (which pulls in the GDCM headers, absent here) is dropped and the file
+#      is cut before class file_parser, so that mask_reader (mask_to_roi) compiles on its own.
 set -euo pipefail
 REF=${MQI_REFERENCE:-/root/reference}
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -26,6 +29,10 @@ sed '22s/.*/        printf("%d: material\\n", i);/' \
 sed '319s/if (r >= r_steps\[n\]) break;/if (r >= r_steps[n] || n == 0) break;/' \
     "$REF/moqui/base/mqi_p_ionization.hpp" > "$TMP/moqui/base/mqi_p_ionization.hpp"
 grep -q 'n == 0' "$TMP/moqui/base/mqi_p_ionization.hpp" || { echo "patch 2 did not apply" >&2; exit 1; }
+{ sed -n '1,/^class file_parser/p' "$REF/moqui/base/mqi_file_handler.hpp" | sed '$d' \
+    | sed '/mqi_beam_module_ion.hpp/d; s/#include <moqui\/base\/mqi_roi.hpp>/#include <moqui\/base\/mqi_roi.hpp>\n#include <moqui\/base\/mqi_common.hpp>\n#include <moqui\/base\/mqi_vec.hpp>\n#include <cassert>\n#include <cstring>\n#include <string>\n#include <vector>/';
+  printf '}\n#endif\n'; } > "$TMP/moqui/base/mqi_file_handler.hpp"
+grep -q 'mask_to_roi' "$TMP/moqui/base/mqi_file_handler.hpp" || { echo "patch 3 did not apply" >&2; exit 1; }
 CXX=${CXX:-g++}
 FLAGS="-std=c++11 -O2 -w -DNDEBUG -I$TMP -I$REF"
 # phantom_env exactly as the reference's tests/mc/phantom CMake builds it (debug physics) ...

@@ -52,8 +52,73 @@ def c2(energy, procs=8, per_proc=125000):
     print("c2", energy, {k: getattr(v, "shape", None) for k, v in keep.items()})
 
 
+F3_GRID = dict(nxyz=[100, 100, 200], lxyz=[100.0, 100.0, 200.0])
+F3_RS = [100.0, 140.0, 150.0, 1.19]          # zlo zhi half-width density[g/cm3]
+F3_AP = [40.0, 60.0, 40.0, 12.0, 8.0]        # zlo zhi half-width open_hx open_hy
+F3_ANGLE_Z = 30.0                            # the beamline frame is rotated about z and shifted
+F3_TRANS = [2.0, -3.0, 0.0]
+
+
+def f3_frame():
+    a = np.deg2rad(F3_ANGLE_Z)
+    c, s = float(np.float32(np.cos(a))), float(np.float32(np.sin(a)))
+    return [c, -s, 0.0, s, c, 0.0, 0.0, 0.0, 1.0] + F3_TRANS
+
+
+def f4_mask_total(nxyz=(100, 100, 200)):
+    """Sum of two overlapping 0/1 masks (tests/test_gpu_beamline_roi.py::make_mask_total)."""
+    nx, ny, nz = nxyz
+    m1 = np.zeros((nz, ny, nx), dtype=np.uint8)
+    m1[60:190, 30:70, 35:65] = 1
+    m2 = np.zeros((nz, ny, nx), dtype=np.uint8)
+    m2[100:120, 40:60, 35:50] = 1
+    return m1 + m2
+
+
+def f3_beamline(procs=8, per_proc=150000):
+    """range shifter slab + voxelised aperture as beamline children in front of a water
+    phantom (100 x 100 x 200 mm, 1 mm voxels), 150 MeV, 20 mm uniform square spot starting at z = 180,
+    beamline frame rotated 30 deg about z and shifted by (2, -3, 0); release physics, Dose."""
+    import argparse
+    sys.path.insert(0, HERE)
+    import ref_run
+    extra = ["--rangeshifter"] + F3_RS + ["--aperture"] + F3_AP + ["--frame"] + f3_frame()
+    a = argparse.Namespace(variant="release", procs=procs, histories_per_proc=per_proc, energy=150.0, spot_size=20.0,
+                           slab=[], seed=777, rebin=4, harness=True, scorers="dose", gauss=None, out=None,
+                           spot_z=180.0, extra=extra, **F3_GRID)
+    res, meta = ref_run.run(a)
+    keep = {k: v for k, v in res.items() if k == "meta" or k.endswith(("_idd", "_idd_se", "_total", "_total_se", "_xy", "_xy_se", "_xz"))}
+    keep = {k: (v.astype(np.float32) if getattr(v, "ndim", 0) > 1 else v) for k, v in keep.items()}
+    np.savez_compressed(os.path.join(GOLD, "f3_beamline_release.npz"), **keep)
+    print("f3", {k: getattr(v, "shape", None) for k, v in keep.items()})
+
+
+def f4_roi(procs=8, per_proc=100000):
+    """SURVEY 8(f)-4: CONTOUR roi (mask_reader::mask_to_roi) on the Dose scorer; two overlapping masks."""
+    import argparse
+    sys.path.insert(0, HERE)
+    import ref_run
+    with tempfile.TemporaryDirectory() as d:
+        mpath = os.path.join(d, "mask_total.raw")
+        f4_mask_total().tofile(mpath)
+        a = argparse.Namespace(variant="release", procs=procs, histories_per_proc=per_proc, energy=150.0, spot_size=25.0,
+                               slab=[], seed=991, rebin=4, harness=True, scorers="dose", gauss=None, out=None,
+                               spot_z=0.5, extra=["--roi_mask", mpath], **F3_GRID)
+        res, meta = ref_run.run(a)
+    keep = {k: v for k, v in res.items() if k == "meta" or k.endswith(("_idd", "_idd_se", "_total", "_total_se", "_xy", "_xz", "_yz"))}
+    keep = {k: (v.astype(np.float32) if getattr(v, "ndim", 0) > 1 else v) for k, v in keep.items()}
+    np.savez_compressed(os.path.join(GOLD, "f4_roi_release.npz"), **keep)
+    print("f4", {k: getattr(v, "shape", None) for k, v in keep.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "f3":
+        f3_beamline()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "f4":
+        f4_roi()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "c2":
         for e in (70, 150, 230):
             c2(e)

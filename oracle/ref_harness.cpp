@@ -6,6 +6,12 @@
 //
 //   ref_harness <phantom_env flags...> --scorers dose|edep|letd|dose+letd|dij [--nspots N] [--spot_pitch mm]
 //               [--gauss sx sy sxp syp sigmaE]
+//               [--rangeshifter zlo zhi half density_g_cm3]      one-voxel slab, create_rangeshifter style
+//               [--aperture zlo zhi half open_hx open_hy]        1 mm voxels, 1e-8 open / 100 closed
+//               [--frame r00 .. r22 tx ty tz]                    rotation_matrix_fwd / translation of both
+//               [--roi_mask file]                                uint8 summed mask -> mask_to_roi CONTOUR roi
+// Beamline children are inserted in front of the phantom (which becomes the last child, as in
+// tps_env::setup_world mqi_tps_env.hpp:732-758), so dense outputs are named <n_beamline>_<name>.raw.
 // Output (into --output_prefix):
 //   0_<name>.raw            dense float64 [nz][ny][nx] per scorer (reference save_reshaped_files)
 //   dij_key1.raw/_key2.raw/_value.raw    occupied (voxel, spot, value) triplets in slot order
@@ -18,6 +24,7 @@
 #include <vector>
 
 #include <moqui/base/environments/mqi_phantom_env.hpp>
+#include <moqui/base/mqi_file_handler.hpp>
 
 namespace
 {
@@ -27,6 +34,11 @@ struct extra_opts {
     float       spot_pitch = 10.f;
     bool        gauss      = false;
     float       g[5]       = { 0, 0, 0, 0, 0 };   // sx sy sxp syp sigmaE
+    bool        has_rs = false, has_ap = false, has_frame = false;
+    float       rs[4]  = { 0, 0, 0, 0 };          // zlo zhi half density
+    float       ap[5]  = { 0, 0, 0, 0, 0 };       // zlo zhi half open_hx open_hy
+    float       frame[12] = { 1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0 };
+    std::string roi_mask;
 };
 
 class harness_env : public mqi::phantom_env<float>
@@ -44,8 +56,62 @@ public:
         mqi::key_value* t = new mqi::key_value[capacity];
         mqi::init_table(t, capacity);
         s->data_ = t;
-        s->roi_  = new mqi::roi_t(mqi::DIRECT, nvox);
+        s->roi_  = roi_override ? roi_override : new mqi::roi_t(mqi::DIRECT, nvox);
         return s;
+    }
+
+    mqi::roi_t* roi_override = nullptr;
+
+    mqi::node_t<R>*
+    bare_node(mqi::grid3d<mqi::density_t, R>* geo) {
+        mqi::node_t<R>* n = new mqi::node_t<R>;
+        n->n_scorers  = 0;
+        n->scorers    = nullptr;
+        n->n_children = 0;
+        n->children   = nullptr;
+        n->geo        = geo;
+        geo->translation_vector = mqi::vec3<R>(opt.frame[9], opt.frame[10], opt.frame[11]);
+        return n;
+    }
+
+    // beamline children in front of the phantom, built like create_rangeshifter / create_voxelized_aperture
+    // (mqi_tps_env.hpp:1605-1736): a one-voxel slab (grid3d with 2 edges per axis, fill_data) and a grid
+    // voxelised at 1 mm holding 1e-8 (open) or 100 (closed)
+    void
+    insert_beamline() {
+        std::vector<mqi::node_t<R>*> nodes;
+        mqi::mat3x3<R> rot(opt.frame[0], opt.frame[1], opt.frame[2], opt.frame[3], opt.frame[4], opt.frame[5],
+                           opt.frame[6], opt.frame[7], opt.frame[8]);
+        if (opt.has_rs) {
+            auto* geo = new mqi::grid3d<mqi::density_t, R>(-opt.rs[2], opt.rs[2], 2, -opt.rs[2], opt.rs[2], 2,
+                                                           opt.rs[0], opt.rs[1], 2, rot);
+            geo->fill_data(opt.rs[3] * 1e-3);
+            nodes.push_back(bare_node(geo));
+        }
+        if (opt.has_ap) {
+            const int nxy = (int) std::ceil(2 * opt.ap[2]), nz = (int) std::ceil(opt.ap[1] - opt.ap[0]);
+            R* xe = new R[nxy + 1];
+            R* ze = new R[nz + 1];
+            for (int i = 0; i <= nxy; ++i) xe[i] = -opt.ap[2] + i * 1.0f;
+            for (int i = 0; i <= nz; ++i) ze[i] = opt.ap[0] + i * 1.0f;
+            auto* geo = new mqi::grid3d<mqi::density_t, R>(xe, nxy + 1, xe, nxy + 1, ze, nz + 1, rot);
+            mqi::density_t* data = new mqi::density_t[(size_t) nxy * nxy * nz];
+            for (int k = 0; k < nz; ++k)
+                for (int j = 0; j < nxy; ++j)
+                    for (int i = 0; i < nxy; ++i) {
+                        const float x = xe[i] + 0.5f, y = xe[j] + 0.5f;
+                        const bool  open = std::fabs(x) < opt.ap[3] && std::fabs(y) < opt.ap[4];
+                        data[((size_t) k * nxy + j) * nxy + i] = open ? 1e-8 : 100.0;
+                    }
+            geo->set_data(data);
+            nodes.push_back(bare_node(geo));
+        }
+        if (nodes.empty()) return;
+        mqi::node_t<R>* ph = this->world->children[0];
+        this->world->n_children = nodes.size() + 1;
+        this->world->children   = new mqi::node_t<R>*[this->world->n_children];
+        for (size_t i = 0; i < nodes.size(); ++i) this->world->children[i] = nodes[i];
+        this->world->children[nodes.size()] = ph;
     }
 
     virtual void
@@ -53,6 +119,19 @@ public:
         mqi::phantom_env<float>::setup_world();   // geometry + density + the default scorer
         mqi::node_t<R>* ph   = this->world->children[0];
         const uint32_t  nvox = nxyz.x * nxyz.y * nxyz.z;
+        insert_beamline();
+        if (!opt.roi_mask.empty()) {
+            // mask_reader::set_mask + mask_to_roi (mqi_file_handler.hpp:160-217) on a summed mask volume
+            std::vector<uint8_t>* m = new std::vector<uint8_t>(nvox);
+            std::ifstream f(opt.roi_mask, std::ios::binary);
+            f.read((char*) m->data(), nvox);
+            mqi::vec3<mqi::ijk_t> dim(nxyz.x, nxyz.y, nxyz.z);
+            mqi::mask_reader      mr(dim);
+            mr.set_mask(m->data());
+            roi_override = mr.mask_to_roi();
+            printf("roi runs %u size %d\n", roi_override->length_, roi_override->get_mask_size());
+            ph->scorers[0]->roi_ = roi_override;
+        }
         if (opt.scorers == "dose") return;
         delete[] ph->scorers[0]->data_;
         ph->scorers[0]->data_ = nullptr;
@@ -145,7 +224,7 @@ public:
 
     void
     save_dij_triplets() {
-        mqi::scorer<R>*        s = this->world->children[0]->scorers[0];
+        mqi::scorer<R>*        s = this->world->children[this->world->n_children - 1]->scorers[0];
         std::vector<uint32_t> k1, k2;
         std::vector<double>   val;
         for (uint32_t i = 0; i < s->max_capacity_; ++i) {
@@ -179,6 +258,20 @@ main(int argc, char* argv[]) {
             o.nspots = std::stoi(argv[++i]);
         } else if (a == "--spot_pitch" && i + 1 < argc) {
             o.spot_pitch = std::stof(argv[++i]);
+        } else if (a == "--rangeshifter" && i + 4 < argc) {
+            o.has_rs = true;
+            for (int k = 0; k < 4; ++k)
+                o.rs[k] = std::stof(argv[++i]);
+        } else if (a == "--aperture" && i + 5 < argc) {
+            o.has_ap = true;
+            for (int k = 0; k < 5; ++k)
+                o.ap[k] = std::stof(argv[++i]);
+        } else if (a == "--frame" && i + 12 < argc) {
+            o.has_frame = true;
+            for (int k = 0; k < 12; ++k)
+                o.frame[k] = std::stof(argv[++i]);
+        } else if (a == "--roi_mask" && i + 1 < argc) {
+            o.roi_mask = argv[++i];
         } else if (a == "--gauss" && i + 5 < argc) {
             o.gauss = true;
             for (int k = 0; k < 5; ++k)

@@ -44,6 +44,7 @@ def reduce_dose(d, nxyz, rebin):
         "idd": d.sum(axis=(1, 2)),
         "xz": d.sum(axis=1),
         "yz": d.sum(axis=2),
+        "xy": d.sum(axis=0),
         "reb": d.reshape(nz, ny // rebin, rebin, nx // rebin, rebin).sum(axis=(2, 4)),
         "total": np.array(d.sum()),
     }
@@ -66,7 +67,7 @@ def run(args):
             os.makedirs(od)
             cmd = [exe, "--lxyz", str(lx), str(ly), str(lz), "--pxyz", "0.0", "0.0", str(-0.5 * lz),
                    "--nxyz", str(nx), str(ny), str(nz),
-                   "--spot_energy", str(args.energy), "0.0", "--spot_position", "0", "0", "0.5",
+                   "--spot_energy", str(args.energy), "0.0", "--spot_position", "0", "0", str(getattr(args, "spot_z", 0.5)),
                    "--spot_size", str(args.spot_size), str(args.spot_size),
                    "--histories", str(args.histories_per_proc), "--phantom_path", ph,
                    "--output_prefix", od, "--random_seed", str(args.seed + 7919 * p), "--gpu_id", "0"]
@@ -74,16 +75,19 @@ def run(args):
                 cmd += ["--scorers", args.scorers]
                 if args.gauss:
                     cmd += ["--gauss"] + [str(g) for g in args.gauss]
+                cmd += [str(x) for x in (getattr(args, "extra", None) or [])]
             procs.append((subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT), od))
         for pr, _ in procs:
             rc = pr.wait()
             if rc != 0:
                 raise RuntimeError("reference process failed rc=%d" % rc)
         wall = time.time() - t0
-        names = sorted(f for f in os.listdir(procs[0][1]) if f.startswith("0_") and f.endswith(".raw"))
+        import re
+        # <child index>_<scorer>.raw: the phantom is child 0, or the last child behind beamline nodes
+        names = sorted(f for f in os.listdir(procs[0][1]) if re.match(r"^\d+_.*\.raw$", f))
         result = {}
         for name in names:
-            key = name[2:-4]
+            key = name.split("_", 1)[1][:-4]
             batches = []
             for _, od in procs:
                 d = np.fromfile(os.path.join(od, name), dtype=np.float64)
@@ -130,6 +134,8 @@ def main():
     ap.add_argument("--harness", action="store_true")
     ap.add_argument("--scorers", default="dose")
     ap.add_argument("--gauss", type=float, nargs=5, default=None)
+    ap.add_argument("--spot-z", type=float, default=0.5)
+    ap.add_argument("--extra", nargs=argparse.REMAINDER, default=None, help="further ref_harness flags")
     ap.add_argument("--out", default=None)
     run(ap.parse_args())
 
