@@ -701,11 +701,14 @@ transport_kernel(const __grid_constant__ Params P) {
 
     // lane state
     float    px = 0, py = 0, pz = 0, dx = 0, dy = 0, dz = 0, ke = 0;
-    bool     recoil = false;   // see TrackIO::recoil (always false in the release variant)
+    // lane flags in ONE register (separate bools end up as predicates, which every out-of-line call
+    // saves and restores through local memory): FL_RECOIL see TrackIO::recoil (debug variant only),
+    // FL_ADVANCE the track left `node` alive and a next child exists (MULTI), FL_DONE this lane found the
+    // queue empty and the history counter exhausted
+    constexpr unsigned FL_ALIVE = 1u, FL_DONE = 2u, FL_RECOIL = 4u, FL_ADVANCE = 8u;
+    unsigned fl = 0u;
     int      ix = 0, iy = 0, iz = 0;
-    bool     alive = false;
     int      node = 0;          // child of the world the lane's track is in (MULTI)
-    bool     advance = false;   // the track left `node` alive and a next child exists (MULTI)
     uint32_t spot_ind = kEmptyKey32;
     uint32_t h0 = 0, h1 = 0, blk = 0;   // Philox counter of the current history
     const uint32_t k0 = (uint32_t) P.seed, k1 = (uint32_t) (P.seed >> 32);
@@ -720,21 +723,21 @@ transport_kernel(const __grid_constant__ Params P) {
     // whole step body ran twice per restart (once for the restarted lane alone: 13 % of all issue slots in
     // ncu).  The full-warp votes below are the join: every lane executes them once per turn, and the
     // warp leaves the loop together once all of its lanes found the source exhausted.
-    bool done = false;   // this lane found the queue empty and the history counter exhausted
     while (true) {
         // ------------------------------------------------------------------ restart the lane
         bool need = false;   // the lane needs a new primary
-        if (!alive && !done) {
-            if ((MULTI && advance) || sp > 0) {
+        if (!(fl & (FL_ALIVE | FL_DONE))) {
+            if ((MULTI && (fl & FL_ADVANCE)) || sp > 0) {
                 TrackIO T;
                 T.px = px; T.py = py; T.pz = pz; T.dx = dx; T.dy = dy; T.dz = dz; T.ke = ke;
                 T.recoil = 0; T.node = node; T.sp = sp;
-                alive = restart_lane<MULTI>(P, stack, T, MULTI && advance ? 1 : 0);
-                sp      = T.sp;
-                advance = false;
-                if (alive) {
+                const bool ok = restart_lane<MULTI>(P, stack, T, MULTI && (fl & FL_ADVANCE) ? 1 : 0);
+                sp = T.sp;
+                fl = 0u;
+                if (ok) {
+                    fl = FL_ALIVE | ((VARIANT == MQI_K_DEBUG && T.recoil != 0) ? FL_RECOIL : 0u);
                     px = T.px; py = T.py; pz = T.pz; dx = T.dx; dy = T.dy; dz = T.dz;
-                    ke = T.ke; recoil = VARIANT == MQI_K_DEBUG && T.recoil != 0;
+                    ke = T.ke;
                     ix = T.ix; iy = T.iy; iz = T.iz;
                     if (MULTI) node = T.node;
                 }   // else: the track never enters the geometry, try again next turn
@@ -763,17 +766,16 @@ transport_kernel(const __grid_constant__ Params P) {
                     spot_ind = qe[Q_SPOT * kQueueCap];
                     if (MULTI) node = (int) qe[Q_NODE * kQueueCap];
                     blk    = P.src.vertices ? 0u : 2u;   // blocks 0-1 belong to the source sampling
-                    recoil = false;
-                    alive  = true;
+                    fl = FL_ALIVE;
                 } else if (src_empty) {
-                    done = true;
+                    fl = FL_DONE;
                 }
             }
             __syncwarp();   // the queue slots just read may be overwritten by the next refill
             q_state = max(q_n - n_need, 0) | (q_state & 0x10000);
         }
-        if (__all_sync(0xffffffffu, done)) break;
-        if (!alive) continue;   // taken after the join: the lane idles this turn, the others are converged
+        if (__all_sync(0xffffffffu, fl & FL_DONE)) break;
+        if (!(fl & FL_ALIVE)) continue;   // taken after the join: the lane idles this turn, the others are converged
 
         // ------------------------------------------------------------------ one voxel step
         ++n_steps;
@@ -839,12 +841,13 @@ transport_kernel(const __grid_constant__ Params P) {
         // intersect() failed (the reference poisons the track and breaks), or a closed aperture voxel
         // (rho > 99.9: mqi_fippel_physics.hpp:81-85): the track ends without scoring
         if (!(d2b > 0.f) || rho > 99.9f) {
-            alive = false;
+            fl = 0u;
             continue;   // rare; the lane rejoins at the ballot of the next turn
         }
 
         bool  stopped = false;
         float p1x, p1y, p1z;              // vtx1.pos
+        const bool recoil = VARIANT == MQI_K_DEBUG && (fl & FL_RECOIL);
         float ke1 = recoil ? 0.f : ke;    // vtx1.ke
 
         if (rho < 1.0e-7f) {
@@ -998,7 +1001,7 @@ transport_kernel(const __grid_constant__ Params P) {
 
         // ------------------------------------------------------------------ advance, :227-232
         if (stopped) {
-            alive = false;
+            fl = 0u;
         } else {
             ix = index_update_axis(ex0, ex1, p1x, d1x, ix);
             iy = index_update_axis(ey0, ey1, p1y, d1y, iy);
@@ -1006,11 +1009,9 @@ transport_kernel(const __grid_constant__ Params P) {
             px = p1x; py = p1y; pz = p1z;
             dx = d1x; dy = d1y; dz = d1z;
             ke = ke1;
-            recoil = false;
-            if ((unsigned) ix >= (unsigned) nx || (unsigned) iy >= (unsigned) ny || (unsigned) iz >= (unsigned) nz) {
-                alive = false;
-                if (MULTI) advance = node + 1 < P.n_nodes;   // the c_ind loop hands the track to the next child
-            }
+            fl = FL_ALIVE;
+            if ((unsigned) ix >= (unsigned) nx || (unsigned) iy >= (unsigned) ny || (unsigned) iz >= (unsigned) nz)
+                fl = (MULTI && node + 1 < P.n_nodes) ? FL_ADVANCE : 0u;   // the c_ind loop hands the track to the next child
         }
     }
 
