@@ -20,10 +20,16 @@
 // What is NOT here (stated in DESIGN.md): DICOM.  The reference reads the spot list, the beam angles
 // and the isocentre from an RTPLAN through GDCM, which is neither vendored by the reference nor
 // installed; this front end reads the same quantities from a small text plan (key `PlanFile`).
-// RTSTRUCT-based options (ReadStructure, StatROIStructFromRT) and mask files are rejected loudly.
+// RTSTRUCT-based options (ReadStructure, StatROIStructFromRT) are rejected loudly; mask files
+// (ScoringMask + Mask, StatROIMaskFilename) are supported: mask_reader (base/mqi_file_handler.hpp:13-217).
+// Beamline children (range shifter, aperture block) are described in the text plan by the quantities
+// characterize_rangeshifter / characterize_aperture (base/mqi_treatment_machine_pbs.hpp:279-331, 375-397)
+// take from the RTPLAN, and built like create_rangeshifter / create_voxelized_aperture
+// (base/environments/mqi_tps_env.hpp:1605-1736).
 #pragma once
 
 #include "mqi_host.hpp"
+#include "mqi_roi.hpp"
 
 #include <algorithm>
 #include <cstring>
@@ -158,6 +164,54 @@ read_mha_ct(const std::string& path) {
     ct.hu.resize(n);
     for (size_t i = 0; i < n; ++i) ct.hu[i] = (int16_t) tmp[i];
     return ct;
+}
+
+// mask_reader::read_mha_file (base/mqi_file_handler.hpp:38-99): uint8 voxels after the ElementDataFile =
+// LOCAL line; only DimSize is looked at (it must match the CT here; the reference does not check)
+inline std::vector<uint8_t>
+read_mha_mask(const std::string& path, int nx, int ny, int nz) {
+    std::ifstream fid(path, std::ios::binary);
+    if (!fid) throw std::runtime_error("cannot open mask file " + path);
+    std::string line;
+    int         mx = 0, my = 0, mz = 0;
+    bool        local = false;
+    while (std::getline(fid, line)) {
+        line = trim_copy(line);
+        const size_t pos = line.find('=');
+        if (pos == std::string::npos) continue;
+        const std::string key = trim_copy(line.substr(0, pos)), value = trim_copy(line.substr(pos + 1));
+        if (strcasecmp(key.c_str(), "DimSize") == 0) {
+            std::stringstream ss(value);
+            ss >> mx >> my >> mz;
+        } else if (strcasecmp(key.c_str(), "ElementDataFile") == 0) {
+            if (strcasecmp(value.c_str(), "LOCAL") != 0) throw std::runtime_error("Mask files does not contain data.");
+            local = true;
+            break;
+        }
+    }
+    if (!local) throw std::runtime_error("bad .mha header in " + path);
+    if (mx != nx || my != ny || mz != nz) throw std::runtime_error("mask " + path + " does not have the CT's dimensions");
+    std::vector<uint8_t> m((size_t) nx * ny * nz);
+    fid.read(reinterpret_cast<char*>(m.data()), m.size());
+    if ((size_t) fid.gcount() != m.size()) throw std::runtime_error("mask file is truncated: " + path);
+    return m;
+}
+
+// mask_reader::read_mask_files (:101-113): the 0/1 masks of all files are ADDED (overlaps give 2, which
+// mask_to_roi treats as neither opening nor closing a run, see mqi_roi.hpp)
+inline std::vector<uint8_t>
+read_mask_files(const std::vector<std::string>& files, int nx, int ny, int nz) {
+    if (files.empty()) throw std::runtime_error("Mask filelist are required for masking scorers.");
+    std::vector<uint8_t> total((size_t) nx * ny * nz, 0);
+    for (const auto& f : files) {
+        printf("Reading maskfile %s\n", f.c_str());
+        const std::vector<uint8_t> m = read_mha_mask(f, nx, ny, nz);
+        for (size_t i = 0; i < total.size(); ++i) {
+            if (m[i] > 1) throw std::runtime_error("mask values must be 0 or 1: " + f);
+            total[i] = (uint8_t) (total[i] + m[i]);
+        }
+    }
+    return total;
 }
 
 // CT edges as read_dcm_dir builds them: first edge = voxel centre - half a voxel (+ robust shift),
@@ -336,6 +390,9 @@ public:
 //   [plan]   name <text> | fractions <n>
 //   [beam]   name <text> | gantry_angle <deg> | couch_angle <deg> | collimator_angle <deg> |
 //            isocenter <x> <y> <z> | snout_position <mm>
+//            optional beamline: rangeshifter_id <ID> [<ID> ...]  |  rangeshifter_wet <WET mm> <IsocenterToRangeShifterDistance mm>
+//            | block_thickness <mm> | block_tray_distance <mm>
+//   [block]  rows "x(mm) y(mm)": polygon of one aperture opening of the beam above (one section per block)
 //   [spots]  rows "E(MeV nominal) x(mm) y(mm) meterset" of the beam above
 // '#' starts a comment.  The quantities are the ones create_coordinate_transform, beam_module_ion and
 // setup_beamsource take from the RTPLAN (BeamLimitingDeviceAngle, GantryAngle, PatientSupportAngle,
@@ -346,6 +403,12 @@ struct plan_beam {
     float                  gantry = 0, couch = 0, collimator = 0, snout = 0;
     float                  iso[3] = { 0, 0, 0 };
     std::vector<plan_spot> spots;
+    // beamline (RTPLAN: RangeShifterSequence / RangeShifterSettingsSequence / IonBlockSequence)
+    std::vector<std::string> rangeshifter_ids;                          // RangeShifterID of every range shifter
+    float                    rangeshifter_wet = 0, rangeshifter_distance = 0;   // RangeShifterWaterEquivalentThickness, IsocenterToRangeShifterDistance
+    bool                     has_rangeshifter = false;
+    float                    block_thickness = 0, block_tray_distance = 0;      // BlockThickness, IsocenterToBlockTrayDistance
+    std::vector<std::vector<std::array<float, 2>>> block_data;          // BlockData of every block: (x, y) polygon points
 };
 
 struct text_plan {
@@ -366,7 +429,8 @@ struct text_plan {
                 section = line.substr(1, line.size() - 2);
                 std::transform(section.begin(), section.end(), section.begin(), ::tolower);
                 if (section == "beam") p.beams.emplace_back();
-                else if (section == "spots" && p.beams.empty()) throw std::runtime_error("[spots] before [beam] in " + path);
+                else if ((section == "spots" || section == "block") && p.beams.empty()) throw std::runtime_error("[" + section + "] before [beam] in " + path);
+                else if (section == "block") p.beams.back().block_data.emplace_back();
                 else if (section != "plan" && section != "spots") throw std::runtime_error("unknown plan section [" + section + "]");
                 continue;
             }
@@ -386,7 +450,21 @@ struct text_plan {
                 else if (k == "collimator_angle") ss >> b.collimator;
                 else if (k == "isocenter") ss >> b.iso[0] >> b.iso[1] >> b.iso[2];
                 else if (k == "snout_position") ss >> b.snout;
+                else if (k == "rangeshifter_id") {
+                    std::string id;
+                    while (ss >> id) b.rangeshifter_ids.push_back(id);
+                    b.has_rangeshifter = true;
+                } else if (k == "rangeshifter_wet") {
+                    ss >> b.rangeshifter_wet >> b.rangeshifter_distance;
+                    b.has_rangeshifter = true;
+                } else if (k == "block_thickness") ss >> b.block_thickness;
+                else if (k == "block_tray_distance") ss >> b.block_tray_distance;
                 else throw std::runtime_error("unknown beam key " + k + " in " + path);
+            } else if (section == "block") {
+                std::array<float, 2> xy { 0.f, 0.f };
+                ss >> xy[0] >> xy[1];
+                if (ss.fail()) throw std::runtime_error("bad block row in " + path + ": " + line);
+                p.beams.back().block_data.back().push_back(xy);
             } else if (section == "spots") {
                 plan_spot s;
                 ss >> s.e >> s.x >> s.y >> s.meterset;
@@ -541,6 +619,9 @@ public:
     bool             record_statistics = false, save_statistics = false;
     float            stat_criteria = -1.f, stat_threshold = 0.f;
     std::vector<int> beam_numbers;   // 1-based, like the reference's bnb
+    bool             scoring_mask = false, save_scorer_map = false;
+    std::vector<std::string> mask_filenames, stat_roi_mask_filenames;
+    std::string      scorer_map_prefix;
     bool             reference_quirks = false;   // extension: reproduce B2 (double scoring with >= 3 scorers)
     int              max_stat_passes = 1000;     // extension: bound on the stopping loop
 
@@ -558,6 +639,8 @@ public:
     std::vector<uint64_t>    spot_histories;
     uint64_t                 total_histories = 0, tracked = 0;
     uint32_t                 num_spots = 0;
+    int                      n_beamline = 0;          // children of the world in front of the patient grid
+    uint64_t                 scoring_roi_size = 0, stat_roi_size = 0;
     int                      bnb = 0;
     float                    sid = 0.f;
     float                    last_stat_percent = 100.f;
@@ -621,9 +704,16 @@ public:
                 if (scorer_string.size() > 1) throw std::runtime_error("Dij cannot be scored with the other quantities");
             }
         }
-        if (parser.get_bool("ScoringMask", false) || parser.get_bool("ReadStructure", false) ||
-            parser.get_bool("StatROIStructFromRT", false) || !parser.get_string_vector("StatROIMaskFilename", ",").empty())
-            throw std::runtime_error("mask / RTSTRUCT regions of interest are not supported by this build (no GDCM)");
+        if (parser.get_bool("ReadStructure", false) || parser.get_bool("StatROIStructFromRT", false))
+            throw std::runtime_error("RTSTRUCT regions of interest are not supported by this build (no GDCM); use mask files");
+        scoring_mask = parser.get_bool("ScoringMask", false);   // :224-241
+        if (scoring_mask) {
+            save_scorer_map = parser.get_bool("SaveMap", true);
+            mask_filenames  = parser.get_string_vector("Mask", ",");
+            if (mask_filenames.empty()) throw std::runtime_error("Mask filename is missing");
+        }
+        if (save_scorer_map) scorer_map_prefix = parser.get_string("ScorerMapName", "scorer_map");
+        stat_roi_mask_filenames = parser.get_string_vector("StatROIMaskFilename", ",");   // :289
         density_scale = parser.get_float("DensityScaling", 1);
         shift[0]      = parser.get_float("XShift", 0);
         shift[1]      = parser.get_float("YShift", 0);
@@ -643,8 +733,11 @@ public:
             if (stat_criteria < 0) throw std::runtime_error("Statistical criteria must be positive float");
         }
         stat_threshold = parser.get_float("StatThreshold", 0.0);
-        if (record_statistics && stat_threshold <= 0)
-            throw std::runtime_error("If no contour or mask is selected, the statical threshold cannot be zero");
+        if (record_statistics && stat_threshold <= 0) {   // :299-315
+            if (stat_roi_mask_filenames.empty())
+                throw std::runtime_error("If no contour or mask is selected, the statical threshold cannot be zero");
+            printf("If statistical threshold is zero, the uncertainty might be biased\n");
+        }
         reference_quirks = parser.get_bool("ReferenceQuirks", false);
         max_stat_passes  = parser.get_int("MaxStatPasses", 1000);
         std::cout << parent_dir << std::endl;
@@ -713,6 +806,111 @@ public:
         }
     }
 
+    // One beamline child of the world in the beam frame (create_beamline tmi:238-276 + the builders
+    // create_rangeshifter / create_voxelized_aperture of the environment)
+    struct beamline_node {
+        std::vector<float> xe, ye, ze, rho;
+        float              pos_z = 0;
+    };
+
+    // characterize_rangeshifter (pbs:279-331) + create_rangeshifter (:1605-1649): a slab of one voxel,
+    // grid3d(pos - vol/2, pos + vol/2, 2 edges per axis), density RangeshifterDensity * 1e-3 g/mm^3
+    beamline_node
+    make_rangeshifter(const plan_beam& b) const {
+        float lx = machine->rangeshifter[0], ly = machine->rangeshifter[1], lz = 0.f, pz = 0.f;
+        if (machine->rangeshifter_thickness.empty()) {
+            std::cout << "Thickness is defined from RangeShifter Setting sequence\n";
+            lz = b.rangeshifter_wet / 1.15;
+            pz = b.rangeshifter_distance;
+            pz -= lz;
+        } else {
+            std::cout << "Thickness is defined from Rangeshifter ID\n";
+            pz = b.snout;
+            for (const auto& id : b.rangeshifter_ids) {
+                auto it = machine->rangeshifter_thickness.find(trim_copy(id));
+                if (it != machine->rangeshifter_thickness.end()) lz += it->second;
+            }
+            if (!(lz > 0)) throw std::runtime_error("range shifter thickness is zero (unknown RangeShifterID?)");
+            pz -= (lz * 0.5 + machine->rangeshifter_snout_gap);
+        }
+        if (!(lx > 0) || !(ly > 0) || !(lz > 0)) throw std::runtime_error("range shifter needs rangeshifter(mm) in the beam model and a positive thickness");
+        std::cout << "Range shifter thickness: " << lz << " (mm) and position: " << pz << " (mm)" << std::endl;
+        beamline_node n;
+        auto two = [](float lo, float hi) {   // grid3d(e_min, e_max, n_e = 2): e_min + i * (e_max - e_min) / 1
+            const float d = (hi - lo) / 1;
+            return std::vector<float> { lo + 0 * d, lo + 1 * d };
+        };
+        n.xe = two(0.f - lx / 2, 0.f + lx / 2);
+        n.ye = two(0.f - ly / 2, 0.f + ly / 2);
+        n.ze = two(pz - lz / 2, pz + lz / 2);
+        printf("Rangeshifter density %.4f\n", rangeshifter_density * 1e-3);
+        n.rho.assign(1, (float) (rangeshifter_density * 1e-3));
+        n.pos_z = pz;
+        return n;
+    }
+
+    // is_inside / sol1_1 (:1738-1768): even-odd test of the voxel centre against the block polygon.  The
+    // reference overwrites `inside` per opening, so with several blocks only the LAST one counts (kept).
+    static bool
+    inside_block(float x, float y, const std::vector<std::vector<std::array<float, 2>>>& blocks) {
+        bool inside = false;
+        for (const auto& seg : blocks) {
+            int          c = 0;
+            const size_t n = seg.size();
+            for (size_t i = 0, j = n - 1; i < n; j = i++) {
+                const float x0 = seg[i][0], y0 = seg[i][1], x1 = seg[j][0], y1 = seg[j][1];
+                if ((((y0 <= y) && (y < y1)) || ((y1 <= y) && (y < y0))) && (x < (x1 - x0) * (y - y0) / (y1 - y0) + x0)) c = !c;
+            }
+            inside = c != 0;
+        }
+        return inside;
+    }
+
+    // characterize_aperture (pbs:375-397) + create_voxelized_aperture (:1651-1736): 1 mm voxels, 1e-8 g/mm^3
+    // where the voxel centre lies inside the opening, 100 elsewhere
+    beamline_node
+    make_aperture(const plan_beam& b) const {
+        const float lx = machine->aperture[0], ly = machine->aperture[1], lz = b.block_thickness;
+        const float pz = b.block_tray_distance + lz * 0.5f;
+        if (!(lx > 0) || !(ly > 0) || !(lz > 0)) throw std::runtime_error("aperture needs aperture(mm) in the beam model and block_thickness in the plan");
+        std::cout << "BlockThickness and Position (center) : " << lz << ", " << pz << " mm" << std::endl;
+        const size_t nx = (size_t) std::ceil(lx / 1.0f), ny = (size_t) std::ceil(ly / 1.0f), nz = (size_t) std::ceil(lz / 1.0f);
+        beamline_node n;
+        n.xe.resize(nx + 1); n.ye.resize(ny + 1); n.ze.resize(nz + 1);
+        for (size_t i = 0; i <= nx; ++i) n.xe[i] = (0.f - lx / 2) + i * 1.0f;
+        for (size_t i = 0; i <= ny; ++i) n.ye[i] = (0.f - ly / 2) + i * 1.0f;
+        for (size_t i = 0; i <= nz; ++i) n.ze[i] = (pz - lz / 2) + i * 1.0f;
+        n.rho.resize(nx * ny * nz);
+        for (size_t i = 0; i < nx; ++i) {
+            const float x = n.xe[i] + 1.0f * 0.5;
+            for (size_t j = 0; j < ny; ++j) {
+                const float y    = n.ye[j] + 1.0f * 0.5;
+                const float rho  = inside_block(x, y, b.block_data) ? 1e-8f : 100.0f;
+                for (size_t k = 0; k < nz; ++k) n.rho[k * nx * ny + j * nx + i] = rho;
+            }
+        }
+        n.pos_z = pz;
+        return n;
+    }
+
+    // create_beamline (tmi:238-276): range shifter first, then the block, sorted by z descending (upstream first)
+    std::vector<beamline_node>
+    build_beamline(const plan_beam& b) const {
+        std::vector<beamline_node> v;
+        std::cout << "number of range shifter: " << (b.has_rangeshifter ? 1 : 0) << std::endl;
+        if (b.has_rangeshifter) {
+            v.push_back(make_rangeshifter(b));
+            printf("RANGE SHIFTER added\n");
+        }
+        std::cout << "number of blocks: " << b.block_data.size() << std::endl;
+        if (!b.block_data.empty()) {
+            v.push_back(make_aperture(b));
+            printf("APERTURE added\n");
+        }
+        std::stable_sort(v.begin(), v.end(), [](const beamline_node& a, const beamline_node& c) { return a.pos_z > c.pos_z; });
+        return v;
+    }
+
     // initialize(): setup_world + setup_materials + setup_beamsource + upload, per device
     void
     initialize() {
@@ -735,6 +933,18 @@ public:
         scorers.clear();
         stat_sum = stat_sumsq = -1;
         const uint64_t nvox = (uint64_t) ct.nx * ct.ny * ct.nz;
+        // beamline children in the beam's frame: rotation / translation of the coordinate transform with
+        // iec2dicom = 90 (setup_world :736-737, create_rangeshifter :1611-1618)
+        const std::vector<beamline_node> beamline = build_beamline(b);
+        const mat3                       R        = beam_rotation(b);
+        n_beamline = (int) beamline.size();
+        // regions of interest (setup_world :771-815)
+        std::vector<uint8_t> scoring_mask_total, stat_mask_total;
+        if (scoring_mask) scoring_mask_total = read_mask_files(mask_filenames, ct.nx, ct.ny, ct.nz);
+        if (record_statistics) {
+            if (!stat_roi_mask_filenames.empty()) stat_mask_total = read_mask_files(stat_roi_mask_filenames, ct.nx, ct.ny, ct.nz);
+            else printf("Statistical ROI is set to entire patient.\n");
+        }
         for (size_t d = 0; d < gpu_ids.size(); ++d) {
             mqi_handle* h = nullptr;
             check(mqi_create(gpu_ids[d], &h), "mqi_create");
@@ -744,10 +954,21 @@ public:
             check(mqi_set_grid_hu(h, grid.xe.data(), (int) grid.xe.size(), grid.ye.data(), (int) grid.ye.size(),
                                   grid.ze.data(), (int) grid.ze.size(), ct.hu.data(), density_scale, nullptr, nullptr),
                   "mqi_set_grid_hu");
+            for (const auto& n : beamline)
+                check(mqi_add_beamline_node(h, n.xe.data(), (int) n.xe.size(), n.ye.data(), (int) n.ye.size(), n.ze.data(),
+                                            (int) n.ze.size(), n.rho.data(), R.m, b.iso),
+                      "mqi_add_beamline_node");
             auto add = [&](int kind, const std::string& name, uint64_t cap, bool save) {
                 const int id = mqi_add_scorer(h, kind, name.c_str(), cap);
                 check(id, "mqi_add_scorer");
                 if (d == 0) scorers.push_back({ id, kind, name, save });
+                const bool is_stat = name == "Dose_stat" || name == "DoseSquare_stat";
+                const std::vector<uint8_t>& m = is_stat ? stat_mask_total : scoring_mask_total;
+                if (!m.empty()) {
+                    uint64_t roi_n = 0;
+                    check(mqi_set_scorer_roi(h, id, m.data(), m.size(), &roi_n), "mqi_set_scorer_roi");
+                    (is_stat ? stat_roi_size : scoring_roi_size) = roi_n;
+                }
                 return id;
             };
             for (const auto& s : scorer_string) {
@@ -886,7 +1107,8 @@ public:
     }
 
     // save_reshaped_files / save_sparse_file: "<BeamName>_<child>_<scorer>.<ext>", values times
-    // ParticlesPerHistory * RBE * NumberOfFraction.  The patient is child 0 (no beamline nodes).
+    // ParticlesPerHistory * RBE * NumberOfFraction.  The patient is the last child of the world: child
+    // 0 without beamline nodes, else the number of beamline nodes (:1860-1866).
     void
     save() {
         const std::string beam_name = plan.beams[bnb - 1].name;
@@ -895,7 +1117,7 @@ public:
         std::vector<double> dense;
         for (const auto& s : scorers) {
             if (!s.save) continue;
-            const std::string filename = beam_name + "_0_" + s.name;
+            const std::string filename = beam_name + "_" + std::to_string(n_beamline) + "_" + s.name;
             if (s.kind == MQI_SCORER_DIJ || sparse_output) {
                 if (s.kind != MQI_SCORER_DIJ) throw std::runtime_error("OutputFormat npz is for the Dij scorer");
                 std::vector<uint32_t> vox, spot;

@@ -8,7 +8,15 @@
 
 static void
 dump_json(mqib::tps_env& env) {
-    printf("{\"seed\": %d, \"n_fractions\": %d, \"sim_type\": %d, \"beams\": [", env.master_seed, env.n_fractions, (int) env.sim_type);
+    // the builders narrate on stdout like the reference: run them before the one-line JSON starts
+    std::vector<std::vector<mqib::tps_env::beamline_node>> all_nodes;
+    for (size_t q = 0; q < env.beam_numbers.size(); ++q) all_nodes.push_back(env.build_beamline(env.plan.beams[env.beam_numbers[q] - 1]));
+    unsigned long long roi_scoring = 0, roi_stat = 0;
+    const uint64_t     nvox = (uint64_t) env.ct.nx * env.ct.ny * env.ct.nz;
+    if (env.scoring_mask) roi_scoring = mqib::mask_to_roi(mqib::read_mask_files(env.mask_filenames, env.ct.nx, env.ct.ny, env.ct.nz).data(), nvox).size();
+    if (env.record_statistics && !env.stat_roi_mask_filenames.empty())
+        roi_stat = mqib::mask_to_roi(mqib::read_mask_files(env.stat_roi_mask_filenames, env.ct.nx, env.ct.ny, env.ct.nz).data(), nvox).size();
+    printf("DRYRUN {\"seed\": %d, \"n_fractions\": %d, \"sim_type\": %d, \"beams\": [", env.master_seed, env.n_fractions, (int) env.sim_type);
     for (size_t q = 0; q < env.beam_numbers.size(); ++q) {
         const mqib::plan_beam& b = env.plan.beams[env.beam_numbers[q] - 1];
         env.sid = b.snout + 50;
@@ -26,9 +34,27 @@ dump_json(mqib::tps_env& env) {
             for (int k = 0; k < 9; ++k) printf("%s%.9g", k ? ", " : "", bl[i].rot[k]);
             printf("], \"trans\": [%.9g, %.9g, %.9g]}", bl[i].trans[0], bl[i].trans[1], bl[i].trans[2]);
         }
+        printf("], \"beamline\": [");
+        const std::vector<mqib::tps_env::beamline_node>& nodes = all_nodes[q];
+        for (size_t i = 0; i < nodes.size(); ++i) {
+            const auto& n = nodes[i];
+            size_t n_open = 0;
+            for (float r : n.rho) n_open += r < 1e-7f;
+            double sx = 0, sy = 0;   // centroid of the open voxels of the first z layer (aperture orientation check)
+            const size_t nx = n.xe.size() - 1, ny = n.ye.size() - 1;
+            size_t       c0 = 0;
+            for (size_t j = 0; j < ny; ++j)
+                for (size_t k = 0; k < nx; ++k)
+                    if (n.rho[j * nx + k] < 1e-7f) { sx += n.xe[k] + 0.5; sy += n.ye[j] + 0.5; ++c0; }
+            printf("%s{\"pos_z\": %.9g, \"n\": [%zu, %zu, %zu], \"xe\": [%.9g, %.9g], \"ye\": [%.9g, %.9g], \"ze\": [%.9g, %.9g], "
+                   "\"rho0\": %.9g, \"open_voxels\": %zu, \"open_centroid\": [%.9g, %.9g]}",
+                   i ? ", " : "", n.pos_z, nx, ny, n.ze.size() - 1, n.xe.front(), n.xe.back(), n.ye.front(), n.ye.back(), n.ze.front(),
+                   n.ze.back(), n.rho[0], n_open, c0 ? sx / c0 : 0.0, c0 ? sy / c0 : 0.0);
+        }
         printf("]}");
     }
-    printf("], \"grid\": {\"n\": [%d, %d, %d], \"xe\": [%.9g, %.9g], \"ye\": [%.9g, %.9g], \"ze\": [%.9g, %.9g]}}\n", env.ct.nx, env.ct.ny,
+    printf("], \"scoring_roi_size\": %llu, \"stat_roi_size\": %llu", roi_scoring, roi_stat);
+    printf(", \"grid\": {\"n\": [%d, %d, %d], \"xe\": [%.9g, %.9g], \"ye\": [%.9g, %.9g], \"ze\": [%.9g, %.9g]}}\n", env.ct.nx, env.ct.ny,
            env.ct.nz, env.grid.xe.front(), env.grid.xe.back(), env.grid.ye.front(), env.grid.ye.back(), env.grid.ze.front(),
            env.grid.ze.back());
 }
@@ -51,7 +77,6 @@ main(int argc, char* argv[]) {
     try {
         mqib::tps_env myenv(input_file);
         if (dry_run) {
-            printf("DRYRUN ");
             dump_json(myenv);
             return 0;
         }

@@ -47,6 +47,20 @@ def write_mha(path, hu, origin, spacing):
         f.write(hu.astype(np.float32).tobytes())
 
 
+def write_mask_mha(path, mask, origin=(0.0, 0.0, 0.0), spacing=(1.0, 1.0, 1.0)):
+    """uint8 0/1 mask volume [nz, ny, nx] in the layout mask_reader::read_mha_file parses
+    (moqui/base/mqi_file_handler.hpp:38-99)."""
+    nz, ny, nx = mask.shape
+    hdr = ("ObjectType = Image\nNDims = 3\nBinaryData = True\nBinaryDataByteOrderMSB = False\nCompressedData = False\n"
+           "TransformMatrix = 1 0 0 0 1 0 0 0 1\nOffset = %.9g %.9g %.9g\nCenterOfRotation = 0 0 0\n"
+           "AnatomicalOrientation = RAI\nElementSpacing = %.9g %.9g %.9g\nDimSize = %d %d %d\n"
+           "ElementType = MET_UCHAR\nElementDataFile = LOCAL\n"
+           % (origin[0], origin[1], origin[2], spacing[0], spacing[1], spacing[2], nx, ny, nz))
+    with open(path, "wb") as f:
+        f.write(hdr.encode())
+        f.write(np.ascontiguousarray(mask, dtype=np.uint8).tobytes())
+
+
 def beam_model_rows(e_lo=60.0, e_hi=240.0, step=10.0):
     """[spot] rows: Enominal E dE x y xp yp ratio"""
     rows = []
@@ -92,7 +106,19 @@ def write_plan(path, beams, name="synthetic", fractions=30):
             f.write("[beam]\nname %s\ngantry_angle %g\ncouch_angle %g\ncollimator_angle %g\n" %
                     (b["name"], b.get("gantry", 0.0), b.get("couch", 0.0), b.get("collimator", 0.0)))
             iso = b.get("iso", (0.0, 0.0, 0.0))
-            f.write("isocenter %g %g %g\nsnout_position %g\n[spots]\n# E x y meterset\n" % (iso[0], iso[1], iso[2], b.get("snout", 250.0)))
+            f.write("isocenter %g %g %g\nsnout_position %g\n" % (iso[0], iso[1], iso[2], b.get("snout", 250.0)))
+            # optional beamline: range shifter by ID (thickness from the beam model) or by WET, aperture blocks
+            if b.get("rangeshifter_ids"):
+                f.write("rangeshifter_id %s\n" % " ".join(b["rangeshifter_ids"]))
+            if b.get("rangeshifter_wet"):
+                f.write("rangeshifter_wet %g %g\n" % tuple(b["rangeshifter_wet"]))
+            if b.get("blocks"):
+                f.write("block_thickness %g\nblock_tray_distance %g\n" % (b.get("block_thickness", 20.0), b.get("block_tray_distance", 60.0)))
+                for poly in b["blocks"]:
+                    f.write("[block]\n# x y\n")
+                    for (x, y) in poly:
+                        f.write("%.6g %.6g\n" % (x, y))
+            f.write("[spots]\n# E x y meterset\n")
             for s in b["spots"]:
                 f.write("%.6g %.6g %.6g %.8g\n" % s)
 
@@ -112,7 +138,8 @@ def write_input(path, parent_dir, out_dir, **kw):
             f.write("%s %s\n" % (k, v))
 
 
-def make_case(root, n=(64, 64, 40), spacing=(4.0, 4.0, 6.0), n_layers=4, pitch=10.0, half_width=20.0, beams=1, seed=1, **input_kw):
+def make_case(root, n=(64, 64, 40), spacing=(4.0, 4.0, 6.0), n_layers=4, pitch=10.0, half_width=20.0, beams=1, seed=1,
+              beam_extra=None, **input_kw):
     """Write ct.mha, machine.txt, plan.txt and moqui_tps.in under `root`; returns the input-file path."""
     os.makedirs(root, exist_ok=True)
     hu, origin = head_ct(n, spacing, seed)
@@ -122,6 +149,7 @@ def make_case(root, n=(64, 64, 40), spacing=(4.0, 4.0, 6.0), n_layers=4, pitch=1
     for i in range(beams):
         bl.append({"name": "G%03d" % (90 * i), "gantry": 90.0 * i, "couch": 0.0, "collimator": 0.0, "iso": (0.0, 0.0, 0.0),
                    "snout": 250.0, "spots": spot_list(n_layers=n_layers, pitch=pitch, half_width=half_width, seed=seed + i)})
+        bl[-1].update(beam_extra or {})
     write_plan(os.path.join(root, "plan.txt"), bl)
     out = input_kw.pop("OutputDir", os.path.join(root, "out"))
     inp = os.path.join(root, "moqui_tps.in")

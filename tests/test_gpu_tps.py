@@ -179,3 +179,88 @@ def test_two_devices_give_the_single_device_dose(root):
     d0 = np.fromfile(os.path.join(a, "G000_0_Dose.raw"), dtype=np.float64)
     d1 = np.fromfile(os.path.join(b, "G000_0_Dose.raw"), dtype=np.float64)
     np.testing.assert_allclose(d0, d1, rtol=1e-9, atol=d0.max() * 1e-12)
+
+
+def test_beamline_children_and_scoring_mask_through_the_front_end(tmp_path):
+    """Range shifter (by ID) + aperture block from the text plan, ScoringMask + StatROI masks from .mha files:
+    the front end must build the same world as the engine driven through ctypes with the geometry the dry
+    run reports (identical streams => identical dose), name the outputs after the patient's child index and
+    leave every voxel outside the mask at zero."""
+    root = str(tmp_path)
+    poly = [(-18, -12), (14, -12), (14, 16), (-18, 16)]
+    extra = {"rangeshifter_ids": ["RS1"], "blocks": [poly], "block_thickness": 20.0, "block_tray_distance": 140.0}
+    mask = np.zeros((N[2], N[1], N[0]), dtype=np.uint8)
+    mask[8:34, 6:50, 14:52] = 1
+    S.write_mask_mha(os.path.join(root, "mask.mha"), mask)
+    od = os.path.join(root, "o_bl")
+    inp = S.make_case(root, n=N, spacing=SP, n_layers=3, beam_extra=extra, ParticlesPerHistory=1500.0, OutputDir=od,
+                      ScoringMask="true", Mask=os.path.join(root, "mask.mha"), Scorer="Dose,EnergyDeposition")
+    src = run_tps(inp, dry=True)
+    out = run_tps(inp)
+    assert "RANGE SHIFTER added" in out and "APERTURE added" in out
+    nodes = src["beams"][0]["beamline"]
+    assert len(nodes) == 2 and src["scoring_roi_size"] == int(mask.sum())
+    d = np.fromfile(os.path.join(od, "G000_2_Dose.raw"), dtype=np.float64).reshape(N[2], N[1], N[0])   # patient = child 2
+    ed = np.fromfile(os.path.join(od, "G000_2_EnergyDeposition.raw"), dtype=np.float64).reshape(N[2], N[1], N[0])
+    assert d[mask == 0].sum() == 0.0 and ed[mask == 0].sum() == 0.0 and d[mask == 1].sum() > 0
+    # the same world through ctypes
+    hu, origin = S.head_ct(N, SP, 1)
+    g = src["grid"]
+    xe = (np.float32(g["xe"][0]) + np.arange(N[0] + 1, dtype=np.float32) * np.float32(SP[0])).astype(np.float32)
+    ye = (np.float32(g["ye"][0]) + np.arange(N[1] + 1, dtype=np.float32) * np.float32(SP[1])).astype(np.float32)
+    ze = np.empty(N[2] + 1, dtype=np.float32)
+    ze[0] = g["ze"][0]
+    for i in range(1, N[2] + 1):
+        ze[i] = ze[i - 1] + np.float32(SP[2])
+    beam = src["beams"][0]
+    rot, trans = beam["spots"][0]["rot"], beam["spots"][0]["trans"]
+    e = capi.Engine(0, physics=capi.PHYSICS_RELEASE)
+    e.set_grid_hu(xe, ye, ze, hu)
+    rs, ap = nodes
+    e.add_beamline_node(np.float32(rs["xe"]), np.float32(rs["ye"]), np.float32(rs["ze"]), np.float32([rs["rho0"]]), rot=rot, trans=trans)
+    axe = (np.float32(ap["xe"][0]) + np.arange(ap["n"][0] + 1, dtype=np.float32)).astype(np.float32)
+    aye = (np.float32(ap["ye"][0]) + np.arange(ap["n"][1] + 1, dtype=np.float32)).astype(np.float32)
+    aze = (np.float32(ap["ze"][0]) + np.arange(ap["n"][2] + 1, dtype=np.float32)).astype(np.float32)
+    xc, yc = axe[:-1] + np.float32(0.5), aye[:-1] + np.float32(0.5)
+    open_xy = (xc[None, :] >= -18) & (xc[None, :] < 14) & (yc[:, None] >= -12) & (yc[:, None] < 16)
+    assert int(open_xy.sum()) * ap["n"][2] == ap["open_voxels"]
+    arho = np.broadcast_to(np.where(open_xy, np.float32(1e-8), np.float32(100.0)), (ap["n"][2],) + open_xy.shape).astype(np.float32)
+    e.add_beamline_node(axe, aye, aze, arho.copy(), rot=rot, trans=trans)
+    s_d = e.add_scorer(capi.SCORER_DOSE, "Dose")
+    s_e = e.add_scorer(capi.SCORER_EDEP, "EnergyDeposition")
+    e.set_scorer_roi(s_d, mask)
+    e.set_scorer_roi(s_e, mask)
+    bl = [capi.make_beamlet(s["energy"], s["mean"], s["sigma"], uniform=False, sigma_energy=s["sigma_energy"],
+                            rot=s["rot"], trans=s["trans"]) for s in beam["spots"]]
+    for b in bl:
+        b.energy_normal = 1
+    hist = [s["histories"] for s in beam["spots"]]
+    e.set_beamlets(bl, hist)
+    e.run(12345, 0, sum(hist))
+    ref = e.get_dense(s_d) * (1500.0 * np.float32(1.1) * 30)
+    assert ref.sum() > 0
+    np.testing.assert_allclose(d, ref, rtol=1e-6, atol=ref.max() * 1e-12)
+    # the range shifter costs range, the aperture removes the spots outside the opening: less dose than the open beam
+    inp0 = S.make_case(os.path.join(root, "open"), n=N, spacing=SP, n_layers=3, ParticlesPerHistory=1500.0,
+                       OutputDir=os.path.join(root, "o_open"), Scorer="Dose")
+    run_tps(inp0)
+    d0 = np.fromfile(os.path.join(root, "o_open", "G000_0_Dose.raw"), dtype=np.float64)
+    assert 0.05 * d0.sum() < d.sum() < 0.9 * d0.sum()
+
+
+def test_stat_roi_mask_drives_the_stopping_criterion(tmp_path):
+    root = str(tmp_path)
+    mask = np.zeros((N[2], N[1], N[0]), dtype=np.uint8)
+    mask[12:28, 20:44, 20:44] = 1
+    S.write_mask_mha(os.path.join(root, "roi.mha"), mask)
+    od = os.path.join(root, "o_stat")
+    inp = S.make_case(root, n=N, spacing=SP, ParticlesPerHistory=3000.0, OutputDir=od, StoppingStatistics="true",
+                      SaveStoppingStatistics="true", StoppingCriteria="6.0", StatThreshold="0.5", MaxStatPasses=60,
+                      StatROIMaskFilename=os.path.join(root, "roi.mha"))
+    out = run_tps(inp)
+    m = re.findall(r"Run (\d+): current uncertainty ([0-9.eE+-]+) %", out)
+    assert m and float(m[-1][1]) <= 6.0
+    ds = np.fromfile(os.path.join(od, "G000_0_Dose_stat.raw"), dtype=np.float64).reshape(N[2], N[1], N[0])
+    dd = np.fromfile(os.path.join(od, "G000_0_Dose.raw"), dtype=np.float64).reshape(N[2], N[1], N[0])
+    assert ds[mask == 0].sum() == 0.0 and ds[mask == 1].sum() > 0      # the stat scorers see only their roi
+    assert dd[mask == 0].sum() > 0                                      # the Dose scorer keeps the DIRECT roi

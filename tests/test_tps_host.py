@@ -175,3 +175,68 @@ def test_npz_writer_is_a_scipy_csr(tmp_path):
     for v, s, x in zip([7, 2, 9, 2, 0, 5], [2, 0, 2, 1, 0, 2], [0.5, 1.5, 2.5, 3.5, 4.5, 5.5]):
         dense[s, v] += x
     np.testing.assert_array_equal(m.toarray(), dense)
+
+
+# ------------------------------------------------------------------------------------------------
+# beamline children and mask regions of interest, host side
+# ------------------------------------------------------------------------------------------------
+def test_beamline_geometry_follows_the_reference_rules(tmp_path):
+    """characterize_rangeshifter (pbs:279-331), characterize_aperture (:375-397), create_beamline sorting
+    (tmi:238-276), create_voxelized_aperture / is_inside (mqi_tps_env.hpp:1651-1768)."""
+    big = [(-30, -20), (30, -20), (30, 20), (-30, 20)]
+    small = [(-10, -5), (20, -5), (20, 15), (-10, 15)]
+    extra = {"rangeshifter_ids": ["RS1"], "blocks": [big, small], "block_thickness": 20.0, "block_tray_distance": 140.0}
+    inp = S.make_case(str(tmp_path), beam_extra=extra)
+    j = dry_run(inp)
+    rs, ap = j["beams"][0]["beamline"]          # sorted by z, upstream first
+    # model: rangeshifter(mm) 300 300, gap 10, "RS1" 40 mm; plan: snout 250
+    assert rs["n"] == [1, 1, 1] and rs["xe"] == [-150, 150] and rs["ye"] == [-150, 150]
+    assert rs["pos_z"] == 250 - (40 * 0.5 + 10) and rs["ze"] == [200, 240]
+    assert abs(rs["rho0"] - 1.19e-3) < 1e-9     # RangeshifterDensity default 1.19 g/cm^3
+    # aperture(mm) 300 300, thickness 20 at tray distance 140: centre 150, 1 mm voxels
+    assert ap["n"] == [300, 300, 20] and ap["pos_z"] == 150 and ap["ze"] == [140, 160]
+    assert ap["rho0"] == 100.0
+    # with several blocks only the LAST polygon counts (is_inside overwrites `inside`): 30 x 20 mm opening
+    assert ap["open_voxels"] == 30 * 20 * 20
+    assert ap["open_centroid"] == [5.0, 5.0]
+    # range shifter by water-equivalent thickness when the model lists no IDs is covered by the formula only:
+    # thickness = WET / 1.15, position = distance - thickness
+    model = os.path.join(str(tmp_path), "machine.txt")
+    txt = open(model).read().replace('"RS1" 40.0\n', "")
+    open(model, "w").write(txt)
+    extra2 = {"rangeshifter_wet": (46.0, 230.0)}
+    S.write_plan(os.path.join(str(tmp_path), "plan.txt"),
+                 [{"name": "G000", "spots": S.spot_list(n_layers=2, pitch=10.0, half_width=10.0), **extra2}])
+    j2 = dry_run(inp)
+    (rs2,) = j2["beams"][0]["beamline"]
+    lz = f32(46.0) / f32(1.15)
+    assert abs(rs2["ze"][1] - rs2["ze"][0] - float(lz)) < 1e-4 and abs(rs2["pos_z"] - float(f32(230.0) - lz)) < 1e-4
+
+
+def test_mask_keys_and_roi_sizes(tmp_path):
+    root = str(tmp_path)
+    n = (64, 64, 40)
+    m1 = np.zeros((n[2], n[1], n[0]), dtype=np.uint8)
+    m1[10:30, 20:40, 20:44] = 1
+    m2 = np.zeros_like(m1)
+    m2[12:14, 25:30, 20:30] = 1                 # overlaps m1 from the start of its rows
+    S.write_mask_mha(os.path.join(root, "m1.mha"), m1)
+    S.write_mask_mha(os.path.join(root, "m2.mha"), m2)
+    inp = S.make_case(root, n=n, ScoringMask="true", Mask="%s,%s" % (os.path.join(root, "m1.mha"), os.path.join(root, "m2.mha")),
+                      StoppingStatistics="true", StoppingCriteria="2.0", StatThreshold="0.0",
+                      StatROIMaskFilename=os.path.join(root, "m1.mha"))
+    j = dry_run(inp)
+    # rows where the sum starts at 2 open their run only where it drops to 1: 10 voxels per such row are lost
+    assert j["scoring_roi_size"] == 20 * 20 * 24 - 2 * 5 * 10
+    assert j["stat_roi_size"] == 20 * 20 * 24
+    # StatThreshold 0 without a stat roi is an error, ScoringMask without Mask too, RTSTRUCT options are refused
+    err = dry_run(S.make_case(root, n=n, StoppingStatistics="true", StoppingCriteria="2.0", StatThreshold="0.0"), expect_fail=True)
+    assert "threshold" in err
+    err = dry_run(S.make_case(root, n=n, ScoringMask="true"), expect_fail=True)
+    assert "Mask filename is missing" in err
+    err = dry_run(S.make_case(root, n=n, ReadStructure="true"), expect_fail=True)
+    assert "RTSTRUCT" in err
+    # a mask with other dimensions is refused
+    S.write_mask_mha(os.path.join(root, "bad.mha"), np.zeros((4, 4, 4), dtype=np.uint8))
+    err = dry_run(S.make_case(root, n=n, ScoringMask="true", Mask=os.path.join(root, "bad.mha")), expect_fail=True)
+    assert "dimensions" in err
