@@ -20,8 +20,10 @@
 // What is NOT here (stated in DESIGN.md): DICOM.  The reference reads the spot list, the beam angles
 // and the isocentre from an RTPLAN through GDCM, which is neither vendored by the reference nor
 // installed; this front end reads the same quantities from a small text plan (key `PlanFile`).
-// RTSTRUCT-based options (ReadStructure, StatROIStructFromRT) are rejected loudly; mask files
-// (ScoringMask + Mask, StatROIMaskFilename) are supported: mask_reader (base/mqi_file_handler.hpp:13-217).
+// Mask files (ScoringMask + Mask, StatROIMaskFilename) are supported: mask_reader
+// (base/mqi_file_handler.hpp:13-217).  The RTSTRUCT options (ReadStructure + BodyContourName,
+// StatROIStructFromRT + StatROI) read their contours from a text structure file (key `StructureFile`)
+// instead of the DICOM RTSTRUCT and rasterise them like fill_contour (mqi_tps_env.hpp:1769-1826).
 // Beamline children (range shifter, aperture block) are described in the text plan by the quantities
 // characterize_rangeshifter / characterize_aperture (base/mqi_treatment_machine_pbs.hpp:279-331, 375-397)
 // take from the RTPLAN, and built like create_rangeshifter / create_voxelized_aperture
@@ -212,6 +214,96 @@ read_mask_files(const std::vector<std::string>& files, int nx, int ny, int nz) {
         }
     }
     return total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Text structure set (stands in for the RTSTRUCT):  [roi] name <text>  then one [contour] section per
+// closed planar contour with rows "x y z" (mm, patient coordinates; ContourData of the RTSTRUCT).
+// ---------------------------------------------------------------------------------------------
+struct text_structures {
+    typedef std::vector<std::array<float, 3>> contour_t;
+    std::vector<std::pair<std::string, std::vector<contour_t>>> rois;
+
+    static text_structures
+    load(const std::string& path) {
+        std::ifstream f(path);
+        if (!f) throw std::runtime_error("RT STRCUTURE does not exist");   // the reference's message (:609)
+        text_structures t;
+        std::string     line, section;
+        while (std::getline(f, line)) {
+            line = trim_copy(line.substr(0, line.find_first_of('#')));
+            if (line.empty()) continue;
+            if (line.front() == '[' && line.back() == ']') {
+                section = line.substr(1, line.size() - 2);
+                std::transform(section.begin(), section.end(), section.begin(), ::tolower);
+                if (section == "roi") t.rois.emplace_back();
+                else if (section == "contour") {
+                    if (t.rois.empty()) throw std::runtime_error("[contour] before [roi] in " + path);
+                    t.rois.back().second.emplace_back();
+                } else throw std::runtime_error("unknown structure section [" + section + "]");
+                continue;
+            }
+            std::stringstream ss(line);
+            if (section == "roi") {
+                std::string k;
+                ss >> k;
+                if (k == "name") {
+                    std::string rest;
+                    std::getline(ss, rest);
+                    t.rois.back().first = trim_copy(rest);
+                }
+            } else if (section == "contour") {
+                std::array<float, 3> p { 0, 0, 0 };
+                ss >> p[0] >> p[1] >> p[2];
+                if (ss.fail()) throw std::runtime_error("bad contour row in " + path + ": " + line);
+                t.rois.back().second.back().push_back(p);
+            }
+        }
+        return t;
+    }
+
+    const std::vector<contour_t>*
+    find(const std::string& name) const {   // ROIName matched without regard to case (:563)
+        for (const auto& r : rois)
+            if (strcasecmp(r.first.c_str(), name.c_str()) == 0) return &r.second;
+        return nullptr;
+    }
+};
+
+// fill_contour + sol1_1 (mqi_tps_env.hpp:1769-1826) for every contour of a roi: the contour's slice is
+// the first i < nz - 1 with ze[i] < z < ze[i+1] (strict, and the last slab is never searched); inside it
+// the pixel CENTRES (edge + half a pixel) of columns / rows [0, n - 1) are tested with the even-odd
+// rule; hits are OR-ed (inner contours do not cut holes).  The volume starts from zeros here (the
+// reference leaves it uninitialised).
+inline std::vector<uint8_t>
+rasterize_contours(const std::vector<text_structures::contour_t>& contours, int nx, int ny, int nz, const float* xe,
+                   const float* ye, const float* ze, float dx, float dy) {
+    std::vector<uint8_t> vol((size_t) nx * ny * nz, 0);
+    for (const auto& c : contours) {
+        if (c.empty()) continue;
+        int z_ind = -1;
+        for (int i = 0; i < nz - 1; i++) {
+            if (c[0][2] > ze[i] && c[0][2] < ze[i + 1]) {
+                z_ind = i;
+                break;
+            }
+        }
+        if (z_ind < 0) continue;
+        const int n = (int) c.size();
+        for (int x_ind = 0; x_ind < nx - 1; x_ind++) {
+            for (int y_ind = 0; y_ind < ny - 1; y_ind++) {
+                const float px = xe[x_ind] + dx * 0.5;
+                const float py = ye[y_ind] + dy * 0.5;
+                int         in = 0;
+                for (int i = 0, j = n - 1; i < n; j = i++) {
+                    const float x0 = c[i][0], y0 = c[i][1], x1 = c[j][0], y1 = c[j][1];
+                    if ((((y0 <= py) && (py < y1)) || ((y1 <= py) && (py < y0))) && (px < (x1 - x0) * (py - y0) / (y1 - y0) + x0)) in = !in;
+                }
+                if (in) vol[(size_t) z_ind * nx * ny + (size_t) y_ind * nx + x_ind] = 1;
+            }
+        }
+    }
+    return vol;
 }
 
 // CT edges as read_dcm_dir builds them: first edge = voxel centre - half a voxel (+ robust shift),
@@ -622,6 +714,9 @@ public:
     bool             scoring_mask = false, save_scorer_map = false;
     std::vector<std::string> mask_filenames, stat_roi_mask_filenames;
     std::string      scorer_map_prefix;
+    bool             read_structure = false, set_stat_roi_from_rtstruct = false;
+    std::string      body_contour_name, stat_roi, structure_path;
+    text_structures  structures;
     bool             reference_quirks = false;   // extension: reproduce B2 (double scoring with >= 3 scorers)
     int              max_stat_passes = 1000;     // extension: bound on the stopping loop
 
@@ -704,8 +799,20 @@ public:
                 if (scorer_string.size() > 1) throw std::runtime_error("Dij cannot be scored with the other quantities");
             }
         }
-        if (parser.get_bool("ReadStructure", false) || parser.get_bool("StatROIStructFromRT", false))
-            throw std::runtime_error("RTSTRUCT regions of interest are not supported by this build (no GDCM); use mask files");
+        body_contour_name          = parser.get_string("BodyContourName", "External");   // :225-226
+        read_structure             = parser.get_bool("ReadStructure", false);
+        set_stat_roi_from_rtstruct = parser.get_bool("StatROIStructFromRT", false);      // :290-296
+        if (set_stat_roi_from_rtstruct) {
+            stat_roi = parser.get_string("StatROI", "");
+            if (stat_roi.empty()) throw std::runtime_error("Statistical ROI is not provided.");
+        }
+        if (read_structure || set_stat_roi_from_rtstruct) {
+            std::string sf = parser.get_string("StructureFile", "");
+            if (sf.empty())
+                throw std::runtime_error("StructureFile (text structure set) is required: reading an RTSTRUCT needs GDCM, which this build does not have");
+            if (!use_absolute_path && sf[0] != '/') sf = parent_dir + "/" + sf;
+            structure_path = sf;
+        }
         scoring_mask = parser.get_bool("ScoringMask", false);   // :224-241
         if (scoring_mask) {
             save_scorer_map = parser.get_bool("SaveMap", true);
@@ -734,7 +841,7 @@ public:
         }
         stat_threshold = parser.get_float("StatThreshold", 0.0);
         if (record_statistics && stat_threshold <= 0) {   // :299-315
-            if (stat_roi_mask_filenames.empty())
+            if (!set_stat_roi_from_rtstruct && stat_roi_mask_filenames.empty())
                 throw std::runtime_error("If no contour or mask is selected, the statical threshold cannot be zero");
             printf("If statistical threshold is zero, the uncertainty might be biased\n");
         }
@@ -748,6 +855,11 @@ public:
         printf("dcm.dim nx %d ny %d nz %d\n", ct.nx, ct.ny, ct.nz);
         plan = text_plan::load(plan_path);
         printf("%s\n", plan_path.c_str());
+        if (!structure_path.empty()) {
+            printf("Loading RTSTRUCT from %s\n", structure_path.c_str());
+            structures = text_structures::load(structure_path);
+            printf("roi seq size %lu\n", (unsigned long) structures.rois.size());
+        }
         {
             const size_t deli = machine_name.find(":");
             std::string  site = machine_name.substr(0, deli);
@@ -911,6 +1023,28 @@ public:
         return v;
     }
 
+    // the summed mask volumes behind the scoring roi and the stat roi (setup_world :771-815): mask files,
+    // else the rasterised body / StatROI contour, else empty (= roi_t(DIRECT))
+    std::vector<uint8_t>
+    contour_mask(const std::string& name) const {
+        const auto* c = structures.find(name);
+        if (!c) throw std::runtime_error("structure " + name + " is not in the structure file");
+        printf("%s\n", name.c_str());
+        return rasterize_contours(*c, ct.nx, ct.ny, ct.nz, grid.xe.data(), grid.ye.data(), grid.ze.data(), ct.dx, ct.dy);
+    }
+    void
+    roi_masks(std::vector<uint8_t>& scoring, std::vector<uint8_t>& stat) const {
+        scoring.clear();
+        stat.clear();
+        if (scoring_mask) scoring = read_mask_files(mask_filenames, ct.nx, ct.ny, ct.nz);
+        else if (read_structure) scoring = contour_mask(body_contour_name);
+        if (record_statistics) {
+            if (set_stat_roi_from_rtstruct) stat = contour_mask(stat_roi);
+            else if (!stat_roi_mask_filenames.empty()) stat = read_mask_files(stat_roi_mask_filenames, ct.nx, ct.ny, ct.nz);
+            else printf("Statistical ROI is set to entire patient.\n");
+        }
+    }
+
     // initialize(): setup_world + setup_materials + setup_beamsource + upload, per device
     void
     initialize() {
@@ -940,11 +1074,7 @@ public:
         n_beamline = (int) beamline.size();
         // regions of interest (setup_world :771-815)
         std::vector<uint8_t> scoring_mask_total, stat_mask_total;
-        if (scoring_mask) scoring_mask_total = read_mask_files(mask_filenames, ct.nx, ct.ny, ct.nz);
-        if (record_statistics) {
-            if (!stat_roi_mask_filenames.empty()) stat_mask_total = read_mask_files(stat_roi_mask_filenames, ct.nx, ct.ny, ct.nz);
-            else printf("Statistical ROI is set to entire patient.\n");
-        }
+        roi_masks(scoring_mask_total, stat_mask_total);
         for (size_t d = 0; d < gpu_ids.size(); ++d) {
             mqi_handle* h = nullptr;
             check(mqi_create(gpu_ids[d], &h), "mqi_create");

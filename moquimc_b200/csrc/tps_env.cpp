@@ -11,11 +11,16 @@ dump_json(mqib::tps_env& env) {
     // the builders narrate on stdout like the reference: run them before the one-line JSON starts
     std::vector<std::vector<mqib::tps_env::beamline_node>> all_nodes;
     for (size_t q = 0; q < env.beam_numbers.size(); ++q) all_nodes.push_back(env.build_beamline(env.plan.beams[env.beam_numbers[q] - 1]));
-    unsigned long long roi_scoring = 0, roi_stat = 0;
-    const uint64_t     nvox = (uint64_t) env.ct.nx * env.ct.ny * env.ct.nz;
-    if (env.scoring_mask) roi_scoring = mqib::mask_to_roi(mqib::read_mask_files(env.mask_filenames, env.ct.nx, env.ct.ny, env.ct.nz).data(), nvox).size();
-    if (env.record_statistics && !env.stat_roi_mask_filenames.empty())
-        roi_stat = mqib::mask_to_roi(mqib::read_mask_files(env.stat_roi_mask_filenames, env.ct.nx, env.ct.ny, env.ct.nz).data(), nvox).size();
+    unsigned long long   roi_scoring = 0, roi_stat = 0;
+    const uint64_t       nvox = (uint64_t) env.ct.nx * env.ct.ny * env.ct.nz;
+    std::vector<uint8_t> m_scoring, m_stat;
+    env.roi_masks(m_scoring, m_stat);
+    if (!m_scoring.empty()) roi_scoring = mqib::mask_to_roi(m_scoring.data(), nvox).size();
+    if (!m_stat.empty()) roi_stat = mqib::mask_to_roi(m_stat.data(), nvox).size();
+    if (const char* dump = getenv("MQI_DRYRUN_DUMP_MASKS")) {   // test hook: the summed mask volumes as raw uint8
+        if (!m_scoring.empty()) std::ofstream(std::string(dump) + "/scoring_mask.raw", std::ios::binary).write((const char*) m_scoring.data(), m_scoring.size());
+        if (!m_stat.empty()) std::ofstream(std::string(dump) + "/stat_mask.raw", std::ios::binary).write((const char*) m_stat.data(), m_stat.size());
+    }
     printf("DRYRUN {\"seed\": %d, \"n_fractions\": %d, \"sim_type\": %d, \"beams\": [", env.master_seed, env.n_fractions, (int) env.sim_type);
     for (size_t q = 0; q < env.beam_numbers.size(); ++q) {
         const mqib::plan_beam& b = env.plan.beams[env.beam_numbers[q] - 1];

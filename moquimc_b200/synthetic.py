@@ -61,6 +61,28 @@ def write_mask_mha(path, mask, origin=(0.0, 0.0, 0.0), spacing=(1.0, 1.0, 1.0)):
         f.write(np.ascontiguousarray(mask, dtype=np.uint8).tobytes())
 
 
+def write_structures(path, rois):
+    """Text structure set (csrc/mqi_tps_host.hpp text_structures): rois = {name: [contour, ...]}, a contour is
+    a list of (x, y, z) points of one closed planar polygon (the RTSTRUCT's ContourData)."""
+    with open(path, "w") as f:
+        for name, contours in rois.items():
+            f.write("[roi]\nname %s\n" % name)
+            for c in contours:
+                f.write("[contour]\n# x y z\n")
+                for (x, y, z) in c:
+                    f.write("%.7g %.7g %.7g\n" % (x, y, z))
+
+
+def ellipse_contours(a, b, z_values, n_points=48, centre=(0.0, 0.0), z_scale=None):
+    """One elliptical contour per z (semi-axes shrink with z_scale(z) if given)."""
+    out = []
+    for z in z_values:
+        k = 1.0 if z_scale is None else z_scale(z)
+        t = np.linspace(0.0, 2.0 * np.pi, n_points, endpoint=False)
+        out.append([(centre[0] + k * a * np.cos(u), centre[1] + k * b * np.sin(u), float(z)) for u in t])
+    return out
+
+
 def beam_model_rows(e_lo=60.0, e_hi=240.0, step=10.0):
     """[spot] rows: Enominal E dE x y xp yp ratio"""
     rows = []

@@ -144,7 +144,7 @@ def test_parser_semantics(case):
     assert "Valid machine is not available" in dry_run(write_variant(root, "m.in", Machine="gtr1:x"), expect_fail=True)
     assert "threshold cannot be zero" in dry_run(write_variant(root, "st.in", StoppingStatistics="true", StoppingCriteria=1.0),
                                                  expect_fail=True)
-    assert "no GDCM" in dry_run(write_variant(root, "rs.in", ReadStructure="true"), expect_fail=True)
+    assert "needs GDCM" in dry_run(write_variant(root, "rs.in", ReadStructure="true"), expect_fail=True)
     # UnitWeights overrides the histories of every spot in a per-spot run (:1488-1491)
     out = dry_run(write_variant(root, "uw.in", Scorer="Dij", UnitWeights=321))
     assert {s["histories"] for s in out["beams"][0]["spots"]} == {321}
@@ -235,8 +235,69 @@ def test_mask_keys_and_roi_sizes(tmp_path):
     err = dry_run(S.make_case(root, n=n, ScoringMask="true"), expect_fail=True)
     assert "Mask filename is missing" in err
     err = dry_run(S.make_case(root, n=n, ReadStructure="true"), expect_fail=True)
-    assert "RTSTRUCT" in err
+    assert "StructureFile" in err
     # a mask with other dimensions is refused
     S.write_mask_mha(os.path.join(root, "bad.mha"), np.zeros((4, 4, 4), dtype=np.uint8))
     err = dry_run(S.make_case(root, n=n, ScoringMask="true", Mask=os.path.join(root, "bad.mha")), expect_fail=True)
     assert "dimensions" in err
+
+
+def rasterize_numpy(contours, xe, ye, ze, dx, dy):
+    """fill_contour + sol1_1 (mqi_tps_env.hpp:1769-1826) restated with numpy in fp32."""
+    nx, ny, nz = len(xe) - 1, len(ye) - 1, len(ze) - 1
+    vol = np.zeros((nz, ny, nx), dtype=np.uint8)
+    px = (xe[:nx - 1] + f32(dx) * f32(0.5)).astype(f32)   # the reference promotes dx * 0.5 to double; identical here
+    py = (ye[:ny - 1] + f32(dy) * f32(0.5)).astype(f32)
+    for c in contours:
+        c = np.asarray(c, dtype=f32)
+        z = c[0, 2]
+        k = next((i for i in range(nz - 1) if ze[i] < z < ze[i + 1]), -1)
+        if k < 0:
+            continue
+        inside = np.zeros((ny - 1, nx - 1), dtype=bool)
+        n = len(c)
+        for i in range(n):
+            j = (i - 1) % n
+            x0, y0, x1, y1 = c[i, 0], c[i, 1], c[j, 0], c[j, 1]
+            cond_y = ((y0 <= py) & (py < y1)) | ((y1 <= py) & (py < y0))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                xi = ((x1 - x0) * (py - y0) / (y1 - y0) + x0).astype(f32)
+            hit = cond_y[:, None] & (px[None, :] < xi[:, None])
+            inside ^= hit
+        vol[k, :ny - 1, :nx - 1] |= inside.astype(np.uint8)
+    return vol
+
+
+def test_structure_contours_are_rasterised_like_fill_contour(tmp_path):
+    root = str(tmp_path)
+    n, sp = (64, 64, 40), (4.0, 4.0, 6.0)
+    zc = (np.arange(n[2]) - (n[2] - 1) / 2.0) * sp[2]
+    body = S.ellipse_contours(70.0, 90.0, zc[3:37], centre=(4.0, -6.0))
+    ptv = S.ellipse_contours(22.0, 18.0, zc[14:26], n_points=24, centre=(-8.0, 10.0))
+    # a contour in the LAST slab is never found (the slice search stops at nz - 1): kept
+    body_plus = body + S.ellipse_contours(70.0, 90.0, [zc[-1]], centre=(4.0, -6.0))
+    S.write_structures(os.path.join(root, "structures.txt"), {"External": body_plus, "PTV 1": ptv})
+    inp = S.make_case(root, n=n, spacing=sp, ReadStructure="true", BodyContourName="external", StructureFile="structures.txt",
+                      StoppingStatistics="true", StoppingCriteria="3.0", StatROIStructFromRT="true", StatROI="PTV 1")
+    env = dict(os.environ, MQI_DRYRUN_DUMP_MASKS=root)
+    r = subprocess.run([EXE, "--dry-run", inp], capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0, r.stderr
+    j = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("DRYRUN ")][-1][len("DRYRUN "):])
+    g = j["grid"]
+    xe = (f32(g["xe"][0]) + np.arange(n[0] + 1, dtype=f32) * f32(sp[0])).astype(f32)
+    ye = (f32(g["ye"][0]) + np.arange(n[1] + 1, dtype=f32) * f32(sp[1])).astype(f32)
+    ze = np.empty(n[2] + 1, dtype=f32)
+    ze[0] = g["ze"][0]
+    for i in range(1, n[2] + 1):
+        ze[i] = ze[i - 1] + f32(sp[2])
+    for name, contours, key in (("scoring_mask.raw", body_plus, "scoring_roi_size"), ("stat_mask.raw", ptv, "stat_roi_size")):
+        got = np.fromfile(os.path.join(root, name), dtype=np.uint8).reshape(n[2], n[1], n[0])
+        want = rasterize_numpy(contours, xe, ye, ze, sp[0], sp[1])
+        assert want.sum() > 0 and np.array_equal(got, want), name
+        assert j[key] == int(want.sum())      # contours are 0/1: every run of the mask is inside the roi
+        assert got[-1].sum() == 0 and got[:, -1, :].sum() == 0 and got[:, :, -1].sum() == 0
+    # unknown structure names and a missing structure file are errors
+    err = dry_run(S.make_case(root, n=n, spacing=sp, ReadStructure="true", BodyContourName="Skin", StructureFile="structures.txt"), expect_fail=True)
+    assert "Skin" in err
+    err = dry_run(S.make_case(root, n=n, spacing=sp, ReadStructure="true"), expect_fail=True)
+    assert "StructureFile" in err
