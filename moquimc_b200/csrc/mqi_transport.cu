@@ -492,9 +492,9 @@ enter_nodes(const Params& P, const Smem& sm, TrackIO& T) {
             py > ye[ny] + 2.f * kGeomTol || pz < ze[0] - 2.f * kGeomTol || pz > ze[nz] + 2.f * kGeomTol) {
             ix = iy = iz = -1;
         } else {
-            ix = index_axis_guess(xe, nx, px, dx, G.inv_w[0]);
-            iy = index_axis_guess(ye, ny, py, dy, G.inv_w[1]);
-            iz = index_axis_guess(ze, nz, pz, dz, G.inv_w[2]);
+            ix = index_axis_fast(xe, nx, px, dx, G.inv_w[0]);
+            iy = index_axis_fast(ye, ny, py, dy, G.inv_w[1]);
+            iz = index_axis_fast(ze, nz, pz, dz, G.inv_w[2]);
         }
         bool  alive = true;
         float d[3]  = { dx, dy, dz };
@@ -653,13 +653,14 @@ refill_queue(const Params& P, uint32_t* q, int q_n) {
 __device__ __noinline__ float2
 delta_retry(uint32_t blk, uint32_t h0, uint32_t key2, float T_cut, float Tmax1, float b1_sq, float inv_2Et_sq) {
     const float inv_Tmax1 = 1.0f / Tmax1;
+    const float g_max     = 1.0f - b1_sq * T_cut * inv_Tmax1 + T_cut * T_cut * inv_2Et_sq;   // see the first try
     while (true) {
         uint32_t wn, wa;
         philox2x32_10(blk, h0, key2, wn, wa);
         blk += 1;
         const float n  = u32_to_uniform(wn);
         const float Te = T_cut * Tmax1 / ((1.0f - n) * Tmax1 + n * T_cut);
-        if (u32_to_uniform(wa) < 1.0f - b1_sq * Te * inv_Tmax1 + Te * Te * inv_2Et_sq) return make_float2(Te, __uint_as_float(blk));
+        if (u32_to_uniform(wa) * g_max < 1.0f - b1_sq * Te * inv_Tmax1 + Te * Te * inv_2Et_sq) return make_float2(Te, __uint_as_float(blk));
     }
 }
 
@@ -951,7 +952,12 @@ transport_kernel(const __grid_constant__ Params P) {
                         const float inv_2Et_sq = 0.5f / (Et1 * Et1);
                         const float n  = fminf(u / c0, 1.0f);
                         float       Te = T_cut * Tmax1 / ((1.0f - n) * Tmax1 + n * T_cut);
-                        if (!(spare_bytes_to_uniform(w[0], w[1], w[2]) < 1.0f - b1_sq * Te / Tmax1 + Te * Te * inv_2Et_sq)) {
+                        // The reference accepts with probability g(Te) = 1 - b^2 Te/Tmax + Te^2/(2 Et^2) (:447-451).  g
+                        // falls with Te on [T_cut, Tmax] (g' < 0 for Te < b^2 Et^2 / Tmax, which is ~1e6 MeV), so
+                        // g(T_cut) bounds it: accepting with g(Te) / g(T_cut) samples the same density with half
+                        // the rejections (4 % instead of 9 %).
+                        const float g_max = 1.0f - b1_sq * T_cut / Tmax1 + T_cut * T_cut * inv_2Et_sq;
+                        if (!(spare_bytes_to_uniform(w[0], w[1], w[2]) * g_max < 1.0f - b1_sq * Te / Tmax1 + Te * Te * inv_2Et_sq)) {
                             const float2 rt = delta_retry(blk, h0, k0 ^ (k1 * 0x85EBCA6Bu) ^ (h1 * 0xC2B2AE35u), T_cut, Tmax1, b1_sq, inv_2Et_sq);
                             Te  = rt.x;
                             blk = __float_as_uint(rt.y);

@@ -853,7 +853,14 @@ delta_post_step(ctx_t* c, track_t* trk, float n_first, float acc_first) {
         else rng_pair2(c->rng, &n, &acc);
         Te = c->T_cut * rel.Te_max;
         Te /= ((1.0 - n) * rel.Te_max + n * c->T_cut);
-        if (acc < 1.0 - rel.beta_sq * Te / rel.Te_max + Te * Te / (2.0 * rel.Et_sq)) break;
+        /* The reference accepts with probability g(Te) = 1 - b^2 Te/Tmax + Te^2/(2 Et^2) (:447-451).  g falls
+         * with Te on [T_cut, Tmax], so g(T_cut) bounds it; like the CUDA path this restatement accepts with
+         * g(Te) / g(T_cut): the same density from the same envelope with half the rejections (part of the
+         * shared sampling protocol). */
+        {
+            float g_max = 1.0 - rel.beta_sq * c->T_cut / rel.Te_max + c->T_cut * c->T_cut / (2.0 * rel.Et_sq);
+            if (acc * g_max < 1.0 - rel.beta_sq * Te / rel.Te_max + Te * Te / (2.0 * rel.Et_sq)) break;
+        }
     }
     if (c->variant == MQO_VARIANT_DEBUG) {
         track_t d  = *trk;
