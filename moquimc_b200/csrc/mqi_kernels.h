@@ -21,10 +21,10 @@
 #define MQI_K_ACCUM_WARP_MATCH 1
 
 #ifndef MQI_K_BLOCK
-#define MQI_K_BLOCK 256
+#define MQI_K_BLOCK 768
 #endif
 #ifndef MQI_K_MIN_BLOCKS
-#define MQI_K_MIN_BLOCKS 3   /* <= 85 registers/thread, 24 warps/SM: measured best of 2/3/4 CTAs of 256 and 8 of 128 on B200 (profiles/r1_experiments.md) */
+#define MQI_K_MIN_BLOCKS 1   /* 24 warps/SM at <= 80 registers/thread in ONE CTA: one copy of the shared-memory tables leaves the most L1; measured best of 128x5 ... 768x1 on B200 (profiles/r1_experiments.md) */
 #endif
 
 #ifndef MQI_K_LATE_LUT

@@ -30,9 +30,10 @@ struct Smem {
 };
 
 // queue of pre-sampled primaries, one per warp, structure of arrays: field f of entry e at
-// [f * kQueueCap + e].  Filled 32 entries at a time by the whole warp (refill_queue), drained by the
-// lanes whose track ended.
-constexpr int kQueueCap    = 64;
+// [f * kQueueCap + e].  Filled by the whole warp when it has run empty (refill_queue: up to 32 entries),
+// drained by the lanes whose track ended.  Shared memory is taken from the L1 carve-out, so the queue
+// is kept as small as one refill.
+constexpr int kQueueCap    = 32;
 enum QueueField { Q_PX = 0, Q_PY, Q_PZ, Q_DX, Q_DY, Q_DZ, Q_KE, Q_IX, Q_IY, Q_IZ, Q_H0, Q_H1, Q_SPOT, Q_NODE, Q_FIELDS };
 constexpr int kQueueWords  = Q_FIELDS * kQueueCap;
 constexpr size_t kTableBytes = kTableN * (2 * sizeof(float4) + sizeof(float2));
@@ -751,7 +752,9 @@ transport_kernel(const __grid_constant__ Params P) {
             const int n_need = __popc(need_mask);
             const int lane   = threadIdx.x & 31;
             uint32_t* q      = sm.queue + (threadIdx.x >> 5) * kQueueWords;
-            if (q_state < n_need) q_state = refill_queue<MULTI>(P, q, q_state);   // warp-uniform (not exhausted, too few entries): every lane helps
+            // warp-uniform: the queue is empty and the source is not exhausted -> every lane helps to refill.
+            // Lanes a nearly empty queue cannot serve this turn idle for one pass and are served next turn.
+            if (q_state == 0) q_state = refill_queue<MULTI>(P, q, 0);
             const int  q_n       = q_state & 0xffff;
             const bool src_empty = (q_state >> 16) != 0;
             if (need) {
