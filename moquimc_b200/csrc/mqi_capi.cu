@@ -153,6 +153,8 @@ struct mqi_handle {
     int          accum    = MQI_ACCUM_ATOMIC;
     int          count_steps = 0;
     int          blocks_per_sm_override = 0;
+    int          l2_persist = 0;               // option "l2_persist": pin the material volume in L2 with a persisting access window (measured: no gain at C1)
+    size_t       l2_persist_max = 0, l2_window_max = 0;
     // physics tables
     float4* d_tab_a0 = nullptr;
     float4* d_tab_a1 = nullptr;
@@ -445,6 +447,8 @@ mqi_create(int device_id, mqi_handle** out) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device_id));
     h->sm_count = prop.multiProcessorCount;
+    h->l2_persist_max = (size_t) prop.persistingL2CacheMaxSize;
+    h->l2_window_max  = (size_t) prop.accessPolicyMaxWindowSize;
     CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
     CU(cudaEventCreate(&h->ev0));
@@ -701,6 +705,7 @@ mqi_set_option(mqi_handle* h, const char* key, int64_t value) {
     const std::string k(key);
     if (k == "count_steps") h->count_steps = value != 0;
     else if (k == "blocks_per_sm") h->blocks_per_sm_override = (int) value;
+    else if (k == "l2_persist") h->l2_persist = value != 0;
     else return fail(MQI_EINVAL, "unknown option " + k);
     return MQI_OK;
 }
@@ -812,6 +817,27 @@ mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t cou
     // persistent grid: a whole number of CTAs per SM, never more lanes than histories
     unsigned long long want = (count + MQI_K_BLOCK - 1) / MQI_K_BLOCK;
     int                grid = (int) std::min<unsigned long long>((unsigned long long) h->sm_count * bps, want);
+    {   // subsystem 3: the 16-bit material volume of the scored grid is read once per voxel step by every
+        // lane; keep it resident in L2 (persisting access window on the launching stream) while the fp64
+        // dose grid streams through the rest.  Larger volumes than the persisting carve-out get a
+        // proportional hit ratio.
+        cudaStreamAttrValue attr;
+        std::memset(&attr, 0, sizeof(attr));
+        if (h->l2_persist && h->l2_persist_max > 0 && h->l2_window_max > 0) {
+            const size_t bytes  = std::min(nvox(h) * sizeof(uint16_t), h->l2_window_max);
+            const size_t carve  = std::min(h->l2_persist_max, bytes);
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                attr.accessPolicyWindow.base_ptr  = h->d_mat;
+                attr.accessPolicyWindow.num_bytes = bytes;
+                attr.accessPolicyWindow.hitRatio  = (float) std::min(1.0, (double) carve / (double) bytes);
+                attr.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp  = cudaAccessPropertyStreaming;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+    }
     CU(cudaMemsetAsync(h->d_counters, 0, C_COUNT * sizeof(unsigned long long), h->stream));
     CU(cudaEventRecord(h->ev0, h->stream));
     CU(launch_transport(p, h->variant, grid, smem, h->stream));

@@ -18,6 +18,8 @@ e.add_scorer(capi.SCORER_DOSE, "dose")
 e.set_accumulation(accum)
 e.set_beamlets([capi.make_beamlet(energy, [0, 0, 0.5, 0, 0, -1], [spot, spot, 0, 0, 0, 0], uniform=True)], [n * 8])
 e.set_option("count_steps", 1)
+if os.environ.get("MQI_L2_PERSIST") is not None:
+    e.set_option("l2_persist", int(os.environ["MQI_L2_PERSIST"]))
 st = e.run(1, 0, min(n, 200000))
 for i in range(3):
     t = time.time()
