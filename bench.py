@@ -111,6 +111,19 @@ class ClockSampler:
 REF_EXE = os.path.join(ROOT, "oracle", "_ref", "phantom_env_cpu_debug")
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """the one JSON line of this run, on the real stdout"""
+    text = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(text.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, text)
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -188,7 +201,7 @@ def bench_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -394,7 +407,7 @@ def bench_b200(args):
                                                   "transport phase only" % (procs, n)}
             except Exception as ex:   # the checker is missing: report it, never fake a number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %s" % ex}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -415,6 +428,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    # stdout carries exactly ONE line, the JSON: anything libraries write to file descriptor 1 on the way
+    # (NCCL prints its version there) goes to stderr instead
+    sys.stdout.flush()
+    global _JSON_FD
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return bench_reference(args)
     return bench_b200(args)
