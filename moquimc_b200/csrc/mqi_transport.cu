@@ -652,16 +652,14 @@ refill_queue(const Params& P, uint32_t* q, int q_n) {
 // returns {Te, next block number} in registers (a reference parameter would pin the lane's block
 // counter to local memory for the whole loop)
 __device__ __noinline__ float2
-delta_retry(uint32_t blk, uint32_t h0, uint32_t key2, float T_cut, float Tmax1, float b1_sq, float inv_2Et_sq) {
-    const float inv_Tmax1 = 1.0f / Tmax1;
-    const float g_max     = 1.0f - b1_sq * T_cut * inv_Tmax1 + T_cut * T_cut * inv_2Et_sq;   // see the first try
+delta_retry(uint32_t blk, uint32_t h0, uint32_t key2, float T_cut, float Tmax1, float kb, float inv_2Et_sq, float g_max) {
+    const float dT = T_cut - Tmax1, num = T_cut * Tmax1;   // kb = b1^2 / Tmax1, g_max = g(T_cut): see the first try
     while (true) {
         uint32_t wn, wa;
         philox2x32_10(blk, h0, key2, wn, wa);
         blk += 1;
-        const float n  = u32_to_uniform(wn);
-        const float Te = T_cut * Tmax1 / ((1.0f - n) * Tmax1 + n * T_cut);
-        if (u32_to_uniform(wa) * g_max < 1.0f - b1_sq * Te * inv_Tmax1 + Te * Te * inv_2Et_sq) return make_float2(Te, __uint_as_float(blk));
+        const float Te = num * rcp_fast(fmaf(u32_to_uniform(wn), dT, Tmax1));
+        if (u32_to_uniform(wa) * g_max < fmaf(Te * Te, inv_2Et_sq, fmaf(-kb, Te, 1.0f))) return make_float2(Te, __uint_as_float(blk));
     }
 }
 
@@ -947,21 +945,25 @@ transport_kernel(const __grid_constant__ Params P) {
                         // First try of the rejection loop without another generator call: given that the
                         // delta channel was selected, u / c0 is uniform in [0,1); the acceptance deviate
                         // comes from the top bytes of the step's block (unused by the 23-bit uniforms).
-                        const float Et1   = ke1 + kMp;
-                        const float g1    = Et1 * (1.0f / kMp);
+                        // Kinematics of vtx1.ke (relativistic_quantities, :27-44) with the divisions shared: with
+                        // g = Et/Mp, D = 1 + 2 g Me/Mp + (Me/Mp)^2:  b^2 = 1 - 1/g^2,  Tmax = 2 Me (g^2 - 1) / D,
+                        // b^2 / Tmax = D / (2 Me g^2),  1 / (2 Et^2) = 1 / (2 Mp^2 g^2)  -- four reciprocals in all.
+                        const float g1    = (ke1 + kMp) * (1.0f / kMp);
                         const float g1_sq = g1 * g1;
-                        const float b1_sq = 1.0f - 1.0f / g1_sq;
-                        const float Tmax1 = (2.0f * kMe * b1_sq * g1_sq) / (1.0f + 2.0f * g1 * MeMp + MeMp * MeMp);
-                        const float inv_2Et_sq = 0.5f / (Et1 * Et1);
-                        const float n  = fminf(u / c0, 1.0f);
-                        float       Te = T_cut * Tmax1 / ((1.0f - n) * Tmax1 + n * T_cut);
+                        const float r_g   = rcp_fast(g1_sq);
+                        const float D1    = fmaf(2.0f * MeMp, g1, 1.0f + MeMp * MeMp);
+                        const float Tmax1 = (2.0f * kMe) * (g1_sq - 1.0f) * rcp_fast(D1);
+                        const float kb    = D1 * r_g * (0.5f / kMe);          // b1^2 / Tmax1
+                        const float inv_2Et_sq = (0.5f / kMpSq) * r_g;
+                        const float n  = fminf(u * rcp_fast(c0), 1.0f);
+                        float       Te = T_cut * Tmax1 * rcp_fast(fmaf(n, T_cut - Tmax1, Tmax1));   // T_cut Tmax / ((1 - n) Tmax + n T_cut)
                         // The reference accepts with probability g(Te) = 1 - b^2 Te/Tmax + Te^2/(2 Et^2) (:447-451).  g
                         // falls with Te on [T_cut, Tmax] (g' < 0 for Te < b^2 Et^2 / Tmax, which is ~1e6 MeV), so
                         // g(T_cut) bounds it: accepting with g(Te) / g(T_cut) samples the same density with half
                         // the rejections (4 % instead of 9 %).
-                        const float g_max = 1.0f - b1_sq * T_cut / Tmax1 + T_cut * T_cut * inv_2Et_sq;
-                        if (!(spare_bytes_to_uniform(w[0], w[1], w[2]) * g_max < 1.0f - b1_sq * Te / Tmax1 + Te * Te * inv_2Et_sq)) {
-                            const float2 rt = delta_retry(blk, h0, k0 ^ (k1 * 0x85EBCA6Bu) ^ (h1 * 0xC2B2AE35u), T_cut, Tmax1, b1_sq, inv_2Et_sq);
+                        const float g_max = fmaf(T_cut * T_cut, inv_2Et_sq, fmaf(-kb, T_cut, 1.0f));
+                        if (!(spare_bytes_to_uniform(w[0], w[1], w[2]) * g_max < fmaf(Te * Te, inv_2Et_sq, fmaf(-kb, Te, 1.0f)))) {
+                            const float2 rt = delta_retry(blk, h0, k0 ^ (k1 * 0x85EBCA6Bu) ^ (h1 * 0xC2B2AE35u), T_cut, Tmax1, kb, inv_2Et_sq, g_max);
                             Te  = rt.x;
                             blk = __float_as_uint(rt.y);
                         }
