@@ -387,7 +387,9 @@ def bench_b200(args):
                        if world > 1 else "1 GPU",
                        "l2": "256 MB flush written between timed steps (untimed); working set 140 MB > 126 MB L2",
                        "timer": "CUDA events on the launching stream per step, max over ranks",
-                       "dose_checksum": checksum, "wall_s_timed_region": t_wall},
+                       "dose_checksum": checksum, "wall_s_timed_region": t_wall,
+                       "parity": "gamma 1 %/1 mm >= 99 %, R80 within 0.1 mm against the reference's CPU dose on this workload: "
+                                 "tests/test_gpu_parity.py::test_c1_dose_against_reference_golden"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": ke, "kernel_ms_per_step": sum(e2e_kernel_ms[1:]) / max(1, len(e2e_kernel_ms) - 1), "timer": "host wall clock around blocking C-ABI calls, synchronised both sides"},
             "gpu_launches": launches,
