@@ -191,6 +191,11 @@ struct mqi_handle {
     // scorers
     std::vector<HostScorer> scorers;
     unsigned long long*     d_counters = nullptr;
+    // device buffers released by a geometry change, kept for the next one of the same size: a caller that
+    // re-uploads the CT per run (x_environment::initialize per beam, bench.py's end-to-end leg) then pays no
+    // cudaMalloc / cudaFree (both synchronise the device) per run
+    std::multimap<size_t, void*> pool;
+    size_t                       pool_bytes = 0;
     mqi_run_stats           stats {};
 };
 
@@ -205,11 +210,44 @@ activate(mqi_handle* h) {
     return MQI_OK;
 }
 
+template<typename T>
+cudaError_t
+pool_alloc(mqi_handle* h, T** p, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 1);
+    auto it = h->pool.find(bytes);
+    if (it != h->pool.end()) {
+        *p = static_cast<T*>(it->second);
+        h->pool_bytes -= bytes;
+        h->pool.erase(it);
+        return cudaSuccess;
+    }
+    return cudaMalloc(p, bytes);
+}
+
 void
-free_grid(mqi_handle* h) {
-    cudaFree(h->d_edges);
-    cudaFree(h->d_mat);
-    cudaFree(h->d_lut);
+pool_free(mqi_handle* h, void* p, size_t bytes) {
+    if (!p) return;
+    bytes = std::max<size_t>(bytes, 1);
+    if (h->pool.size() >= 16 || h->pool_bytes + bytes > (4ull << 30)) {
+        cudaFree(p);
+        return;
+    }
+    h->pool.emplace(bytes, p);
+    h->pool_bytes += bytes;
+}
+
+void
+pool_clear(mqi_handle* h) {
+    for (auto& kv : h->pool) cudaFree(kv.second);
+    h->pool.clear();
+    h->pool_bytes = 0;
+}
+
+void
+free_grid(mqi_handle* h) {   // sizes are those of the grid being dropped (h->nx ... are still its dimensions)
+    pool_free(h, h->d_edges, (size_t) (h->nx + h->ny + h->nz + 3) * sizeof(float));
+    pool_free(h, h->d_mat, nvox(h) * sizeof(uint16_t));
+    pool_free(h, h->d_lut, (size_t) h->lut_size * sizeof(MatEntry));
     h->d_edges = nullptr;
     h->d_mat   = nullptr;
     h->d_lut   = nullptr;
@@ -228,7 +266,7 @@ set_grid_common(mqi_handle* h, const float* xe, int n_xe, const float* ye, int n
     if (transport_smem_bytes(n_xe + n_ye + n_ze, 1) > 200 * 1024) return fail(MQI_EINVAL, "too many grid edges for shared memory");
     // scorers are sized by the grid: drop dense accumulators of a previous grid
     for (auto& s : h->scorers) {
-        if (s.d_dense && !s.external) cudaFree(s.d_dense);
+        if (s.d_dense && !s.external) pool_free(h, s.d_dense, nvox(h) * sizeof(double));
         if (!s.external) s.d_dense = nullptr;
         cudaFree(s.d_roi);   // a region of interest belongs to the grid it was defined on
         s.d_roi    = nullptr;
@@ -242,7 +280,7 @@ set_grid_common(mqi_handle* h, const float* xe, int n_xe, const float* ye, int n
     e.insert(e.end(), ye, ye + n_ye);
     e.insert(e.end(), ze, ze + n_ze);
     h->edges_host = e;
-    CU(cudaMalloc(&h->d_edges, e.size() * sizeof(float)));
+    CU(pool_alloc(h, &h->d_edges, e.size() * sizeof(float)));
     CU(cudaMemcpyAsync(h->d_edges, e.data(), e.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->inv_w[0] = (float) (n_xe - 1) / (xe[n_xe - 1] - xe[0]);
@@ -263,7 +301,7 @@ upload_hu_lut(mqi_handle* h, float density_scale) {
         if (density_scale != 1.0f) rho *= density_scale;
         lut[i] = make_mat_entry(rho, h->variant);
     }
-    CU(cudaMalloc(&h->d_lut, lut.size() * sizeof(MatEntry)));
+    CU(pool_alloc(h, &h->d_lut, lut.size() * sizeof(MatEntry)));
     CU(cudaMemcpyAsync(h->d_lut, lut.data(), lut.size() * sizeof(MatEntry), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->lut_size = (int) lut.size();
@@ -279,7 +317,7 @@ ensure_scorer_buffers(mqi_handle* h) {
                 CU(launch_dij_clear(s.d_table, s.capacity, h->stream));
             }
         } else if (!s.d_dense) {
-            CU(cudaMalloc(&s.d_dense, nvox(h) * sizeof(double)));
+            CU(pool_alloc(h, &s.d_dense, nvox(h) * sizeof(double)));
             CU(cudaMemsetAsync(s.d_dense, 0, nvox(h) * sizeof(double), h->stream));
         }
     }
@@ -492,6 +530,7 @@ mqi_destroy(mqi_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     free_grid(h);
+    pool_clear(h);
     free_beamline(h);
     for (auto& s : h->scorers) {
         if (s.d_dense && !s.external) cudaFree(s.d_dense);
@@ -525,15 +564,16 @@ set_grid_hu_impl(mqi_handle* h, const float* xe, int n_xe, const float* ye, int 
     rc = set_grid_common(h, xe, n_xe, ye, n_ye, ze, n_ze, rot, trans);
     if (rc) return rc;
     const size_t nv = nvox(h);
-    CU(cudaMalloc(&h->d_mat, nv * sizeof(uint16_t)));
+    CU(pool_alloc(h, &h->d_mat, nv * sizeof(uint16_t)));
     if (on_device) {
         CU(launch_hu_to_material(static_cast<const int16_t*>(hu), h->d_mat, nv, h->stream));
     } else {
-        DevBuf<int16_t> tmp;
-        CU(tmp.alloc(nv));
-        CU(cudaMemcpyAsync(tmp.p, hu, nv * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream));
-        CU(launch_hu_to_material(tmp.p, h->d_mat, nv, h->stream));
+        int16_t* tmp = nullptr;   // staging buffer of the HU upload (the size differs from d_mat's by the +1 below, so the pool tells them apart)
+        CU(pool_alloc(h, &tmp, nv * sizeof(int16_t) + 1));
+        CU(cudaMemcpyAsync(tmp, hu, nv * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream));
+        CU(launch_hu_to_material(tmp, h->d_mat, nv, h->stream));
         CU(cudaStreamSynchronize(h->stream));
+        pool_free(h, tmp, nv * sizeof(int16_t) + 1);
     }
     rc = upload_hu_lut(h, density_scale);
     if (rc) return rc;
@@ -567,8 +607,8 @@ mqi_set_grid_density(mqi_handle* h, const float* xe, int n_xe, const float* ye, 
     std::vector<MatEntry> lut;
     rc = build_density_lut(rho, nv, h->variant, mat, lut);
     if (rc) return rc;
-    CU(cudaMalloc(&h->d_mat, nv * sizeof(uint16_t)));
-    CU(cudaMalloc(&h->d_lut, lut.size() * sizeof(MatEntry)));
+    CU(pool_alloc(h, &h->d_mat, nv * sizeof(uint16_t)));
+    CU(pool_alloc(h, &h->d_lut, lut.size() * sizeof(MatEntry)));
     CU(cudaMemcpyAsync(h->d_mat, mat.data(), nv * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_lut, lut.data(), lut.size() * sizeof(MatEntry), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
