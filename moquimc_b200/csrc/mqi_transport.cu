@@ -1295,15 +1295,16 @@ transport_smem_bytes(int n_edge_floats, int n_nodes) {
 typedef void (*transport_fn)(const Params);
 static transport_fn
 pick_transport(int variant, bool simple, bool multi) {
+    if (multi && simple) return variant == MQI_K_DEBUG ? transport_kernel<MQI_K_DEBUG, true, true> : transport_kernel<MQI_K_RELEASE, true, true>;
     if (multi) return variant == MQI_K_DEBUG ? transport_kernel<MQI_K_DEBUG, false, true> : transport_kernel<MQI_K_RELEASE, false, true>;
     if (variant == MQI_K_DEBUG) return simple ? transport_kernel<MQI_K_DEBUG, true, false> : transport_kernel<MQI_K_DEBUG, false, false>;
     return simple ? transport_kernel<MQI_K_RELEASE, true, false> : transport_kernel<MQI_K_RELEASE, false, false>;
 }
 
-// one dense Dose scorer with a DIRECT roi on a single-node world -> the specialised kernel
+// one dense Dose scorer with a DIRECT roi -> the kernels with the scorer loop compiled out
 bool
 transport_is_simple(const Params& p) {
-    return p.n_nodes == 1 && p.n_scorers == 1 && p.sc[0].kind == MQI_K_DOSE && !p.sc[0].roi && !(p.quirks & MQI_K_QUIRK_B2);
+    return p.n_scorers == 1 && p.sc[0].kind == MQI_K_DOSE && !p.sc[0].roi && !(p.quirks & MQI_K_QUIRK_B2);
 }
 
 cudaError_t
