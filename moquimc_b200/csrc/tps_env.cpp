@@ -6,6 +6,8 @@
 // (beamlets, histories per spot, CT edges) as JSON without touching a GPU: used by the CPU tests.
 #include "mqi_tps_host.hpp"
 
+#include <iterator>
+
 static void
 dump_json(mqib::tps_env& env) {
     // the builders narrate on stdout like the reference: run them before the one-line JSON starts
@@ -76,6 +78,20 @@ main(int argc, char* argv[]) {
             const std::vector<uint32_t> vox { 7, 2, 9, 2, 0, 5 }, spot { 2, 0, 2, 1, 0, 2 };
             const std::vector<double>   val { 0.5, 1.5, 2.5, 3.5, 4.5, 5.5 };
             mqib::save_csr_npz(argv[i + 1], 3, 10, vox, spot, val);
+            return 0;
+        } else if (std::string(argv[i]) == "--roi-selftest" && i + 1 < argc) {
+            // run-length roi of a raw uint8 summed-mask file (CPU suite): prints "start stride acc_stride" per run,
+            // then the compressed index of every 7th voxel
+            std::ifstream        f(argv[i + 1], std::ios::binary);
+            std::vector<uint8_t> m((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+            const mqib::RoiRuns  r = mqib::mask_to_roi(m.data(), m.size());
+            printf("runs %zu size %u\n", r.start.size(), r.size());
+            for (size_t k = 0; k < r.start.size(); ++k) printf("run %u %u %u\n", r.start[k], r.stride[k], r.acc_stride[k]);
+            for (size_t v = 0; v < m.size(); v += 7) printf("idx %zu %lld\n", v, (long long) r.compressed_index((uint32_t) v));
+            const std::vector<uint32_t> bits = r.bitmask();
+            size_t                      pop  = 0;
+            for (uint32_t w : bits) pop += (size_t) __builtin_popcount(w);
+            printf("bits %zu\n", pop);
             return 0;
         } else input_file = argv[i];
     }

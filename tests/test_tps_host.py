@@ -301,3 +301,71 @@ def test_structure_contours_are_rasterised_like_fill_contour(tmp_path):
     assert "Skin" in err
     err = dry_run(S.make_case(root, n=n, spacing=sp, ReadStructure="true"), expect_fail=True)
     assert "StructureFile" in err
+
+
+def roi_python(mask):
+    """mask_reader::mask_to_roi + roi_t::get_contour_idx restated in plain Python (mqi_file_handler.hpp:176-217,
+    mqi_roi.hpp:88-100), with the documented fix: a run still open at the end of the volume is closed there."""
+    start, stride, acc = [], [], []
+    open_, s0 = False, 0
+    for i, v in enumerate(mask):
+        if v == 1 and not open_:
+            open_, s0 = True, i
+        if v == 0 and open_:
+            open_ = False
+            start.append(s0)
+            stride.append(i - s0)
+            acc.append((acc[-1] if acc else 0) + i - s0)
+    if open_:
+        start.append(s0)
+        stride.append(len(mask) - s0)
+        acc.append((acc[-1] if acc else 0) + len(mask) - s0)
+
+    def idx(v):
+        c = sum(1 for s in start if s <= v) - 1     # lower_bound_cpp(v) - 1
+        if c < 0:
+            return -1
+        d = v - start[c]
+        if d < stride[c]:
+            return d + (acc[c - 1] if c > 0 else 0)
+        return -1
+    return start, stride, acc, idx
+
+
+@pytest.mark.parametrize("case", ["random", "zeros", "ones", "open_end", "overlap", "single"])
+def test_run_length_roi_matches_the_reference_rule(tmp_path, case):
+    rng = np.random.default_rng(7)
+    n = 400
+    if case == "random":
+        m = (rng.random(n) < 0.5).astype(np.uint8)
+    elif case == "zeros":
+        m = np.zeros(n, np.uint8)
+    elif case == "ones":
+        m = np.ones(n, np.uint8)
+    elif case == "open_end":
+        m = np.zeros(n, np.uint8); m[350:] = 1; m[10:20] = 1
+    elif case == "overlap":   # sums of two masks: 2 neither opens nor closes a run
+        m = (rng.random(n) < 0.4).astype(np.uint8) + (rng.random(n) < 0.4).astype(np.uint8)
+    else:
+        m = np.zeros(n, np.uint8); m[0] = 1
+    path = os.path.join(str(tmp_path), "m.raw")
+    m.tofile(path)
+    r = subprocess.run([EXE, "--roi-selftest", path], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    start, stride, acc, idx = roi_python(m.tolist())
+    runs = [tuple(int(x) for x in ln.split()[1:]) for ln in lines if ln.startswith("run ")]
+    assert runs == list(zip(start, stride, acc))
+    assert lines[0] == "runs %d size %d" % (len(start), acc[-1] if acc else 0)
+    got = {int(ln.split()[1]): int(ln.split()[2]) for ln in lines if ln.startswith("idx ")}
+    assert got == {v: idx(v) for v in range(0, n, 7)}
+    assert int([ln for ln in lines if ln.startswith("bits ")][0].split()[1]) == sum(stride)
+    # the oracle's restatement agrees (it is the checker of the device bitmask in the GPU suite)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    s2, t2, member = O.mask_to_roi(m)
+    assert list(s2) == start and list(t2) == stride
+    exp = np.zeros(n, np.uint8)
+    for s, t in zip(start, stride):
+        exp[s:s + t] = 1
+    assert np.array_equal(member, exp)
