@@ -98,6 +98,9 @@ MQI_API int mqi_device_count(void);
 /* cudaSetDevice(gpu_id): mqi_phantom_env.hpp:45, mqi_tps_env.hpp:163 */
 MQI_API int mqi_create(int device_id, mqi_handle** out);
 MQI_API int mqi_destroy(mqi_handle* h);
+/* free and total bytes of HBM on the handle's device (cudaMemGetInfo); the tps front end sizes the Dij
+ * table from it where the reference hard-codes 512*512*300*5 slots (mqi_tps_env.hpp:922) */
+MQI_API int mqi_device_memory(mqi_handle* h, uint64_t* free_bytes, uint64_t* total_bytes);
 
 /* __PHYSICS_DEBUG__ switch + quirk mask; must be called before mqi_set_grid_* (the calibration LUT
  * depends on it: materials/mqi_patient_materials.hpp:420-424,457-461). */

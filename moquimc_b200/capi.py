@@ -63,6 +63,7 @@ def load():
         "mqi_device_count": [],
         "mqi_create": [i32, C.POINTER(vp)],
         "mqi_destroy": [vp],
+        "mqi_device_memory": [vp, C.POINTER(u64), C.POINTER(u64)],
         "mqi_set_physics": [vp, i32, u32],
         "mqi_set_grid_hu": [vp, fp, i32, fp, i32, fp, i32, vp, f32, fp, fp],
         "mqi_set_grid_hu_device": [vp, fp, i32, fp, i32, fp, i32, vp, f32, fp, fp],
@@ -165,6 +166,12 @@ class Engine:
         if rc < 0:
             raise MqiError(rc, self.L.mqi_last_error().decode())
         return rc
+
+    def device_memory(self):
+        """(free, total) bytes of HBM on the engine's device"""
+        f, t = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.L.mqi_device_memory(self.h, C.byref(f), C.byref(t)))
+        return f.value, t.value
 
     def close(self):
         if self.h:

@@ -468,6 +468,17 @@ mqi_device_count(void) {
 }
 
 int
+mqi_device_memory(mqi_handle* h, uint64_t* free_bytes, uint64_t* total_bytes) {
+    if (!h) return fail(MQI_EINVAL, "handle is null");
+    CU(cudaSetDevice(h->device));
+    size_t f = 0, t = 0;
+    CU(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (uint64_t) f;
+    if (total_bytes) *total_bytes = (uint64_t) t;
+    return MQI_OK;
+}
+
+int
 mqi_create(int device_id, mqi_handle** out) {
     if (!out) return fail(MQI_EINVAL, "out is null");
     *out = nullptr;

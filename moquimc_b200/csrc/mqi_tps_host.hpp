@@ -1114,9 +1114,17 @@ public:
                     add(MQI_SCORER_LETT_DENOM, "LETt_denom", nvox, true);
                 } else if (strcasecmp(s.c_str(), "Dij") == 0) {
                     // the reference hard-codes 512*512*300*5 slots (:922); sized here from the work instead:
-                    // at most one entry per scored step, 4x head room, capped at the reference's size
-                    uint64_t cap = std::min<uint64_t>(393216000ull, std::max<uint64_t>(1u << 20, total_histories * 64ull));
-                    if (dij_capacity > 0) cap = dij_capacity;   // extension: DijCapacity (slots of 16 B); a load below 0.4 runs ~30 % faster
+                    // at most one entry per scored step of this device's share of the histories, bounded below
+                    // and by a quarter of the device's free HBM.  The probe sequence is bound by uncoalesced
+                    // 32-byte sectors, so the load factor is what counts: C4 (2.9e8 entries) runs at 4.7e7
+                    // histories/s in the reference's 393 216 000 slots (load 0.73) and at 6.4e7 in 1.6e9
+                    // slots (26 GB, load 0.18) -- profiles/r1_experiments.md.
+                    uint64_t dev_share = (total_histories + handles.size() - 1) / handles.size();
+                    uint64_t free_b = 0, total_b = 0;
+                    check(mqi_device_memory(h, &free_b, &total_b), "mqi_device_memory");
+                    uint64_t cap = std::max<uint64_t>(1u << 20, std::min<uint64_t>(dev_share * 64ull, free_b / 4 / 16));
+                    if (reference_quirks) cap = std::min<uint64_t>(cap, 393216000ull);
+                    if (dij_capacity > 0) cap = dij_capacity;   // extension: DijCapacity (slots of 16 B)
                     add(MQI_SCORER_DIJ, s, cap | 1ull, true);
                 }   // TrackLength: accepted by the parser, creates no scorer (as in the reference :850-933)
             }

@@ -70,8 +70,14 @@ node_ref(const Params& P, const Smem& sm, int node) {
 // (pre-summed for the mean free path: linear interpolation commutes with the sum), mqi_p_ionization.hpp:
 // 254-268, mqi_pp_elastic.hpp:221-235, mqi_po_elastic.hpp:243-256, mqi_po_inelastic.hpp:141-155.
 // row of the p-ionisation grid (Ei = 0.1, step 0.5): uint16_t((Ek - Ei) / 0.5)
+#if MQI_K_ROWU
+// float -> unsigned conversion saturates negative arguments (and NaN) to 0: one clamp instead of two
+__device__ __forceinline__ int row_a(float ek) { return (int) min(__float2uint_rz((ek - 0.1f) * 2.0f), (unsigned) (kTableN - 1)); }
+__device__ __forceinline__ int row_b(float ek) { return (int) min(__float2uint_rz((ek - 0.5f) * 2.0f), (unsigned) (kTableN - 1)); }
+#else
 __device__ __forceinline__ int row_a(float ek) { return min(max((int) ((ek - 0.1f) * 2.0f), 0), kTableN - 1); }
 __device__ __forceinline__ int row_b(float ek) { return min(max((int) ((ek - 0.5f) * 2.0f), 0), kTableN - 1); }
+#endif
 
 // |dEdx| in water (restricted stopping power), mqi_p_ionization.hpp:271-286
 __device__ __forceinline__ float
@@ -804,7 +810,7 @@ transport_kernel(const __grid_constant__ Params P) {
         // the per-step Philox block {u_mfp, u_a, u_b, u_phi}; consumed (blk advances) only if the step
         // turns out to be a condensed-history step
         uint32_t w[4];
-        philox4x32_10_rk(blk, 0u, h0, h1, P.rk, w);
+        philox4x32_rk<MQI_K_PHILOX_ROUNDS>(blk, 0u, h0, h1, P.rk, w);
         const float u_mfp = u32_to_uniform(w[0]);
         const float u_phi = u32_to_uniform(w[3]);
         float z_loss, z_theta;
@@ -815,8 +821,17 @@ transport_kernel(const __grid_constant__ Params P) {
         const float Et       = ke + kMp;
         const float gamma    = Et * (1.0f / kMp);
         const float gamma_sq = gamma * gamma;
+#if MQI_K_KIN2
+        // beta^2 gamma^2 = gamma^2 - 1 =: x.  One reciprocal of x serves 1 / beta^2 = gamma^2 / x (straggling
+        // variance) and 1 / (P^2 beta^2) = gamma^2 / (Mp x)^2 (Highland angle): two MUFU.RCP per step instead of four
+        const float bg_sq    = gamma_sq - 1.0f;
+        const float inv_bg   = rcp_fast(bg_sq);
+        const float inv_beta_sq = gamma_sq * inv_bg;
+        const float Te_max   = (2.0f * kMe) * bg_sq * rcp_fast(fmaf(2.0f * MeMp, gamma, 1.0f + MeMp * MeMp));
+#else
         const float beta_sq  = 1.0f - 1.0f / gamma_sq;
         const float Te_max   = (2.0f * kMe * beta_sq * gamma_sq) / (1.0f + 2.0f * gamma * MeMp + MeMp * MeMp);
+#endif
         // rows of vtx0.ke: one row of the p-ion grid serves the delta cross section, |dEdx| and the csda
         // range; clamped rows make every lookup safe, out-of-table energies are masked by selects
         const int    ia   = row_a(ke);
@@ -921,15 +936,23 @@ transport_kernel(const __grid_constant__ Params P) {
                     while (n > 0 && r < B.x) B = sm.a1[--n];
                     const float dE_mean = ke - fmaf(r - B.x, B.z, 0.1f + n * 0.5f);
                     const float Te      = fminf(Te_max, 0.08511f);
+#if MQI_K_KIN2
+                    const float var     = P.dedx_term0 * rho * (1.0f / kWaterRho) * liw * (Te * (inv_beta_sq - 0.5f));
+#else
                     const float var     = P.dedx_term0 * rho * (1.0f / kWaterRho) * liw * (Te / beta_sq * (1.0f - 0.5f * beta_sq));
+#endif
                     const float dE      = R0 < liw ? ke : fabsf(fmaf(z_loss, sqrtf(var), dE_mean));
                     float rr = 1.0f;
                     if (dE >= ke) {
                         rr      = ke / dE;
                         stopped = true;
                     }
+#if MQI_K_KIN2
+                    const float th_sq = (13.9f * 13.9f / kMpSq) * inv_beta_sq * inv_bg * len * M.inv_x0;
+#else
                     const float P_sq  = Et * Et - kMpSq;
                     const float th_sq = (13.9f * 13.9f) / (P_sq * beta_sq) * len * M.inv_x0;
+#endif
                     const float th    = fabsf(z_theta) * sqrtf(2.0f * th_sq);
                     rotate_direction(d1x, d1y, d1z, th, kTwoPi * u_phi);
                     res.dE += dE * rr;

@@ -145,3 +145,12 @@ def test_ragged_beamline_node_dij_and_roi_in_a_multi_node_world():
     assert len(got & exp) > 0.93 * max(len(got), len(exp))
     gi, oi = dense.reshape(NZ, NY, NX).sum(axis=(1, 2)), od.reshape(NZ, NY, NX).sum(axis=(1, 2))
     assert abs(M.r80_mm(gi) - M.r80_mm(oi)) < 0.3
+
+
+def test_device_memory_reports_hbm_and_tracks_a_dij_table():
+    e, _ = engine()
+    free0, total = e.device_memory()
+    assert 0 < free0 <= total and total > 100e9          # a B200 carries 180 GB
+    e.add_scorer(capi.SCORER_DIJ, "Dij", 64_000_001)     # 16 B per slot = 1.02 GB
+    free1, _ = e.device_memory()
+    assert 0.9e9 < free0 - free1 < 1.3e9
