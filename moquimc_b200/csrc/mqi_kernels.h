@@ -31,14 +31,8 @@
 #define MQI_K_LATE_LUT 1   /* delay the material LUT load behind the step's random numbers (see mqi_transport.cu) */
 #endif
 
-#ifndef MQI_K_KIN2
-#define MQI_K_KIN2 0       /* step kinematics from one reciprocal of gamma^2 - 1 (see mqi_transport.cu) */
-#endif
-#ifndef MQI_K_ROWU
-#define MQI_K_ROWU 0       /* table rows through the saturating float -> unsigned conversion */
-#endif
 #ifndef MQI_K_PHILOX_ROUNDS
-#define MQI_K_PHILOX_ROUNDS 10   /* rounds of the per-step Philox4x32 block (the oracle uses the same number) */
+#define MQI_K_PHILOX_ROUNDS 7    /* rounds of every Philox4x32 block of the RNG protocol; the oracle uses the same number (MQO_PHILOX_ROUNDS) */
 #endif
 
 namespace mqib

@@ -70,14 +70,9 @@ node_ref(const Params& P, const Smem& sm, int node) {
 // (pre-summed for the mean free path: linear interpolation commutes with the sum), mqi_p_ionization.hpp:
 // 254-268, mqi_pp_elastic.hpp:221-235, mqi_po_elastic.hpp:243-256, mqi_po_inelastic.hpp:141-155.
 // row of the p-ionisation grid (Ei = 0.1, step 0.5): uint16_t((Ek - Ei) / 0.5)
-#if MQI_K_ROWU
 // float -> unsigned conversion saturates negative arguments (and NaN) to 0: one clamp instead of two
 __device__ __forceinline__ int row_a(float ek) { return (int) min(__float2uint_rz((ek - 0.1f) * 2.0f), (unsigned) (kTableN - 1)); }
 __device__ __forceinline__ int row_b(float ek) { return (int) min(__float2uint_rz((ek - 0.5f) * 2.0f), (unsigned) (kTableN - 1)); }
-#else
-__device__ __forceinline__ int row_a(float ek) { return min(max((int) ((ek - 0.1f) * 2.0f), 0), kTableN - 1); }
-__device__ __forceinline__ int row_b(float ek) { return min(max((int) ((ek - 0.5f) * 2.0f), 0), kTableN - 1); }
-#endif
 
 // |dEdx| in water (restricted stopping power), mqi_p_ionization.hpp:271-286
 __device__ __forceinline__ float
@@ -92,7 +87,7 @@ stopping_power(const Smem& sm, float ek) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// RNG plumbing.  Protocol (shared with the oracle): Philox4x32-10, key = seed, counter =
+// RNG plumbing.  Protocol (shared with the oracle): Philox4x32-7, key = seed, counter =
 // (block, 0, history_lo, history_hi); one aligned block {u_mfp, u_a, u_b, u_phi} per physics step,
 // further blocks on demand inside a discrete interaction.  The per-step block is generated inline;
 // every other use goes through one out-of-line copy to keep the hot loop small.
@@ -100,7 +95,7 @@ stopping_power(const Smem& sm, float ek) {
 __device__ __noinline__ uint4
 philox_block(uint32_t blk, uint32_t h0, uint32_t h1, uint32_t k0, uint32_t k1) {
     uint32_t o[4];
-    philox4x32_10(blk, 0u, h0, h1, k0, k1, o);
+    philox4x32<kPhiloxRounds>(blk, 0u, h0, h1, k0, k1, o);
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
@@ -565,7 +560,7 @@ enter_nodes(const Params& P, const Smem& sm, TrackIO& T) {
 // loop goes on), or (b) the secondary on top of its stack, which starts at child 0 again (:160-162).
 template<bool MULTI>
 __device__ __noinline__ bool
-restart_lane(const Params& P, const Secondary* stack, TrackIO& T, int advance) {
+restart_lane(const Params& P, const Secondary* __restrict__ stack, TrackIO& __restrict__ T, int advance) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem sm = smem_view(smem_raw, P.n_edge_floats, P.n_nodes);
     if (MULTI && advance) {
@@ -583,7 +578,7 @@ restart_lane(const Params& P, const Secondary* stack, TrackIO& T, int advance) {
         }
         T.node += 1;   // the caller only advances when a next child exists
     } else {
-        const Secondary& s = stack[--T.sp];
+        const Secondary s = stack[--T.sp];   // by value: the nine loads are issued back to back, then the stores
         T.px = s.px; T.py = s.py; T.pz = s.pz; T.dx = s.dx; T.dy = s.dy; T.dz = s.dz;
         T.ke     = s.ke0;
         T.recoil = s.ke1_off != 0.f;   // pushed as (ke0, -ke0, ke0) by the debug variant only
@@ -788,7 +783,9 @@ transport_kernel(const __grid_constant__ Params P) {
         if (!(fl & FL_ALIVE)) continue;   // taken after the join: the lane idles this turn, the others are converged
 
         // ------------------------------------------------------------------ one voxel step
-        ++n_steps;
+        // the option "count_steps" runs the general kernel: the counter is a spilled register (LDL + IADD + STL
+        // per step) that the single-Dose-scorer kernel does not pay for
+        if (!SIMPLE) ++n_steps;
         const GridDev& G  = node_ref<MULTI>(P, sm, node);
         const int      nx = G.nx, ny = G.ny, nz = G.nz;
         const float*   xe = sm.edges + (MULTI ? G.edge_off : 0);
@@ -810,7 +807,7 @@ transport_kernel(const __grid_constant__ Params P) {
         // the per-step Philox block {u_mfp, u_a, u_b, u_phi}; consumed (blk advances) only if the step
         // turns out to be a condensed-history step
         uint32_t w[4];
-        philox4x32_rk<MQI_K_PHILOX_ROUNDS>(blk, 0u, h0, h1, P.rk, w);
+        philox4x32_rk<kPhiloxRounds>(blk, 0u, h0, h1, P.rk, w);
         const float u_mfp = u32_to_uniform(w[0]);
         const float u_phi = u32_to_uniform(w[3]);
         float z_loss, z_theta;
@@ -821,17 +818,12 @@ transport_kernel(const __grid_constant__ Params P) {
         const float Et       = ke + kMp;
         const float gamma    = Et * (1.0f / kMp);
         const float gamma_sq = gamma * gamma;
-#if MQI_K_KIN2
         // beta^2 gamma^2 = gamma^2 - 1 =: x.  One reciprocal of x serves 1 / beta^2 = gamma^2 / x (straggling
         // variance) and 1 / (P^2 beta^2) = gamma^2 / (Mp x)^2 (Highland angle): two MUFU.RCP per step instead of four
         const float bg_sq    = gamma_sq - 1.0f;
         const float inv_bg   = rcp_fast(bg_sq);
         const float inv_beta_sq = gamma_sq * inv_bg;
         const float Te_max   = (2.0f * kMe) * bg_sq * rcp_fast(fmaf(2.0f * MeMp, gamma, 1.0f + MeMp * MeMp));
-#else
-        const float beta_sq  = 1.0f - 1.0f / gamma_sq;
-        const float Te_max   = (2.0f * kMe * beta_sq * gamma_sq) / (1.0f + 2.0f * gamma * MeMp + MeMp * MeMp);
-#endif
         // rows of vtx0.ke: one row of the p-ion grid serves the delta cross section, |dEdx| and the csda
         // range; clamped rows make every lookup safe, out-of-table energies are masked by selects
         const int    ia   = row_a(ke);
@@ -851,10 +843,13 @@ transport_kernel(const __grid_constant__ Params P) {
         // before the ~100 independent instructions above have been issued.
         const MatEntry M = G.lut[mat_idx + (__float_as_uint(u_mfp) >> 31)];
 #endif
-        float       d1x = dx, d1y = dy, d1z = dz;   // vtx1.dir: copy taken before intersect() zeroes tiny components
-        const float tx = cell_tmax_axis(ex0, ex1, nx, px, dx, ix);
-        const float ty = cell_tmax_axis(ey0, ey1, ny, py, dy, iy);
-        const float tz = cell_tmax_axis(ez0, ez1, nz, pz, dz, iz);
+        // vtx0.dir with its tiny components zeroed in place by intersect() (z*), next to the un-zeroed copy the
+        // reference keeps in vtx1.dir (d1*); the lane's own dx, dy, dz are only read here
+        float       zx = dx, zy = dy, zz = dz;
+        float       d1x = dx, d1y = dy, d1z = dz;
+        const float tx = cell_tmax_axis(ex0, ex1, nx, px, zx, ix);
+        const float ty = cell_tmax_axis(ey0, ey1, ny, py, zy, iy);
+        const float tz = cell_tmax_axis(ez0, ez1, nz, pz, zz, iz);
         const float d2b = min3_ref(tx, ty, tz);
         const float rho = M.rho;
         // intersect() failed (the reference poisons the track and breaks), or a closed aperture voxel
@@ -869,27 +864,33 @@ transport_kernel(const __grid_constant__ Params P) {
         const bool recoil = VARIANT == MQI_K_DEBUG && (fl & FL_RECOIL);
         float ke1 = recoil ? 0.f : ke;    // vtx1.ke
 
-        if (rho < 1.0e-7f) {
-            // vacuum: move to the boundary, nothing to score (mqi_fippel_physics.hpp:77-80)
-            p1x = px + dx * d2b; p1y = py + dy * d2b; p1z = pz + dz * d2b;
-        } else {
-            StepResult res;
-            res.dE = recoil ? ke : 0.f; res.local_dE = 0.f; res.te_debug = 0.f; res.len = 0.f;
-            float rsp0;
-            if (ke <= kTpCut) {
-                // below the tracking cut: dump the energy, :86-94 + last_step mqi_p_ionization.hpp:482-490
-                if (ke < 0.f) ke = 0.f;
-                rsp0 = rsp_eval(M, ke);
-                res.dE += ke;
-                ke1 -= ke;
-                float step_len = 0.f;
-                if (res.dE > 0.f && ke > 0.f) {
-                    const float liw = res.dE / stopping_power(sm, ke);
-                    step_len        = liw * kWaterRho / (rsp0 * rho);
+        StepResult res;
+        res.dE = recoil ? ke : 0.f; res.local_dE = 0.f; res.te_debug = 0.f; res.len = 0.f;
+        float rsp0 = 1.0f;
+        {
+            // the two rare kinds of step (vacuum voxel, track below the cut) share one test in the step body
+            const bool vacuum = rho < 1.0e-7f;
+            if (vacuum | (ke <= kTpCut)) {
+                if (vacuum) {
+                    // vacuum: move to the boundary (mqi_fippel_physics.hpp:77-80); a zero deposit of zero
+                    // length is skipped by every hit function below, like the reference's early return
+                    res.dE = 0.f;
+                    p1x = px + zx * d2b; p1y = py + zy * d2b; p1z = pz + zz * d2b;
+                } else {
+                    // below the tracking cut: dump the energy, :86-94 + last_step mqi_p_ionization.hpp:482-490
+                    if (ke < 0.f) ke = 0.f;
+                    rsp0 = rsp_eval(M, ke);
+                    res.dE += ke;
+                    ke1 -= ke;
+                    float step_len = 0.f;
+                    if (res.dE > 0.f && ke > 0.f) {
+                        const float liw = res.dE / stopping_power(sm, ke);
+                        step_len        = liw * kWaterRho / (rsp0 * rho);
+                    }
+                    p1x = px + zx * step_len; p1y = py + zy * step_len; p1z = pz + zz * step_len;
+                    res.len = step_len;
+                    stopped = true;
                 }
-                p1x = px + dx * step_len; p1y = py + dy * step_len; p1z = pz + dz * step_len;
-                res.len = step_len;
-                stopped = true;
             } else {
                 // ---------------- class-II condensed-history step, fippel_physics::stepping :95-216
                 blk += 1;
@@ -901,8 +902,11 @@ transport_kernel(const __grid_constant__ Params P) {
                 const float4 a2  = sm.a0[i2];
                 const int    j2  = row_b(e2);
                 const float2 b2  = sm.bs[j2];
-                const float cs2_ion = e2 >= 0.1f ? fmaf(e2 - (0.1f + i2 * 0.5f), a2.y, a2.x) : 0.f;
-                const float cs2_sum = cs2_ion + (e2 >= 0.5f ? fmaf(e2 - (0.5f + j2 * 0.5f), b2.y, b2.x) : 0.f);
+                float cs2_ion_v = fmaf(e2 - (0.1f + i2 * 0.5f), a2.y, a2.x);
+                float cs2_nuc_v = fmaf(e2 - (0.5f + j2 * 0.5f), b2.y, b2.x);
+                asm("" : "+f"(cs2_ion_v), "+f"(cs2_nuc_v));   // evaluated by every lane, then selected: no branch around two FFMA
+                const float cs2_ion = e2 >= 0.1f ? cs2_ion_v : 0.f;
+                const float cs2_sum = cs2_ion + (e2 >= 0.5f ? cs2_nuc_v : 0.f);
                 const bool  use1   = cs1_sum >= cs2_sum;
                 const float cs_sum = (use1 ? cs1_sum : cs2_sum) * rho;
                 const float c0     = (use1 ? cs1_ion : cs2_ion) * rho;   // delta-electron channel
@@ -910,8 +914,9 @@ transport_kernel(const __grid_constant__ Params P) {
                 const float mfp = -logf(u_mfp) / cs_sum;
                 constexpr float step_limit = 1.0f;   // cms * rho_w / (rsp * rho): max_step, mqi_fippel_physics.hpp:20
                 const bool  to_boundary = d2b < mfp && d2b < step_limit;
-                const bool  discrete    = !to_boundary && (mfp < d2b || fabsf(mfp - d2b) < kGeomTol) &&
-                                          (mfp < step_limit || fabsf(mfp - step_limit) < kGeomTol);
+                // same decision without short-circuit evaluation (no divergent branch in the step body)
+                const bool  discrete    = !to_boundary & ((mfp < d2b) | (fabsf(mfp - d2b) < kGeomTol)) &
+                                          ((mfp < step_limit) | (fabsf(mfp - step_limit) < kGeomTol));
                 const float len         = to_boundary ? d2b : (discrete ? mfp : step_limit);
                 // ---------------- along step (CSDA + straggling + MCS), mqi_p_ionization.hpp:298-420
                 {
@@ -927,43 +932,41 @@ transport_kernel(const __grid_constant__ Params P) {
                     const int   n0 = min(ia, kTableN - 2);
                     int         n  = min(max((int) ((fmaf(-liw, sp_w, ke) - 0.1f) * 2.0f), 0), n0);
                     float4      B  = sm.a1[n];
-                    while (n < n0) {
-                        const float4 Bn = sm.a1[n + 1];
-                        if (r < Bn.x) break;
-                        B = Bn;
-                        ++n;
+                    // the guess is right for nearly every step: one test (row n holds r, or nothing above /
+                    // below to move to) skips both correction loops
+                    {
+                        const float up = sm.a1[min(n + 1, n0)].x;
+                        if (!((r >= B.x || n == 0) && (r < up || n == n0))) {
+                            while (n < n0) {
+                                const float4 Bn = sm.a1[n + 1];
+                                if (r < Bn.x) break;
+                                B = Bn;
+                                ++n;
+                            }
+                            while (n > 0 && r < B.x) B = sm.a1[--n];
+                        }
                     }
-                    while (n > 0 && r < B.x) B = sm.a1[--n];
                     const float dE_mean = ke - fmaf(r - B.x, B.z, 0.1f + n * 0.5f);
                     const float Te      = fminf(Te_max, 0.08511f);
-#if MQI_K_KIN2
                     const float var     = P.dedx_term0 * rho * (1.0f / kWaterRho) * liw * (Te * (inv_beta_sq - 0.5f));
-#else
-                    const float var     = P.dedx_term0 * rho * (1.0f / kWaterRho) * liw * (Te / beta_sq * (1.0f - 0.5f * beta_sq));
-#endif
                     const float dE      = R0 < liw ? ke : fabsf(fmaf(z_loss, sqrtf(var), dE_mean));
                     float rr = 1.0f;
                     if (dE >= ke) {
                         rr      = ke / dE;
                         stopped = true;
                     }
-#if MQI_K_KIN2
                     const float th_sq = (13.9f * 13.9f / kMpSq) * inv_beta_sq * inv_bg * len * M.inv_x0;
-#else
-                    const float P_sq  = Et * Et - kMpSq;
-                    const float th_sq = (13.9f * 13.9f) / (P_sq * beta_sq) * len * M.inv_x0;
-#endif
                     const float th    = fabsf(z_theta) * sqrtf(2.0f * th_sq);
                     rotate_direction(d1x, d1y, d1z, th, kTwoPi * u_phi);
                     res.dE += dE * rr;
                     const float sl = rr * len;
-                    p1x = fmaf(dx, sl, px); p1y = fmaf(dy, sl, py); p1z = fmaf(dz, sl, pz);
+                    p1x = fmaf(zx, sl, px); p1y = fmaf(zy, sl, py); p1z = fmaf(zz, sl, pz);
                     res.len = sl;
                     ke1 -= dE * rr;
                 }
                 // ---------------- discrete interaction at the end of the step, :156-197
                 if (discrete && ke1 > kTpCut) {
-                    d1x = dx; d1y = dy; d1z = dz;   // vtx1.dir = vtx0.dir (B11)
+                    d1x = zx; d1y = zy; d1z = zz;   // vtx1.dir = vtx0.dir (B11)
                     const float u = cs_sum * u_phi;  // u_phi is unused on this step: selects the process
                     if (u < c0) {
                         // delta electron, p_ionization_tabulated::post_step mqi_p_ionization.hpp:425-477.
@@ -997,7 +1000,7 @@ transport_kernel(const __grid_constant__ Params P) {
                         ke1 -= Te;
                     } else {
                         NucIO io;
-                        io.px = px; io.py = py; io.pz = pz; io.dx = dx; io.dy = dy; io.dz = dz;
+                        io.px = px; io.py = py; io.pz = pz; io.dx = zx; io.dy = zy; io.dz = zz;
                         io.p1x = p1x; io.p1y = p1y; io.p1z = p1z;
                         io.d1x = d1x; io.d1y = d1y; io.d1z = d1z;
                         io.ke1 = ke1; io.dE = res.dE; io.local_dE = res.local_dE;
@@ -1029,7 +1032,7 @@ transport_kernel(const __grid_constant__ Params P) {
                 float       vf    = (res.dE + res.local_dE) * kdose / rsp0;
                 if (VARIANT == MQI_K_DEBUG) vf = fmaf(res.te_debug * kdose, inv_rsp_at_zero_energy(M), vf);
                 const double v    = (double) vf;
-                if (cnb != 0u && v > 0.0) dense_add(P.sc[0].dense, cnb, v, P.accum_mode);
+                if (cnb != 0u && v > 0.0) atomicAdd(P.sc[0].dense + cnb, v);   // warp-match accumulation runs the general kernel
             } else {
                 score_step<VARIANT>(P, M, cnb, spot_ind, inv_vol, rsp0, res);
             }
@@ -1052,7 +1055,7 @@ transport_kernel(const __grid_constant__ Params P) {
     }
 
     // per-lane step counter -> global (one atomic per lane per launch)
-    if (n_steps && P.count_steps) atomicAdd(P.counters + C_STEPS, (unsigned long long) n_steps);
+    if (!SIMPLE && n_steps && P.count_steps) atomicAdd(P.counters + C_STEPS, (unsigned long long) n_steps);
 }
 
 
@@ -1327,7 +1330,8 @@ pick_transport(int variant, bool simple, bool multi) {
 // one dense Dose scorer with a DIRECT roi -> the kernels with the scorer loop compiled out
 bool
 transport_is_simple(const Params& p) {
-    return p.n_scorers == 1 && p.sc[0].kind == MQI_K_DOSE && !p.sc[0].roi && !(p.quirks & MQI_K_QUIRK_B2);
+    return p.n_scorers == 1 && p.sc[0].kind == MQI_K_DOSE && !p.sc[0].roi && !(p.quirks & MQI_K_QUIRK_B2) &&
+           p.accum_mode == MQI_K_ACCUM_ATOMIC && !p.count_steps;
 }
 
 cudaError_t

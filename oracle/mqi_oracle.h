@@ -101,6 +101,8 @@ void     mqo_rotate_direction(const float dir_in[3], float theta, float phi, flo
 void     mqo_physics_probe(float ek, float out[9]);
 
 /* ---- RNG protocol (shared with the CUDA path) ---- */
+#define MQO_PHILOX_ROUNDS 7   /* rounds of every Philox4x32 block of the protocol (== MQI_K_PHILOX_ROUNDS of the kernel) */
+void  mqo_philox4x32_r(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]);
 void  mqo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 float mqo_u32_to_uniform(uint32_t x);
 void  mqo_philox2x32_10(const uint32_t ctr[2], uint32_t key, uint32_t out[2]);

@@ -7,9 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from moquimc_b200 import build as B
 
 VARIANTS = {
-    "v12": (768, 1, 0), "kin2": (768, 1, 0, "-DMQI_K_KIN2=1"), "rowu": (768, 1, 0, "-DMQI_K_ROWU=1"),
-    "ph7": (768, 1, 0, "-DMQI_K_PHILOX_ROUNDS=7"), "kin2_rowu": (768, 1, 0, "-DMQI_K_KIN2=1", "-DMQI_K_ROWU=1"),
-    "all13": (768, 1, 0, "-DMQI_K_KIN2=1", "-DMQI_K_ROWU=1", "-DMQI_K_PHILOX_ROUNDS=7"),
+    "cur": (768, 1, 0), "ph10": (768, 1, 0, "-DMQI_K_PHILOX_ROUNDS=10"),
     "b256": (256, 4, 0), "b512": (512, 2, 0), "b128": (128, 8, 0), "b256_3": (256, 3, 0),
     "early_lut": (256, 4, 0, "-DMQI_K_LATE_LUT=0"), "base": (256, 4, 0),
     "b256_4": (256, 4, 0), "early_lut3": (256, 3, 0, "-DMQI_K_LATE_LUT=0"), "b512_1": (512, 1, 0), "b384_2": (384, 2, 0), "b768_1": (768, 1, 0), "dlcm_cg": (768, 1, 0, "-Xptxas", "-dlcm=cg"), "dlcm_ca": (768, 1, 0, "-Xptxas", "-dlcm=ca"),

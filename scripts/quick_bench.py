@@ -17,7 +17,7 @@ e.set_grid_hu(xe, ye, ze, np.zeros((350, 200, 200), dtype=np.int16))
 e.add_scorer(capi.SCORER_DOSE, "dose")
 e.set_accumulation(accum)
 e.set_beamlets([capi.make_beamlet(energy, [0, 0, 0.5, 0, 0, -1], [spot, spot, 0, 0, 0, 0], uniform=True)], [n * 8])
-e.set_option("count_steps", 1)
+e.set_option("count_steps", int(os.environ.get("MQI_COUNT_STEPS", "0")))   # the counter costs ~2 %
 if os.environ.get("MQI_L2_PERSIST") is not None:
     e.set_option("l2_persist", int(os.environ["MQI_L2_PERSIST"]))
 st = e.run(1, 0, min(n, 200000))

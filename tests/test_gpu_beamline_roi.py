@@ -276,7 +276,7 @@ def test_gpu_roi_against_reference_golden(golden_dir):
     mt = T.G.f4_mask_total()
     _, _, member = O.mask_to_roi(mt)
     m3 = member.reshape(NZ, NY, NX).astype(bool)
-    n = 1_000_000
+    n = 4_000_000
     e = capi.Engine(0, physics=capi.PHYSICS_RELEASE)
     xe, ye, ze = grid_edges()
     e.set_grid_hu(xe, ye, ze, np.zeros((NZ, NY, NX), dtype=np.int16))
@@ -290,5 +290,10 @@ def test_gpu_roi_against_reference_golden(golden_dir):
     assert abs(d.sum() / ref_tot - 1.0) < 3 * float(g["water_dE_total_total_se"]) / ref_tot + 2e-3
     idd = d.sum(axis=(1, 2))
     assert M.gamma_1d(ref_idd, idd, 1.0)[0] >= 0.99
+    # lateral projection on 5x5-rebinned pixels.  The reference run itself (1.2e6 histories) carries 0.9 % noise
+    # per pixel, which is the floor of this comparison whatever n is (scripts/roi_noise_probe.py: rms 0.9-1.0 %,
+    # maximum over the ~100 pixels 1.8-2.6 % for n >= 4e6 with either Philox round count, and 2.1-3.9 % at n = 1e6)
     a, r = T.rebin2(d.sum(axis=0), 5), T.rebin2(ref_xy, 5)
-    assert np.abs(a - r).max() / r.max() < 0.03
+    dev = (a - r) / r.max()
+    assert np.sqrt((dev[r > 0.5 * r.max()] ** 2).mean()) < 0.0125
+    assert np.abs(dev).max() < 0.035
