@@ -12,7 +12,7 @@
  *
  * Every function cites the reference file:line (relative to /root/reference/moqui) it follows.
  * Random numbers: the reference uses std::default_random_engine (CPU) / curand XORWOW (GPU); this
- * restatement uses the counter-based Philox4x32-10 protocol of DESIGN.md ("RNG protocol") so that
+ * restatement uses the counter-based Philox4x32-7 protocol of DESIGN.md ("RNG protocol") so that
  * it can be compared history by history with the CUDA path.
  */
 #ifndef MQI_ORACLE_H
