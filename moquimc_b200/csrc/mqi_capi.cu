@@ -152,6 +152,7 @@ struct mqi_handle {
     uint32_t     quirks   = 0;
     int          accum    = MQI_ACCUM_ATOMIC;
     int          count_steps = 0;
+    int          dij_write_combine = 1;        // option "dij_write_combine": consecutive hits of a lane on one (voxel, spot) key are summed in registers and inserted once
     int          blocks_per_sm_override = 0;
     int          l2_persist = 0;               // option "l2_persist": pin the material volume in L2 with a persisting access window (measured: no gain at C1)
     size_t       l2_persist_max = 0, l2_window_max = 0;
@@ -364,6 +365,10 @@ fill_params(const mqi_handle* h, Params& p) {
     p.quirks      = h->quirks;
     p.accum_mode  = h->accum;
     p.count_steps = h->count_steps;
+    p.dij_wc_scorer = -1;
+    if (h->dij_write_combine)
+        for (int i = 0; i < p.n_scorers; ++i)
+            if (p.sc[i].kind == MQI_SCORER_DIJ) { p.dij_wc_scorer = i; break; }
     p.dedx_term0  = dedx_term0();
     p.tab_a0      = h->d_tab_a0;
     p.tab_a1      = h->d_tab_a1;
@@ -757,6 +762,7 @@ mqi_set_option(mqi_handle* h, const char* key, int64_t value) {
     if (k == "count_steps") h->count_steps = value != 0;
     else if (k == "blocks_per_sm") h->blocks_per_sm_override = (int) value;
     else if (k == "l2_persist") h->l2_persist = value != 0;
+    else if (k == "dij_write_combine") h->dij_write_combine = value != 0;
     else return fail(MQI_EINVAL, "unknown option " + k);
     return MQI_OK;
 }

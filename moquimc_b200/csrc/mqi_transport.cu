@@ -413,10 +413,30 @@ lett_hit(int kind, float dE, float len, float rho) {
 
 // one insert per scorer per step, keyed to the voxel occupied at step start: mqi_transport.hpp:204-225,
 // hit functions scorers/mqi_scorer_energy_deposit.hpp:14-137
+// Write-combining in front of the hash table: a track makes two to three steps inside a CT voxel (the step is
+// limited to 1 mm of water, the voxels are 1.5-2.5 mm), so consecutive hits of a lane mostly carry the same
+// (voxel, spot) key.  The lane sums them in registers and inserts once when the voxel changes or the track ends
+// (flush_dij in the re-arm prologue): the insert -- a dependent chain of uncoalesced L2/DRAM sector accesses --
+// is what bounds the sparse scorer (profiles/r1_experiments.md).  Same keys, same home slots, same sums up to
+// the order of the additions.
+struct DijCombine {
+    uint32_t key;   // voxel of the pending hit, kEmptyKey32 = nothing pending
+    double   val;
+};
+
+__device__ __forceinline__ void
+flush_dij(const Params& P, DijCombine& wc, uint32_t spot_ind) {
+    if (wc.key != kEmptyKey32) {
+        const ScorerDev& S = P.sc[P.dij_wc_scorer];
+        dij_add(S.table, S.capacity, wc.key, spot_ind, wc.val, P.counters);
+        wc.key = kEmptyKey32;
+    }
+}
+
 template<int VARIANT>
 __device__ __forceinline__ void
 score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, float inv_vol, float rsp0,
-           const StepResult& r) {
+           const StepResult& r, DijCombine& wc) {
     // dose_to_water: (dE + local_dE) * 1.60218e-10 / (V * rho * rsp(rho, vtx0.ke))
     const float  kdose   = 1.60218e-10f * inv_vol * M.inv_rho;
     const double dose    = (double) ((r.dE + r.local_dE) * kdose / rsp0);
@@ -438,8 +458,21 @@ score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, 
         if (!(v > 0.0)) continue;   // insert_hashtable: value <= 0 -> skip
         // quirk B2: the reference's non-stat kernel scores scorers [0, n-2) twice when n >= 3
         if ((P.quirks & MQI_K_QUIRK_B2) && s < n - 2) v += v;
-        if (kind == MQI_K_DIJ) dij_add(P.sc[s].table, P.sc[s].capacity, cnb, spot_ind, v, P.counters);
-        else dense_add(P.sc[s].dense, cnb, v, P.accum_mode);
+        if (kind == MQI_K_DIJ) {
+            if (s == P.dij_wc_scorer) {
+                if (wc.key == cnb) {
+                    wc.val += v;
+                } else {
+                    flush_dij(P, wc, spot_ind);
+                    wc.key = cnb;
+                    wc.val = v;
+                }
+            } else {
+                dij_add(P.sc[s].table, P.sc[s].capacity, cnb, spot_ind, v, P.counters);
+            }
+        } else {
+            dense_add(P.sc[s].dense, cnb, v, P.accum_mode);
+        }
     }
 }
 
@@ -716,6 +749,8 @@ transport_kernel(const __grid_constant__ Params P) {
     uint32_t h0 = 0, h1 = 0, blk = 0;   // Philox counter of the current history
     const uint32_t k0 = (uint32_t) P.seed, k1 = (uint32_t) (P.seed >> 32);
     unsigned n_steps = 0;
+    DijCombine wc;   // general kernel only
+    wc.key = kEmptyKey32; wc.val = 0.0;
 
     // the warp's queue of pre-sampled primaries: entries in the queue | history counter exhausted << 16
     // (warp-uniform; one register)
@@ -730,6 +765,7 @@ transport_kernel(const __grid_constant__ Params P) {
         // ------------------------------------------------------------------ restart the lane
         bool need = false;   // the lane needs a new primary
         if (!(fl & (FL_ALIVE | FL_DONE))) {
+            if (!SIMPLE) flush_dij(P, wc, spot_ind);   // the track ended: insert its pending write-combined Dij hit
             if ((MULTI && (fl & FL_ADVANCE)) || sp > 0) {
                 TrackIO T;
                 T.px = px; T.py = py; T.pz = pz; T.dx = dx; T.dy = dy; T.dz = dz; T.ke = ke;
@@ -1034,7 +1070,7 @@ transport_kernel(const __grid_constant__ Params P) {
                 const double v    = (double) vf;
                 if (cnb != 0u && v > 0.0) atomicAdd(P.sc[0].dense + cnb, v);   // warp-match accumulation runs the general kernel
             } else {
-                score_step<VARIANT>(P, M, cnb, spot_ind, inv_vol, rsp0, res);
+                score_step<VARIANT>(P, M, cnb, spot_ind, inv_vol, rsp0, res, wc);
             }
         }
 

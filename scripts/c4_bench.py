@@ -1,4 +1,4 @@
-"""C4 (Dij, 5 000 spots x 1e4 histories, 256 x 256 x 150 CT) throughput probe: python scripts/c4_bench.py [capacity] [spots] [per]"""
+"""C4 (Dij, 5 000 spots x 1e4 histories, 256 x 256 x 150 CT) throughput probe: python scripts/c4_bench.py [capacity] [spots] [per] [write_combine]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -27,8 +27,12 @@ e.set_grid_hu(xe, ye, ze, hu)
 s = e.add_scorer(capi.SCORER_DIJ, "Dij", capacity=cap | 1)
 e.set_beamlets(bl, [per] * len(bl))
 e.set_option("count_steps", 1)
+wc = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+e.set_option("dij_write_combine", wc)
 for rep in range(2):
     e.clear_scorers()
     st = e.run(seed=77, first=0, count=len(bl) * per, per_spot=True)
+    nnz = e.get_sparse_count(s) if hasattr(e, "get_sparse_count") else -1
+    print("write_combine %d nnz %d " % (wc, nnz), end="")
     print("capacity %d: %d histories kernel %.1f ms -> %.3e hist/s, steps/hist %.1f, table full %d"
           % (cap, st.histories, st.kernel_ms, st.histories / (st.kernel_ms * 1e-3), st.steps / st.histories, st.dij_table_full), flush=True)
