@@ -11,7 +11,7 @@ VARIANTS = {
     "b256": (256, 4, 0), "b512": (512, 2, 0), "b128": (128, 8, 0), "b256_3": (256, 3, 0),
     "early_lut": (256, 4, 0, "-DMQI_K_LATE_LUT=0"), "base": (256, 4, 0),
     "b256_4": (256, 4, 0), "early_lut3": (256, 3, 0, "-DMQI_K_LATE_LUT=0"), "b512_1": (512, 1, 0), "b384_2": (384, 2, 0), "b768_1": (768, 1, 0), "dlcm_cg": (768, 1, 0, "-Xptxas", "-dlcm=cg"), "dlcm_ca": (768, 1, 0, "-Xptxas", "-dlcm=ca"),
-    "b640_1": (640, 1, 0), "b896_1": (896, 1, 0),
+    "b640_1": (640, 1, 0), "b896_1": (896, 1, 0), "b1024_1": (1024, 1, 0), "b832_1": (832, 1, 0), "b448_2": (448, 2, 0),
     "b128_5": (128, 5, 0), "b320_2": (320, 2, 0), "b224_3": (224, 3, 0), "b192_3": (192, 3, 0), "b352_2": (352, 2, 0),
 }
 
