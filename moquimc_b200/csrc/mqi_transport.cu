@@ -433,7 +433,7 @@ flush_dij(const Params& P, DijCombine& wc, uint32_t spot_ind) {
     }
 }
 
-template<int VARIANT>
+template<int VARIANT, bool DIJWC>
 __device__ __forceinline__ void
 score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, float inv_vol, float rsp0,
            const StepResult& r, DijCombine& wc) {
@@ -459,7 +459,7 @@ score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, 
         // quirk B2: the reference's non-stat kernel scores scorers [0, n-2) twice when n >= 3
         if ((P.quirks & MQI_K_QUIRK_B2) && s < n - 2) v += v;
         if (kind == MQI_K_DIJ) {
-            if (s == P.dij_wc_scorer) {
+            if (DIJWC && s == P.dij_wc_scorer) {
                 if (wc.key == cnb) {
                     wc.val += v;
                 } else {
@@ -706,7 +706,7 @@ delta_retry(uint32_t blk, uint32_t h0, uint32_t key2, float T_cut, float Tmax1, 
 // scorer loop and the other hit functions are compiled out of the voxel-step loop.
 // MULTI: the world has beamline children (range shifter, aperture) in front of the scored grid; every
 // lane carries the index of the child it is in and reads that child's descriptor from shared memory.
-template<int VARIANT, bool SIMPLE, bool MULTI>
+template<int VARIANT, bool SIMPLE, bool MULTI, bool DIJWC = false>
 __global__ void __launch_bounds__(MQI_K_BLOCK, MQI_K_MIN_BLOCKS)
 transport_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -749,7 +749,7 @@ transport_kernel(const __grid_constant__ Params P) {
     uint32_t h0 = 0, h1 = 0, blk = 0;   // Philox counter of the current history
     const uint32_t k0 = (uint32_t) P.seed, k1 = (uint32_t) (P.seed >> 32);
     unsigned n_steps = 0;
-    DijCombine wc;   // general kernel only
+    DijCombine wc;   // DIJWC instantiations only (a Dij scorer with write-combining): costs three registers
     wc.key = kEmptyKey32; wc.val = 0.0;
 
     // the warp's queue of pre-sampled primaries: entries in the queue | history counter exhausted << 16
@@ -765,7 +765,7 @@ transport_kernel(const __grid_constant__ Params P) {
         // ------------------------------------------------------------------ restart the lane
         bool need = false;   // the lane needs a new primary
         if (!(fl & (FL_ALIVE | FL_DONE))) {
-            if (!SIMPLE) flush_dij(P, wc, spot_ind);   // the track ended: insert its pending write-combined Dij hit
+            if (DIJWC) flush_dij(P, wc, spot_ind);   // the track ended: insert its pending write-combined Dij hit
             if ((MULTI && (fl & FL_ADVANCE)) || sp > 0) {
                 TrackIO T;
                 T.px = px; T.py = py; T.pz = pz; T.dx = dx; T.dy = dy; T.dz = dz; T.ke = ke;
@@ -1070,7 +1070,7 @@ transport_kernel(const __grid_constant__ Params P) {
                 const double v    = (double) vf;
                 if (cnb != 0u && v > 0.0) atomicAdd(P.sc[0].dense + cnb, v);   // warp-match accumulation runs the general kernel
             } else {
-                score_step<VARIANT>(P, M, cnb, spot_ind, inv_vol, rsp0, res, wc);
+                score_step<VARIANT, DIJWC>(P, M, cnb, spot_ind, inv_vol, rsp0, res, wc);
             }
         }
 
@@ -1355,12 +1355,16 @@ transport_smem_bytes(int n_edge_floats, int n_nodes) {
 }
 
 typedef void (*transport_fn)(const Params);
+template<bool SIMPLE, bool MULTI, bool DIJWC>
 static transport_fn
-pick_transport(int variant, bool simple, bool multi) {
-    if (multi && simple) return variant == MQI_K_DEBUG ? transport_kernel<MQI_K_DEBUG, true, true> : transport_kernel<MQI_K_RELEASE, true, true>;
-    if (multi) return variant == MQI_K_DEBUG ? transport_kernel<MQI_K_DEBUG, false, true> : transport_kernel<MQI_K_RELEASE, false, true>;
-    if (variant == MQI_K_DEBUG) return simple ? transport_kernel<MQI_K_DEBUG, true, false> : transport_kernel<MQI_K_DEBUG, false, false>;
-    return simple ? transport_kernel<MQI_K_RELEASE, true, false> : transport_kernel<MQI_K_RELEASE, false, false>;
+pick_variant(int variant) {
+    return variant == MQI_K_DEBUG ? transport_kernel<MQI_K_DEBUG, SIMPLE, MULTI, DIJWC> : transport_kernel<MQI_K_RELEASE, SIMPLE, MULTI, DIJWC>;
+}
+static transport_fn
+pick_transport(int variant, bool simple, bool multi, bool dijwc) {
+    if (simple) return multi ? pick_variant<true, true, false>(variant) : pick_variant<true, false, false>(variant);
+    if (dijwc) return multi ? pick_variant<false, true, true>(variant) : pick_variant<false, false, true>(variant);
+    return multi ? pick_variant<false, true, false>(variant) : pick_variant<false, false, false>(variant);
 }
 
 // one dense Dose scorer with a DIRECT roi -> the kernels with the scorer loop compiled out
@@ -1372,7 +1376,7 @@ transport_is_simple(const Params& p) {
 
 cudaError_t
 transport_occupancy(const Params& p, int variant, size_t smem, int* blocks_per_sm) {
-    transport_fn f = pick_transport(variant, transport_is_simple(p), p.n_nodes > 1);
+    transport_fn f = pick_transport(variant, transport_is_simple(p), p.n_nodes > 1, p.dij_wc_scorer >= 0);
     cudaError_t  e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, f, MQI_K_BLOCK, smem);
@@ -1380,7 +1384,7 @@ transport_occupancy(const Params& p, int variant, size_t smem, int* blocks_per_s
 
 cudaError_t
 launch_transport(const Params& p, int variant, int grid, size_t smem, cudaStream_t st) {
-    pick_transport(variant, transport_is_simple(p), p.n_nodes > 1)<<<grid, MQI_K_BLOCK, smem, st>>>(p);
+    pick_transport(variant, transport_is_simple(p), p.n_nodes > 1, p.dij_wc_scorer >= 0)<<<grid, MQI_K_BLOCK, smem, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -17,7 +17,7 @@ if nodes >= 2:
     e.add_beamline_node(axe, axe, aze, np.broadcast_to(np.where(op, np.float32(1e-8), np.float32(100.0)), (20, 80, 80)).astype(np.float32).copy())
 e.add_scorer(capi.SCORER_DOSE, "Dose")
 e.set_beamlets([capi.make_beamlet(180.0, [0, 0, 180.0, 0, 0, -1], [15, 15, 0, 0, 0, 0], uniform=True)], [n * 4])
-e.set_option("count_steps", 1)
+e.set_option("count_steps", int(os.environ.get("MQI_COUNT_STEPS", "0")))   # counting runs the general kernel
 for i in range(3):
     st = e.run(1, i * n, n)
     print("nodes %d: %d histories kernel %.2f ms -> %.3e hist/s, steps/hist %.1f" % (nodes, st.histories, st.kernel_ms, st.histories / (st.kernel_ms * 1e-3), st.steps / st.histories), flush=True)
