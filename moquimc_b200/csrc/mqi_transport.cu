@@ -1067,8 +1067,10 @@ transport_kernel(const __grid_constant__ Params P) {
                 const float kdose = 1.60218e-10f * inv_vol * M.inv_rho;
                 float       vf    = (res.dE + res.local_dE) * kdose / rsp0;
                 if (VARIANT == MQI_K_DEBUG) vf = fmaf(res.te_debug * kdose, inv_rsp_at_zero_energy(M), vf);
-                const double v    = (double) vf;
-                if (cnb != 0u && v > 0.0) atomicAdd(P.sc[0].dense + cnb, v);   // warp-match accumulation runs the general kernel
+                // cvt.f64.f32 directly: under -ftz the compiler first flushes a denormal deposit with a multiply by one
+                double v;
+                asm("cvt.f64.f32 %0, %1;" : "=d"(v) : "f"(vf));
+                if (cnb != 0u && vf > 0.f) atomicAdd(P.sc[0].dense + cnb, v);   // warp-match accumulation runs the general kernel
             } else {
                 score_step<VARIANT, DIJWC>(P, M, cnb, spot_ind, inv_vol, rsp0, res, wc);
             }
