@@ -699,6 +699,22 @@ delta_retry(uint32_t blk, uint32_t h0, uint32_t key2, float T_cut, float Tmax1, 
     }
 }
 
+// do { if (r >= r_steps[n]) break; } while (--n > 0) of the reference's range-table inversion (mqi_p_ionization.hpp:
+// 298-420), started from a guessed row: the largest row n <= n0 whose range does not exceed r.  Out of line: the
+// guess is right for nearly every step.
+__device__ __noinline__ int
+csda_row_fix(const float4* a1, int n, int n0, float r) {
+    float bx = a1[n].x;
+    while (n < n0) {
+        const float nx = a1[n + 1].x;
+        if (r < nx) break;
+        bx = nx;
+        ++n;
+    }
+    while (n > 0 && r < bx) bx = a1[--n].x;
+    return n;
+}
+
 // ---------------------------------------------------------------------------------------------
 // the transport kernel
 // ---------------------------------------------------------------------------------------------
@@ -974,17 +990,12 @@ transport_kernel(const __grid_constant__ Params P) {
                     int         n  = min(max((int) ((fmaf(-liw, sp_w, ke) - 0.1f) * 2.0f), 0), n0);
                     float4      B  = sm.a1[n];
                     // the guess is right for nearly every step: one test (row n holds r, or nothing above /
-                    // below to move to) skips both correction loops
+                    // below to move to); the correction loops are out of line
                     {
                         const float up = sm.a1[min(n + 1, n0)].x;
-                        if (!((r >= B.x || n == 0) && (r < up || n == n0))) {
-                            while (n < n0) {
-                                const float4 Bn = sm.a1[n + 1];
-                                if (r < Bn.x) break;
-                                B = Bn;
-                                ++n;
-                            }
-                            while (n > 0 && r < B.x) B = sm.a1[--n];
+                        if (!(((r >= B.x) | (n == 0)) & ((r < up) | (n == n0)))) {
+                            n = csda_row_fix(sm.a1, n, n0, r);
+                            B = sm.a1[n];
                         }
                     }
                     const float dE_mean = ke - fmaf(r - B.x, B.z, 0.1f + n * 0.5f);

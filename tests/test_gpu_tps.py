@@ -58,7 +58,11 @@ def engine_for(root, src, scorers, per_spot=False, seed=12345, capacity=0):
 
 @pytest.fixture(scope="module")
 def root(tmp_path_factory):
-    return str(tmp_path_factory.mktemp("tpsgpu"))
+    """the synthetic case (ct.mha, machine.txt, plan.txt) every test of this module reads: written here, so that any
+    test can run on its own (-k)"""
+    r = str(tmp_path_factory.mktemp("tpsgpu"))
+    S.make_case(r, n=N, spacing=SP, ParticlesPerHistory=2000.0, OutputDir=os.path.join(r, "o_dose"))
+    return r
 
 
 def test_per_beam_dose_files_and_scaling(root):
