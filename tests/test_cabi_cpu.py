@@ -46,3 +46,13 @@ def test_product_does_not_reference_the_oracle():
                 text = open(os.path.join(dp, f), errors="ignore").read()
                 assert "mqi_oracle" not in text and "oracle_lib" not in text, os.path.join(dp, f)
                 assert "libmqi_oracle" not in text
+
+
+def test_kernel_and_oracle_share_the_philox_round_count():
+    """The RNG protocol is one constant in two places: the kernel's MQI_K_PHILOX_ROUNDS and the
+    oracle's MQO_PHILOX_ROUNDS.  Identical-stream parity tests only mean something while they agree."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    k = re.search(r"#define\s+MQI_K_PHILOX_ROUNDS\s+(\d+)", open(os.path.join(root, "moquimc_b200", "csrc", "mqi_kernels.h")).read())
+    o = re.search(r"#define\s+MQO_PHILOX_ROUNDS\s+(\d+)", open(os.path.join(root, "oracle", "mqi_oracle.h")).read())
+    assert k and o and int(k.group(1)) == int(o.group(1)) == 7
