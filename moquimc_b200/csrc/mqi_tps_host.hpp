@@ -1119,7 +1119,7 @@ public:
                     // 32-byte sectors, so the load factor is what counts: C4 (2.9e8 entries) runs at 4.7e7
                     // histories/s in the reference's 393 216 000 slots (load 0.73) and at 6.4e7 in 1.6e9
                     // slots (26 GB, load 0.18) -- profiles/r1_experiments.md.
-                    uint64_t dev_share = (total_histories + handles.size() - 1) / handles.size();
+                    uint64_t dev_share = (total_histories + gpu_ids.size() - 1) / gpu_ids.size();
                     uint64_t free_b = 0, total_b = 0;
                     check(mqi_device_memory(h, &free_b, &total_b), "mqi_device_memory");
                     uint64_t cap = std::max<uint64_t>(1u << 20, std::min<uint64_t>(dev_share * 64ull, free_b / 4 / 16));
