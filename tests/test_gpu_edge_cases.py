@@ -156,3 +156,33 @@ def test_device_memory_reports_hbm_and_tracks_a_dij_table():
     e.run(seed=1, first=0, count=64, per_spot=True)
     free1, _ = e.device_memory()
     assert free0 - free1 > 1.0e9
+
+
+def test_dij_write_combining_changes_nothing_but_the_number_of_inserts():
+    """Per-lane write-combining in front of the hash table (option dij_write_combine): same (voxel, spot) key set,
+    same sums up to the order of the additions, with a second Dij scorer (inserted directly) and a dense Dose scorer
+    alongside; rows still add up to the dense dose."""
+    def run(wc):
+        e, ids = engine(kinds=(capi.SCORER_DIJ, capi.SCORER_DOSE, capi.SCORER_DIJ), capacity=1_000_003)
+        e.set_option("dij_write_combine", wc)
+        bl = [capi.make_beamlet(90.0 + 15.0 * i, [-12.0 + 8.0 * i, 3.0, 0.5, 0, 0, -1], [3, 3, 0, 0.002, 0.002, 0], uniform=False)
+              for i in range(4)]
+        e.set_beamlets(bl, [3000] * 4)
+        st = e.run(seed=5, first=0, count=12000, per_spot=True)
+        assert st.histories == 12000 and st.dij_table_full == 0
+        out = []
+        for s in (ids[0], ids[2]):
+            k1, k2, v = e.get_sparse(s)
+            out.append({(int(a), int(b)): c for a, b, c in zip(k1, k2, v)})
+        return out, e.get_dense(ids[1]).ravel()
+    (a0, a2), dense_a = run(1)
+    (b0, b2), dense_b = run(0)
+    assert a0.keys() == b0.keys() == a2.keys() == b2.keys() and len(a0) > 10000
+    kk = sorted(a0)
+    ref = np.array([b0[k] for k in kk])
+    for got in (a0, a2, b2):
+        np.testing.assert_allclose(np.array([got[k] for k in kk]), ref, rtol=1e-9)
+    np.testing.assert_allclose(dense_a, dense_b, rtol=1e-9, atol=1e-22)
+    acc = np.zeros(dense_a.size)
+    np.add.at(acc, np.array([k[0] for k in kk]), np.array([a0[k] for k in kk]))
+    np.testing.assert_allclose(acc, dense_a, rtol=1e-9, atol=dense_a.max() * 1e-13)
