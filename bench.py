@@ -218,17 +218,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_issue(histories_per_launch, kernel_ms, sm_mhz):
+def ncu_issue(histories_per_launch, kernel_ms, sm_mhz, sm_count=148):
     """Issue-slot utilisation of the transport kernel, the bound that actually holds: warp
     instructions per launch from the committed ncu capture (smsp__inst_executed.sum at this launch size) over
-    the live kernel time, against 148 SMs x 4 schedulers x the SM clock sampled during the timed region."""
+    the live kernel time, against SMs x 4 schedulers x the SM clock sampled during the timed region."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
         d = json.load(open(p))
         if int(d["histories_per_launch"]) != int(histories_per_launch) or not sm_mhz:
             return None
         achieved = float(d["warp_instructions_per_launch"]) / (kernel_ms * 1e-3)
-        peak = 148 * 4 * float(sm_mhz) * 1e6
+        peak = int(sm_count) * 4 * float(sm_mhz) * 1e6
         return {"achieved_warp_inst_per_s": achieved, "peak_warp_inst_per_s": peak, "frac": achieved / peak,
                 "source": "smsp__inst_executed.sum of profiles/roofline_traffic.json over the live kernel time"}
     except Exception:
@@ -415,7 +415,8 @@ def bench_b200(args):
                          "traffic": ncu_traffic(H), "peak_source": peak_src, "kernel": "transport_kernel<debug>",
                          "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "latency/issue bound, not HBM bound: the dose grid hot set stays in L2 (see DESIGN.md)",
-                         "issue_slots": ncu_issue(H, k_ms, (clocks or {}).get("sm_mhz"))},
+                         "issue_slots": ncu_issue(H, k_ms, (clocks or {}).get("sm_mhz"),
+                                                  torch.cuda.get_device_properties(dev).multi_processor_count)},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
