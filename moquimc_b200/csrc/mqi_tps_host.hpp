@@ -846,6 +846,11 @@ public:
                 throw std::runtime_error("If no contour or mask is selected, the statical threshold cannot be zero");
             printf("If statistical threshold is zero, the uncertainty might be biased\n");
         }
+        // accepted and without effect here: TotalThreads sizes the reference's launch (<<<threads/512, 512>>>, :1107);
+        // this path launches one persistent CTA per SM whatever the history count.  ScoreToCTGrid is forced to
+        // true by the reference itself (:243).
+        (void) parser.get_int("TotalThreads", -1);
+        (void) parser.get_bool("ScoreToCTGrid", true);
         reference_quirks = parser.get_bool("ReferenceQuirks", false);
         max_stat_passes  = parser.get_int("MaxStatPasses", 1000);
         dij_capacity     = (uint64_t) std::strtoull(parser.get_string("DijCapacity", "0").c_str(), nullptr, 10);
