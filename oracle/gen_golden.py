@@ -52,6 +52,21 @@ def c2(energy, procs=8, per_proc=125000):
     print("c2", energy, {k: getattr(v, "shape", None) for k, v in keep.items()})
 
 
+def c2_edep(energy=150, procs=8, per_proc=50000):
+    """The C2 slab phantom with the EnergyDeposition scorer alone (scorers/mqi_scorer_energy_deposit.hpp:14-22: dE +
+    local dE in MeV per step, no division by the voxel mass) through oracle/ref_harness.cpp --scorers edep."""
+    import argparse
+    sys.path.insert(0, HERE)
+    import ref_run
+    a = argparse.Namespace(variant="release", procs=procs, histories_per_proc=per_proc, energy=float(energy), spot_size=10.0,
+                           nxyz=[200, 200, 350], lxyz=[100.0, 100.0, 350.0], slab=[[50.0, 70.0, 1000.0], [70.0, 100.0, -741.0]],
+                           seed=777, rebin=8, harness=True, scorers="edep", gauss=None, out=None)
+    res, meta = ref_run.run(a)
+    keep = {k: v for k, v in res.items() if k == "meta" or k.endswith(("_idd", "_idd_se", "_total", "_total_se"))}
+    np.savez_compressed(os.path.join(GOLD, "c2_slabs%d_edep_release.npz" % int(energy)), **keep)
+    print("c2_edep", energy, {k: getattr(v, "shape", None) for k, v in keep.items()})
+
+
 F3_GRID = dict(nxyz=[100, 100, 200], lxyz=[100.0, 100.0, 200.0])
 F3_RS = [100.0, 140.0, 150.0, 1.19]          # zlo zhi half-width density[g/cm3]
 F3_AP = [40.0, 60.0, 40.0, 12.0, 8.0]        # zlo zhi half-width open_hx open_hy
@@ -118,6 +133,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "f4":
         f4_roi()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "c2_edep":
+        c2_edep()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "c2":
         for e in (70, 150, 230):

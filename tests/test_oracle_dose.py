@@ -59,3 +59,27 @@ def test_oracle_slab_transport_and_letd_match_reference_golden(golden_dir):
     m = r10(gd) > 0.2 * r10(gd).max()
     assert np.abs((r10(ni)[m] / r10(di)[m]) / (r10(gn)[m] / r10(gd)[m]) - 1.0).max() < 0.04
     assert abs(di.sum() / float(gold["LETd_denom_total"]) - 1.0) < 5e-3
+
+
+def test_oracle_energy_deposition_matches_reference_golden(golden_dir):
+    """EnergyDeposition scorer (scorers/mqi_scorer_energy_deposit.hpp:14-22) on the C2 slab phantom at 150 MeV, release
+    physics: restatement vs the reference's own CPU run through oracle/ref_harness.cpp --scorers edep
+    (tests/golden/c2_slabs150_edep_release.npz, generator oracle/gen_golden.py c2_edep).  MeV per primary history."""
+    gold = np.load(os.path.join(golden_dir, "c2_slabs150_edep_release.npz"))
+    xe, ye, ze = O.uniform_edges(-50, 50, 200), O.uniform_edges(-50, 50, 200), O.uniform_edges(-350, 0, 350)
+    hu = np.zeros((350, 200, 200), dtype=np.int64)
+    hu[350 - 70:350 - 50] = 1000
+    hu[350 - 100:350 - 70] = -741
+    rho = O.hu_to_density(np.arange(-1000, 2996))[hu.ravel() + 1000].astype(np.float32)
+    g, keep = O.make_grid(xe, ye, ze, rho)
+    b = O.make_beamlet(150.0, [0, 0, 0.5, 0, 0, -1], [10, 10, 0, 0, 0, 0], uniform=True)
+    n = 20000
+    (e,), st = O.transport(g, O.VARIANT_RELEASE, [b], [n], seed=21, h0=0, n=n, kinds=[O.SCORER_EDEP])
+    idd = e.reshape(350, -1).sum(axis=1) / n
+    ref_idd, ref_tot = gold["Edep_idd"], float(gold["Edep_total"])
+    # 143.9 of the 150 MeV are deposited locally (the rest leaves with nuclear secondaries that are not tracked)
+    assert 140.0 < ref_tot < 148.0
+    assert abs(idd.sum() / ref_tot - 1.0) < 3e-3
+    assert abs(M.r80_mm(idd) - M.r80_mm(ref_idd)) < 0.15
+    rate, _, _ = M.gamma_1d(ref_idd, idd, 1.0)
+    assert rate >= 0.99
