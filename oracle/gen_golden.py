@@ -52,6 +52,25 @@ def c2(energy, procs=8, per_proc=125000):
     print("c2", energy, {k: getattr(v, "shape", None) for k, v in keep.items()})
 
 
+def c2_scorers(energy, scorers, tag, procs=8, per_proc=50000, seed=777):
+    import argparse
+    sys.path.insert(0, HERE)
+    import ref_run
+    a = argparse.Namespace(variant="release", procs=procs, histories_per_proc=per_proc, energy=float(energy), spot_size=10.0,
+                           nxyz=[200, 200, 350], lxyz=[100.0, 100.0, 350.0], slab=[[50.0, 70.0, 1000.0], [70.0, 100.0, -741.0]],
+                           seed=seed, rebin=8, harness=True, scorers=scorers, gauss=None, out=None)
+    res, meta = ref_run.run(a)
+    keep = {k: v for k, v in res.items() if k == "meta" or k.endswith(("_idd", "_idd_se", "_total", "_total_se"))}
+    np.savez_compressed(os.path.join(GOLD, "c2_slabs%d_%s_release.npz" % (int(energy), tag)), **keep)
+    print("c2", scorers, energy, {k: getattr(v, "shape", None) for k, v in keep.items()})
+
+
+def c2_lett(energy=150):
+    """The C2 slab phantom with the track-averaged LET scorers (scorers/mqi_scorer_energy_deposit.hpp:141-177:
+    numerator = step length x LET, denominator = step length) through oracle/ref_harness.cpp --scorers lett."""
+    c2_scorers(energy, "lett", "lett", seed=778)
+
+
 def c2_edep(energy=150, procs=8, per_proc=50000):
     """The C2 slab phantom with the EnergyDeposition scorer alone (scorers/mqi_scorer_energy_deposit.hpp:14-22: dE +
     local dE in MeV per step, no division by the voxel mass) through oracle/ref_harness.cpp --scorers edep."""
@@ -133,6 +152,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "f4":
         f4_roi()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "c2_lett":
+        c2_lett()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "c2_edep":
         c2_edep()

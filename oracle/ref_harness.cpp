@@ -4,7 +4,7 @@
 // calls mc::transport_particles_patient directly with a scorer_offset_vector, exactly as
 // mqi_tps_env.hpp:1119-1135 does.  Test infrastructure only (oracle/_ref/ref_harness_*).
 //
-//   ref_harness <phantom_env flags...> --scorers dose|edep|letd|dose+letd|dij [--nspots N] [--spot_pitch mm]
+//   ref_harness <phantom_env flags...> --scorers dose|edep|letd|lett|dose+letd|dij [--nspots N] [--spot_pitch mm]
 //               [--gauss sx sy sxp syp sigmaE]
 //               [--rangeshifter zlo zhi half density_g_cm3]      one-voxel slab, create_rangeshifter style
 //               [--aperture zlo zhi half open_hx open_hy]        1 mm voxels, 1e-8 open / 100 closed
@@ -141,6 +141,9 @@ public:
         } else if (opt.scorers == "letd") {
             v.push_back(make_scorer("LETd_numer", nvox, mqi::LETd_weight1<R>, nvox));
             v.push_back(make_scorer("LETd_denom", nvox, mqi::LETd_weight2<R>, nvox));
+        } else if (opt.scorers == "lett") {   // track-averaged LET, scorers/mqi_scorer_energy_deposit.hpp:141-177
+            v.push_back(make_scorer("LETt_numer", nvox, mqi::LETt_weight1<R>, nvox));
+            v.push_back(make_scorer("LETt_denom", nvox, mqi::LETt_weight2<R>, nvox));
         } else if (opt.scorers == "dose+letd") {   // 3 scorers: exercises the double-scoring quirk
             v.push_back(make_scorer("Dose", nvox, mqi::dose_to_water<R>, nvox));
             v.push_back(make_scorer("LETd_numer", nvox, mqi::LETd_weight1<R>, nvox));

@@ -83,3 +83,29 @@ def test_oracle_energy_deposition_matches_reference_golden(golden_dir):
     assert abs(M.r80_mm(idd) - M.r80_mm(ref_idd)) < 0.15
     rate, _, _ = M.gamma_1d(ref_idd, idd, 1.0)
     assert rate >= 0.99
+
+
+def test_oracle_track_averaged_let_matches_reference_golden(golden_dir):
+    """LETt numerator / denominator (scorers/mqi_scorer_energy_deposit.hpp:141-177: step length x LET and step length) on
+    the C2 slab phantom at 150 MeV: restatement vs the reference's own CPU run through oracle/ref_harness.cpp
+    --scorers lett (tests/golden/c2_slabs150_lett_release.npz, generator oracle/gen_golden.py c2_lett)."""
+    gold = np.load(os.path.join(golden_dir, "c2_slabs150_lett_release.npz"))
+    xe, ye, ze = O.uniform_edges(-50, 50, 200), O.uniform_edges(-50, 50, 200), O.uniform_edges(-350, 0, 350)
+    hu = np.zeros((350, 200, 200), dtype=np.int64)
+    hu[350 - 70:350 - 50] = 1000
+    hu[350 - 100:350 - 70] = -741
+    rho = O.hu_to_density(np.arange(-1000, 2996))[hu.ravel() + 1000].astype(np.float32)
+    g, keep = O.make_grid(xe, ye, ze, rho)
+    b = O.make_beamlet(150.0, [0, 0, 0.5, 0, 0, -1], [10, 10, 0, 0, 0, 0], uniform=True)
+    n = 20000
+    (num, den), st = O.transport(g, O.VARIANT_RELEASE, [b], [n], seed=22, h0=0, n=n, kinds=[O.SCORER_LETT_NUMER, O.SCORER_LETT_DENOM])
+    ni, di = num.reshape(350, -1).sum(axis=1) / n, den.reshape(350, -1).sum(axis=1) / n
+    gn, gd = gold["LETt_numer_idd"], gold["LETt_denom_idd"]
+    # total track length and total length-weighted LET per primary history
+    assert abs(di.sum() / float(gold["LETt_denom_total"]) - 1.0) < 3e-3
+    assert abs(ni.sum() / float(gold["LETt_numer_total"]) - 1.0) < 5e-3
+    # the track length per depth bin falls off at the end of range like the fluence: same R80 of the length profile
+    assert abs(M.r80_mm(di) - M.r80_mm(gd)) < 0.2
+    r10 = lambda a: a.reshape(35, 10).sum(axis=1)   # noqa: E731
+    m = r10(gd) > 0.2 * r10(gd).max()
+    assert np.abs((r10(ni)[m] / r10(di)[m]) / (r10(gn)[m] / r10(gd)[m]) - 1.0).max() < 0.03
