@@ -65,6 +65,24 @@ def c2_scorers(energy, scorers, tag, procs=8, per_proc=50000, seed=777):
     print("c2", scorers, energy, {k: getattr(v, "shape", None) for k, v in keep.items()})
 
 
+G1_GAUSS = [4.0, 3.0, 0.004, 0.003, 1.5]     # sigma x, y [mm], x', y' [rad], energy [MeV]: the pbs beamlet of configs 3-5
+
+
+def g1_gauss(procs=8, per_proc=50000):
+    """A gaussian pencil beam (phsp_6d + norm_1d, the beamlet treatment_machine_pbs builds per spot) of 150 MeV into
+    the C1 water phantom through oracle/ref_harness.cpp --gauss: pins the source sampling at transport level."""
+    import argparse
+    sys.path.insert(0, HERE)
+    import ref_run
+    a = argparse.Namespace(variant="release", procs=procs, histories_per_proc=per_proc, energy=150.0, spot_size=0.0,
+                           nxyz=[200, 200, 350], lxyz=[100.0, 100.0, 350.0], slab=[], seed=4711, rebin=8, harness=True,
+                           scorers="dose", gauss=G1_GAUSS, out=None)
+    res, meta = ref_run.run(a)
+    keep = {k: v for k, v in res.items() if k == "meta" or k.endswith(("_idd", "_idd_se", "_total", "_total_se", "_xz", "_yz"))}
+    np.savez_compressed(os.path.join(GOLD, "g1_gauss150_release.npz"), **keep)
+    print("g1", {k: getattr(v, "shape", None) for k, v in keep.items()})
+
+
 def c2_lett(energy=150):
     """The C2 slab phantom with the track-averaged LET scorers (scorers/mqi_scorer_energy_deposit.hpp:141-177:
     numerator = step length x LET, denominator = step length) through oracle/ref_harness.cpp --scorers lett."""
@@ -152,6 +170,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "f4":
         f4_roi()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "g1":
+        g1_gauss()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "c2_lett":
         c2_lett()
