@@ -33,17 +33,18 @@ def test_oracle_transport_matches_reference_golden_dose(golden_dir, name, varian
     assert d.ravel()[0] == 0.0   # voxel 0 is never scored (B1)
 
 
-def test_oracle_slab_transport_and_letd_match_reference_golden(golden_dir):
-    """Config C2 at 150 MeV (bone / lung slabs, release physics, Dose + LETd with the reference's double scoring
-    of Dose, quirk B2): restatement vs the reference's own CPU run (tests/golden/c2_slabs150_release.npz)."""
-    gold = np.load(os.path.join(golden_dir, "c2_slabs150_release.npz"))
+@pytest.mark.parametrize("energy", [70, 150, 230])
+def test_oracle_slab_transport_and_letd_match_reference_golden(golden_dir, energy):
+    """Config C2 at 70 / 150 / 230 MeV (bone / lung slabs, release physics, Dose + LETd with the reference's double
+    scoring of Dose, quirk B2): restatement vs the reference's own CPU run (tests/golden/c2_slabs<E>_release.npz)."""
+    gold = np.load(os.path.join(golden_dir, "c2_slabs%d_release.npz" % energy))
     xe, ye, ze = O.uniform_edges(-50, 50, 200), O.uniform_edges(-50, 50, 200), O.uniform_edges(-350, 0, 350)
     hu = np.zeros((350, 200, 200), dtype=np.int64)
     hu[350 - 70:350 - 50] = 1000
     hu[350 - 100:350 - 70] = -741
     rho = O.hu_to_density(np.arange(-1000, 2996))[hu.ravel() + 1000].astype(np.float32)
     g, keep = O.make_grid(xe, ye, ze, rho)
-    b = O.make_beamlet(150.0, [0, 0, 0.5, 0, 0, -1], [10, 10, 0, 0, 0, 0], uniform=True)
+    b = O.make_beamlet(float(energy), [0, 0, 0.5, 0, 0, -1], [10, 10, 0, 0, 0, 0], uniform=True)
     n = 20000
     (d, num, den), st = O.transport(g, O.VARIANT_RELEASE, [b], [n], seed=8, h0=0, n=n, quirks=O.QUIRK_B2_DOUBLE_SCORE,
                                     kinds=[O.SCORER_DOSE, O.SCORER_LETD_NUMER, O.SCORER_LETD_DENOM])
