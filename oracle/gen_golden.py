@@ -83,6 +83,21 @@ def g1_gauss(procs=8, per_proc=50000):
     print("g1", {k: getattr(v, "shape", None) for k, v in keep.items()})
 
 
+def c2_debug(energy=150, procs=8, per_proc=50000):
+    """The C2 slab phantom, Dose only, with the DEBUG physics variant (-D__PHYSICS_DEBUG__: the water shortcut of
+    spr_default, zero-energy delta daughters, recoil daughters) through the reference's own phantom_env."""
+    import argparse
+    sys.path.insert(0, HERE)
+    import ref_run
+    a = argparse.Namespace(variant="debug", procs=procs, histories_per_proc=per_proc, energy=float(energy), spot_size=10.0,
+                           nxyz=[200, 200, 350], lxyz=[100.0, 100.0, 350.0], slab=[[50.0, 70.0, 1000.0], [70.0, 100.0, -741.0]],
+                           seed=9001, rebin=8, harness=False, scorers="dose", gauss=None, out=None)
+    res, meta = ref_run.run(a)
+    keep = {k: v for k, v in res.items() if k == "meta" or k.endswith(("_idd", "_idd_se", "_total", "_total_se"))}
+    np.savez_compressed(os.path.join(GOLD, "c2_slabs%d_debug.npz" % int(energy)), **keep)
+    print("c2_debug", energy, {k: getattr(v, "shape", None) for k, v in keep.items()})
+
+
 def c2_lett(energy=150):
     """The C2 slab phantom with the track-averaged LET scorers (scorers/mqi_scorer_energy_deposit.hpp:141-177:
     numerator = step length x LET, denominator = step length) through oracle/ref_harness.cpp --scorers lett."""
@@ -170,6 +185,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "f4":
         f4_roi()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "c2_debug":
+        c2_debug()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "g1":
         g1_gauss()

@@ -78,3 +78,21 @@ def test_gaussian_pencil_beam_against_reference_golden(golden_dir):
         for mine, ref in ((xz, gold["water_dE_total_xz"]), (yz, gold["water_dE_total_yz"])):
             a, r = _quantile_sigma(mine[k0:k1].sum(axis=0), x), _quantile_sigma(ref[k0:k1].sum(axis=0), x)
             assert abs(a / r - 1.0) < 0.02, (k0, a, r)
+
+
+def test_debug_variant_in_heterogeneous_media_against_reference_golden(golden_dir):
+    """-D__PHYSICS_DEBUG__ through bone and lung (tests/golden/c2_slabs150_debug.npz: the reference's own CPU
+    phantom_env): the part of the delta-electron dose the reference loses to rsp(rho, 0) = inf (quirk B16) is lost
+    here too, slab by slab."""
+    gold = np.load(os.path.join(golden_dir, "c2_slabs150_debug.npz"))
+    e = c1_engine(capi.PHYSICS_DEBUG, hu=slab_hu(), scorers=(capi.SCORER_DOSE,))
+    n = 2_000_000
+    e.set_beamlets([c1_beamlet(150.0, 10.0)], [n])
+    idd = depth_profiles(e, 1, n, 4, seed=577)[0]
+    ref_idd = gold["water_dE_total_idd"]
+    assert abs(idd.sum() / float(gold["water_dE_total_total"]) - 1.0) < 3e-3
+    assert abs(M.r80_mm(idd) - M.r80_mm(ref_idd)) < 0.1
+    assert M.gamma_1d(ref_idd, idd, 1.0)[0] >= 0.99
+    for lo, hi in ((0, 50), (50, 70), (70, 100), (100, 160)):   # water, bone, lung, water (depth d mm <-> k = 349 - floor(d))
+        a, r = idd[350 - hi:350 - lo].sum(), ref_idd[350 - hi:350 - lo].sum()
+        assert abs(a / r - 1.0) < 0.005, (lo, hi, a, r)

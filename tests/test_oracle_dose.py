@@ -144,3 +144,29 @@ def test_oracle_gaussian_pencil_beam_matches_reference_golden(golden_dir):
             assert abs(a / r - 1.0) < 0.03, (k0, a, r)
     # the spot is asymmetric (4 mm x 3 mm at the surface) and stays so
     assert 1.25 < _quantile_sigma(xz[340:350].sum(axis=0), x) / _quantile_sigma(yz[340:350].sum(axis=0), x) < 1.42
+
+
+def test_oracle_debug_variant_in_heterogeneous_media_matches_reference_golden(golden_dir):
+    """The DEBUG physics variant (-D__PHYSICS_DEBUG__: water shortcut of spr_default, zero-energy delta daughters,
+    recoil daughters) through bone and lung slabs at 150 MeV: restatement vs the reference's own CPU phantom_env
+    (tests/golden/c2_slabs150_debug.npz, generator oracle/gen_golden.py c2_debug).  Quirk B16: the delta daughter's
+    deposit is divided by rsp(rho, 0), which is infinite outside the energy-independent branches, so that part of the
+    dose is lost in bone and lung -- the restatement has to lose it too."""
+    gold = np.load(os.path.join(golden_dir, "c2_slabs150_debug.npz"))
+    xe, ye, ze = O.uniform_edges(-50, 50, 200), O.uniform_edges(-50, 50, 200), O.uniform_edges(-350, 0, 350)
+    hu = np.zeros((350, 200, 200), dtype=np.int64)
+    hu[350 - 70:350 - 50] = 1000
+    hu[350 - 100:350 - 70] = -741
+    rho = O.hu_to_density(np.arange(-1000, 2996))[hu.ravel() + 1000].astype(np.float32)
+    g, keep = O.make_grid(xe, ye, ze, rho)
+    b = O.make_beamlet(150.0, [0, 0, 0.5, 0, 0, -1], [10, 10, 0, 0, 0, 0], uniform=True)
+    n = 20000
+    (d,), st = O.transport(g, O.VARIANT_DEBUG, [b], [n], seed=41, h0=0, n=n, kinds=[O.SCORER_DOSE])
+    idd, ref_idd = d.reshape(350, -1).sum(axis=1) / n, gold["water_dE_total_idd"]
+    assert abs(idd.sum() / float(gold["water_dE_total_total"]) - 1.0) < 5e-3
+    assert abs(M.r80_mm(idd) - M.r80_mm(ref_idd)) < 0.15
+    assert M.gamma_1d(ref_idd, idd, 1.0)[0] >= 0.99
+    # slab by slab (depth d mm <-> k = 349 - floor(d)): water 0-50, bone 50-70, lung 70-100, water behind
+    for lo, hi in ((0, 50), (50, 70), (70, 100), (100, 160)):
+        a, r = idd[350 - hi:350 - lo].sum(), ref_idd[350 - hi:350 - lo].sum()
+        assert abs(a / r - 1.0) < 0.01, (lo, hi, a, r)
