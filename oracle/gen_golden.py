@@ -83,6 +83,52 @@ def g1_gauss(procs=8, per_proc=50000):
     print("g1", {k: getattr(v, "shape", None) for k, v in keep.items()})
 
 
+D1_SPOTS, D1_PITCH, D1_ENERGY, D1_SPOT = 3, 15.0, 120.0, 3.0
+
+
+def d1_dij(procs=8, per_proc=30000):
+    """Dij at transport level: three 120 MeV spots 15 mm apart in the C1 water phantom through oracle/ref_harness.cpp
+    --scorers dij (the reference's transport_particles_patient with its scorer_offset_vector = spot of each history,
+    insert_hashtable keyed by (voxel, spot)); the occupied slots are reduced to one depth profile and one lateral
+    centroid per spot."""
+    import time
+    nx, ny, nz = 200, 200, 350
+    exe = os.path.join(HERE, "_ref", "ref_harness_release")
+    idd = np.zeros((D1_SPOTS, nz))
+    cx = np.zeros(D1_SPOTS)
+    tot = np.zeros((procs, D1_SPOTS))
+    with tempfile.TemporaryDirectory() as work:
+        ph = os.path.join(work, "phantom.raw")
+        np.zeros(nx * ny * nz, dtype=np.int16).tofile(ph)
+        runs = []
+        for p in range(procs):
+            od = os.path.join(work, "o%d" % p)
+            os.makedirs(od)
+            cmd = [exe, "--lxyz", "100", "100", "350", "--pxyz", "0.0", "0.0", "-175.0", "--nxyz", str(nx), str(ny), str(nz),
+                   "--spot_energy", str(D1_ENERGY), "0.0", "--spot_position", "0", "0", "0.5", "--spot_size", str(D1_SPOT), str(D1_SPOT),
+                   "--histories", str(per_proc), "--phantom_path", ph, "--output_prefix", od, "--random_seed", str(5150 + 7919 * p),
+                   "--gpu_id", "0", "--scorers", "dij", "--nspots", str(D1_SPOTS), "--spot_pitch", str(D1_PITCH)]
+            runs.append((subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT), od))
+        for p, (pr, od) in enumerate(runs):
+            assert pr.wait() == 0
+            k1 = np.fromfile(os.path.join(od, "dij_key1.raw"), dtype=np.uint32).astype(np.int64)
+            k2 = np.fromfile(os.path.join(od, "dij_key2.raw"), dtype=np.uint32).astype(np.int64)
+            v = np.fromfile(os.path.join(od, "dij_value.raw"), dtype=np.float64)
+            assert k2.max() == D1_SPOTS - 1
+            z, x = k1 // (nx * ny), k1 % nx
+            np.add.at(idd, (k2, z), v)
+            np.add.at(cx, k2, v * ((x + 0.5) * 0.5 - 50.0))
+            np.add.at(tot[p], k2, v)
+    per_spot = procs * (per_proc // D1_SPOTS)
+    total = tot.sum(axis=0)
+    out = {"dij_idd": idd / per_spot, "dij_centroid_x": cx / total, "dij_total": total / per_spot,
+           "dij_total_se": tot.std(axis=0, ddof=1) * np.sqrt(procs) / per_spot,
+           "meta": np.array(str({"spots": D1_SPOTS, "pitch": D1_PITCH, "energy": D1_ENERGY, "spot_size": D1_SPOT,
+                                 "histories_per_spot": per_spot, "variant": "release"}))}
+    np.savez_compressed(os.path.join(GOLD, "d1_dij3_release.npz"), **out)
+    print("d1", {k: getattr(v, "shape", None) for k, v in out.items()}, out["dij_centroid_x"], out["dij_total"])
+
+
 def c2_debug(energy=150, procs=8, per_proc=50000):
     """The C2 slab phantom, Dose only, with the DEBUG physics variant (-D__PHYSICS_DEBUG__: the water shortcut of
     spr_default, zero-energy delta daughters, recoil daughters) through the reference's own phantom_env."""
@@ -185,6 +231,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "f4":
         f4_roi()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "d1":
+        d1_dij()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "c2_debug":
         c2_debug()

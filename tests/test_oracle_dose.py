@@ -170,3 +170,38 @@ def test_oracle_debug_variant_in_heterogeneous_media_matches_reference_golden(go
     for lo, hi in ((0, 50), (50, 70), (70, 100), (100, 160)):
         a, r = idd[350 - hi:350 - lo].sum(), ref_idd[350 - hi:350 - lo].sum()
         assert abs(a / r - 1.0) < 0.01, (lo, hi, a, r)
+
+
+def test_oracle_dij_rows_match_reference_golden(golden_dir):
+    """Dij at transport level (the reference's transport_particles_patient with scorer_offset_vector = spot of each
+    history, insert_hashtable keyed by (voxel, spot); mqi_transport.hpp:113-250): three 120 MeV spots 15 mm apart.
+    Restatement vs the reference's own CPU run through oracle/ref_harness.cpp --scorers dij --nspots 3
+    (tests/golden/d1_dij3_release.npz, generator oracle/gen_golden.py d1): every row of the matrix is the dose of
+    its own spot -- total, depth profile, lateral position."""
+    import ast
+    gold = np.load(os.path.join(golden_dir, "d1_dij3_release.npz"))
+    meta = ast.literal_eval(str(gold["meta"]))
+    n_spots, pitch = meta["spots"], meta["pitch"]
+    xe, ye, ze = O.uniform_edges(-50, 50, 200), O.uniform_edges(-50, 50, 200), O.uniform_edges(-350, 0, 350)
+    rho = np.full(200 * 200 * 350, O.hu_to_density(np.array([0]))[0], dtype=np.float32)
+    g, keep = O.make_grid(xe, ye, ze, rho)
+    bl = [O.make_beamlet(meta["energy"], [(s - 0.5 * (n_spots - 1)) * pitch, 0, 0.5, 0, 0, -1], [meta["spot_size"]] * 2 + [0, 0, 0, 0],
+                         uniform=True) for s in range(n_spots)]
+    per = 20000
+    (tab,), st = O.transport(g, O.VARIANT_RELEASE, bl, [per] * n_spots, seed=51, h0=0, n=per * n_spots, kinds=[O.SCORER_DIJ],
+                             per_spot=True, dij_capacity=6_000_011)
+    k1, k2, v = tab["key1"].astype(np.int64), tab["key2"].astype(np.int64), tab["value"]
+    assert set(np.unique(k2)) == set(range(n_spots))
+    idd = np.zeros((n_spots, 350))
+    np.add.at(idd, (k2, k1 // 40000), v)
+    idd /= per
+    cx = np.zeros(n_spots)
+    np.add.at(cx, k2, v * ((k1 % 200 + 0.5) * 0.5 - 50.0))
+    cx /= idd.sum(axis=1) * per
+    for s in range(n_spots):
+        assert abs(idd[s].sum() / float(gold["dij_total"][s]) - 1.0) < 5e-3, s
+        assert abs(cx[s] - float(gold["dij_centroid_x"][s])) < 0.1, s            # mm
+        assert abs(M.r80_mm(idd[s]) - M.r80_mm(gold["dij_idd"][s])) < 0.15, s
+        assert M.gamma_1d(gold["dij_idd"][s], idd[s], 1.0)[0] >= 0.99, s
+    # neighbouring rows do not leak into each other: 15 mm apart, 3 mm half-width
+    assert abs(cx[0] + pitch) < 0.1 and abs(cx[1]) < 0.1 and abs(cx[2] - pitch) < 0.1
