@@ -311,6 +311,31 @@ main(int argc, char** argv) {
         dump("rot_ang.f32", ang);
         dump("rot_out.f32", dout);
     }
+    // ---- 8. beam frame: coordinate_transform(collimator, gantry, couch, iec2dicom) (mqi_coordinate_transform.hpp:52-58),
+    // with the angles as treatment_machine_ion::create_coordinate_transform passes them (couch negated, iec2dicom 90)
+    // and as phantom_env --spot_angles passes them (iec2dicom 0)
+    {
+        std::vector<float> ang, rot, moved;
+        const float        colls[] = { 0.f, 15.f, -30.f, 90.f }, gans[] = { 0.f, 45.f, 90.f, 180.f, 270.f, 333.f },
+                    couches[] = { 0.f, 10.f, -20.f, 90.f }, iecs[] = { 0.f, 90.f };
+        for (float c : colls)
+            for (float ga : gans)
+                for (float co : couches)
+                    for (float ie : iecs) {
+                        std::array<R, 4>             a = { c, ga, co, ie };
+                        mqi::vec3<R>                 pos(1.5f, -2.5f, 40.f);
+                        mqi::coordinate_transform<R> t(a, pos);
+                        ang.push_back(c); ang.push_back(ga); ang.push_back(co); ang.push_back(ie);
+                        const R* m = &t.rotation.xx;
+                        for (int i = 0; i < 9; ++i) rot.push_back(m[i]);
+                        // a source-frame point and direction mapped to the patient frame: R * p + T, R * d
+                        mqi::vec3<R> p(3.f, -4.f, 465.f), q = t.rotation * p + t.translation;
+                        moved.push_back(q.x); moved.push_back(q.y); moved.push_back(q.z);
+                    }
+        dump("ct_ang.f32", ang);
+        dump("ct_rot.f32", rot);
+        dump("ct_moved.f32", moved);
+    }
     printf("ref_kat: wrote KATs to %s\n", g_dir.c_str());
     return 0;
 }

@@ -369,3 +369,40 @@ def test_run_length_roi_matches_the_reference_rule(tmp_path, case):
     for s, t in zip(start, stride):
         exp[s:s + t] = 1
     assert np.array_equal(member, exp)
+
+
+def test_beam_frame_matches_the_reference_coordinate_transform(tmp_path, golden_dir):
+    """The beam frame of every beam -- collimator, gantry, couch (negated) and iec2dicom = 90 degrees composed by
+    coordinate_transform (mqi_coordinate_transform.hpp:52-58, create_coordinate_transform tmi:42-70) -- against
+    matrices the reference header itself produced (oracle/ref_kat.cpp section 8 -> tests/golden/kat_release.npz).
+    The numpy restatement used by the other tests of this module is held to the same vectors."""
+    k = np.load(os.path.join(golden_dir, "kat_release.npz"))
+    ang, rot, moved = k["ct_ang"].reshape(-1, 4), k["ct_rot"].reshape(-1, 3, 3), k["ct_moved"].reshape(-1, 3)
+    sel = [i for i in range(len(ang)) if ang[i, 3] == 90.0]
+    assert len(sel) == 96
+    for i in sel:   # the restatement: rot_matrix takes the couch angle as the plan states it
+        np.testing.assert_allclose(rot_matrix(ang[i, 0], ang[i, 1], -ang[i, 2]), rot[i], atol=3e-7)
+    # the C++ host code, through the text plan (a subset keeps the plan small: every gantry angle, mixed collimator / couch)
+    pick = [i for i in sel if (i // 2) % 5 == 0][:20]
+    root = str(tmp_path)
+    os.makedirs(root, exist_ok=True)
+    hu, origin = S.head_ct((32, 32, 20), (4.0, 4.0, 6.0), 1)
+    S.write_mha(os.path.join(root, "ct.mha"), hu, origin, (4.0, 4.0, 6.0))
+    S.write_beam_model(os.path.join(root, "machine.txt"))
+    iso = (1.5, -2.5, 40.0)                                   # the translation of the KAT
+    beams = [{"name": "B%02d" % n, "collimator": float(ang[i, 0]), "gantry": float(ang[i, 1]), "couch": float(-ang[i, 2]),
+              "iso": iso, "snout": 250.0, "spots": S.spot_list(n_layers=1, pitch=20.0, half_width=10.0, seed=3)}
+             for n, i in enumerate(pick)]
+    S.write_plan(os.path.join(root, "plan.txt"), beams)
+    inp = os.path.join(root, "moqui_tps.in")
+    S.write_input(inp, root, os.path.join(root, "out"), ParticlesPerHistory=1e4)
+    out = dry_run(inp)
+    assert len(out["beams"]) == len(pick)
+    for beam, i in zip(out["beams"], pick):
+        for sp in beam["spots"]:
+            np.testing.assert_allclose(np.array(sp["rot"]).reshape(3, 3), rot[i], atol=3e-7)
+            np.testing.assert_allclose(sp["trans"], iso, atol=1e-6)
+    # and one point carried through a frame by hand: R * p + T as the reference computed it
+    p = np.array([3.0, -4.0, 465.0])
+    for i in sel[:8]:
+        np.testing.assert_allclose(rot[i].astype(np.float64) @ p + np.array(iso), moved[i], rtol=2e-6, atol=2e-5)
