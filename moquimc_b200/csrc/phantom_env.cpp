@@ -13,8 +13,26 @@
 #include <chrono>
 #include <iostream>
 
+// phantom_env --write-selftest <dir>: the output writers on a small fixed volume, without a device.  The files are
+// compared byte for byte with the ones the reference's io::save_to_mhd / save_to_mha wrote for the same volume
+// (oracle/ref_kat.cpp section 9 -> tests/golden/fmt_writers.npz, tests/test_cli.py).
+static int
+write_selftest(const std::string& dir) {
+    mqib::grid_desc g;
+    g.xe = { -1.25f, -0.75f, -0.25f, 0.25f, 0.75f };
+    g.ye = { 10.f, 10.75f, 11.5f, 12.25f };
+    g.ze = { -3.7f, -2.45f, -1.2f };
+    double src[24];
+    for (int i = 0; i < 24; ++i)
+        src[i] = 0.001 * i * i - 0.0137 * i + (i % 5 == 0 ? 0.0 : 1e-9 * i);
+    mqib::save_to_mhd(g, src, (double) 2.5f, dir, "fmt_mhd", 24);
+    mqib::save_to_mha(g, src, (double) 2.5f, dir, "fmt_mha", 24);
+    return 0;
+}
+
 int
 main(int argc, char* argv[]) {
+    if (argc == 3 && std::string(argv[1]) == "--write-selftest") return write_selftest(argv[2]);
     auto      start = std::chrono::high_resolution_clock::now();
     mqib::cli cl;
     cl.read(argc, argv);

@@ -22,9 +22,16 @@ def kat(variant):
     with tempfile.TemporaryDirectory() as d:
         subprocess.check_call([os.path.join(HERE, "_ref", "ref_kat_" + variant), d], stdout=subprocess.DEVNULL)
         out = {}
+        fmt = {}
         for f in sorted(os.listdir(d)):
             name, ext = f.rsplit(".", 1)
+            if name.startswith("fmt_"):   # files written by the reference's own output writers: kept as bytes
+                fmt[f.replace(".", "_")] = np.fromfile(os.path.join(d, f), dtype=np.uint8)
+                continue
             out[name] = np.fromfile(os.path.join(d, f), dtype=DT[ext])
+        if variant == "release":
+            np.savez_compressed(os.path.join(GOLD, "fmt_writers.npz"), **fmt)
+            print("fmt", {k: v.shape for k, v in fmt.items()})
         # the physics tables live in moquimc_b200/data/mqi_tables_v1.bin; keep only a checksum here
         for k in ("tables", "density_correction"):
             out[k + "_sum"] = np.array(out.pop(k).astype(np.float64).sum())

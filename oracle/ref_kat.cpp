@@ -336,6 +336,37 @@ main(int argc, char** argv) {
         dump("ct_rot.f32", rot);
         dump("ct_moved.f32", moved);
     }
+    // ---- 9. output writers: io::save_to_mhd / save_to_mha (mqi_io.hpp:493-591) on a small ragged-offset grid; the
+    // files themselves are the vectors (gen_golden.py packs fmt_* into tests/golden/fmt_writers.npz as bytes)
+    {
+        const float xe[5] = { -1.25f, -0.75f, -0.25f, 0.25f, 0.75f };
+        const float ye[4] = { 10.f, 10.75f, 11.5f, 12.25f };
+        const float ze[3] = { -3.7f, -2.45f, -1.2f };
+        mqi::node_t<R> node;
+        node.geo = new mqi::grid3d<mqi::density_t, R>(xe, 5, ye, 4, ze, 3);
+        double src[24];
+        for (int i = 0; i < 24; ++i)
+            src[i] = 0.001 * i * i - 0.0137 * i + (i % 5 == 0 ? 0.0 : 1e-9 * i);
+        mqi::io::save_to_mhd<R>(&node, src, (R) 2.5, g_dir, "fmt_mhd", 24);
+        mqi::io::save_to_mha<R>(&node, src, (R) 2.5, g_dir, "fmt_mha", 24);
+    }
+    // ---- 10. sparse output: io::save_to_npz (mqi_io.hpp:249-320) of a small (voxel, spot) table: the six entries of
+    // tps_env --npz-selftest, in the same slot order, 3 spots x 10 voxels
+    {
+        const uint32_t  cap = 16;
+        mqi::scorer<R>* sc  = new mqi::scorer<R>("Dij", cap, mqi::dose_to_water<R>);
+        mqi::key_value* t   = new mqi::key_value[cap];
+        mqi::init_table(t, cap);
+        const uint32_t vox[6] = { 7, 2, 9, 2, 0, 5 }, spot[6] = { 2, 0, 2, 1, 0, 2 }, slot[6] = { 1, 3, 4, 8, 9, 14 };
+        for (int i = 0; i < 6; ++i) {
+            t[slot[i]].key1  = vox[i];
+            t[slot[i]].key2  = spot[i];
+            t[slot[i]].value = 0.5 + i;
+        }
+        sc->data_ = t;
+        mqi::vec3<mqi::ijk_t> dim(10, 1, 1);
+        mqi::io::save_to_npz<R>(sc, (R) 1.0, g_dir, "fmt_npz", dim, 3);
+    }
     printf("ref_kat: wrote KATs to %s\n", g_dir.c_str());
     return 0;
 }
