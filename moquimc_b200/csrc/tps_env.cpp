@@ -79,6 +79,30 @@ main(int argc, char* argv[]) {
             const std::vector<double>   val { 0.5, 1.5, 2.5, 3.5, 4.5, 5.5 };
             mqib::save_csr_npz(argv[i + 1], 3, 10, vox, spot, val);
             return 0;
+        } else if (std::string(argv[i]) == "--parse-selftest" && i + 1 < argc) {
+            // input-parameter format self-test for the CPU suite: the queries of oracle/ref_kat.cpp section 11, answered by
+            // this file_parser; the reference's own file_parser answered them in tests/golden/fmt_writers.npz
+            mqib::file_parser p(argv[i + 1], " ");
+            std::ostream&     o = std::cout;
+            const char*       skeys[] = { "GPUID", "randomseed", "ParentDir", "SCORER", "Mask", "OutputDir", "Machine", "UnitWeights",
+                                    "Duplicate", "NoValue", "Missing", "EmptyList", "Trailing", "ZShift" };
+            for (const char* k : skeys) o << k << "|s|" << p.get_string(k, "<default>") << "|\n";
+            const char* ikeys[] = { "GPUID", "RandomSeed", "BeamNumbers", "Missing", "Trailing", "XShift", "ParticlesPerHistory" };
+            for (const char* k : ikeys) o << k << "|i|" << p.get_int(k, -7) << "|\n";
+            const char* fkeys[] = { "XShift", "YShift", "ZShift", "ParticlesPerHistory", "Missing", "RandomSeed" };
+            for (const char* k : fkeys) o << k << "|f|" << std::setprecision(9) << p.get_float(k, 0.125f) << "|\n";
+            const char* bkeys[] = { "OverwriteResults", "SaveMap", "ReadStructure", "ScoringMask", "StoppingStatistics", "Missing",
+                                    "UnitWeights", "GPUID", "XShift" };
+            for (const char* k : bkeys) o << k << "|b|" << p.get_bool(k, false) << p.get_bool(k, true) << "|\n";
+            const char* vkeys[] = { "scorer", "Mask", "BeamNumbers", "Missing", "EmptyList", "GPUID" };
+            for (const char* k : vkeys) {
+                o << k << "|v|";
+                for (const auto& t : p.get_string_vector(k, ",")) o << "[" << t << "]";
+                o << "|";
+                for (int t : p.get_int_vector(k, ",")) o << t << ";";
+                o << "|\n";
+            }
+            return 0;
         } else if (std::string(argv[i]) == "--roi-selftest" && i + 1 < argc) {
             // run-length roi of a raw uint8 summed-mask file (CPU suite): prints "start stride acc_stride" per run,
             // then the compressed index of every 7th voxel

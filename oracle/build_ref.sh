@@ -33,6 +33,13 @@ grep -q 'n == 0' "$TMP/moqui/base/mqi_p_ionization.hpp" || { echo "patch 2 did n
     | sed '/mqi_beam_module_ion.hpp/d; s/#include <moqui\/base\/mqi_roi.hpp>/#include <moqui\/base\/mqi_roi.hpp>\n#include <moqui\/base\/mqi_common.hpp>\n#include <moqui\/base\/mqi_vec.hpp>\n#include <cassert>\n#include <cstring>\n#include <string>\n#include <vector>/';
   printf '}\n#endif\n'; } > "$TMP/moqui/base/mqi_file_handler.hpp"
 grep -q 'mask_to_roi' "$TMP/moqui/base/mqi_file_handler.hpp" || { echo "patch 3 did not apply" >&2; exit 1; }
+#   4. the generic part of class file_parser (constructor, read_input_parameters, get_string ... get_bool; the
+#      reference file from "class file_parser" up to the line before string_to_scorer_type, which needs the GDCM-side
+#      enums) as a scratch header of its own, used by ref_kat section 11 only.
+{ printf '#pragma once\n#include <cstring>\n#include <fstream>\n#include <iostream>\n#include <string>\n#include <vector>\n#include <moqui/base/mqi_common.hpp>\n#include <moqui/base/mqi_utils.hpp>\nnamespace mqi {\n';
+  sed -n '/^class file_parser/,/string_to_scorer_type/p' "$REF/moqui/base/mqi_file_handler.hpp" | head -n -3;
+  printf '};\n}\n'; } > "$TMP/moqui/base/mqi_file_parser_only.hpp"
+grep -q 'get_bool' "$TMP/moqui/base/mqi_file_parser_only.hpp" || { echo "patch 4 did not apply" >&2; exit 1; }
 CXX=${CXX:-g++}
 FLAGS="-std=c++11 -O2 -w -DNDEBUG -I$TMP -I$REF"
 # phantom_env exactly as the reference's tests/mc/phantom CMake builds it (debug physics) ...

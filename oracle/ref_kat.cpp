@@ -15,11 +15,14 @@
 //                                              mqi_po_elastic.hpp:243-256, mqi_po_inelastic.hpp:141-155
 //   track_t::update_post_vertex_direction      base/mqi_track.hpp:163-172 (+ mqi_matrix.hpp:69-150)
 #include <cstdio>
+#include <fstream>
+#include <iomanip>
 #include <cstdint>
 #include <string>
 #include <vector>
 
 #include <moqui/base/environments/mqi_phantom_env.hpp>
+#include <moqui/base/mqi_file_parser_only.hpp>   // scratch header cut from mqi_file_handler.hpp by build_ref.sh (patch 4)
 
 static std::string g_dir;
 
@@ -366,6 +369,39 @@ main(int argc, char** argv) {
         sc->data_ = t;
         mqi::vec3<mqi::ijk_t> dim(10, 1, 1);
         mqi::io::save_to_npz<R>(sc, (R) 1.0, g_dir, "fmt_npz", dim, 3);
+    }
+    // ---- 11. the moqui input-parameter format: file_parser (mqi_file_handler.hpp:220-380) on a file with comments,
+    // tabs, odd spacing, mixed-case and repeated keys, empty values and lists; the queries of tps_env --parse-selftest
+    {
+        const std::string in = g_dir + "/fmt_parser_in.txt";
+        {
+            std::ofstream f(in);
+            f << "# a full-line comment\n\nGPUID 0\n   RandomSeed   -1932   # trailing comment\n"
+              << "ParentDir\t/data/case one/\nscorer Dose, LETd ,Dij\nMask a.mha,b.mha , c.mha\nBeamNumbers 1, 3,5\n"
+              << "XShift 1.5e0\nYShift -2\nZShift .25abc\nOverwriteResults True\nSaveMap 1\nReadStructure false\n"
+              << "ScoringMask 0\nStoppingStatistics tRuE\nUnitWeights\nDUPLICATE first\nDuplicate second\nNoValue\n"
+              << "OutputDir ./out # x\nParticlesPerHistory 2.5e4\nMachine pbs:/a b/machine.txt\nEmptyList \nTrailing 7   \n";
+        }
+        mqi::file_parser   p(in, " ");
+        std::ofstream      o(g_dir + "/fmt_parser_out.txt");
+        const char*        skeys[] = { "GPUID", "randomseed", "ParentDir", "SCORER", "Mask", "OutputDir", "Machine", "UnitWeights",
+                                "Duplicate", "NoValue", "Missing", "EmptyList", "Trailing", "ZShift" };
+        for (const char* k : skeys) o << k << "|s|" << p.get_string(k, "<default>") << "|\n";
+        const char* ikeys[] = { "GPUID", "RandomSeed", "BeamNumbers", "Missing", "Trailing", "XShift", "ParticlesPerHistory" };
+        for (const char* k : ikeys) o << k << "|i|" << p.get_int(k, -7) << "|\n";
+        const char* fkeys[] = { "XShift", "YShift", "ZShift", "ParticlesPerHistory", "Missing", "RandomSeed" };
+        for (const char* k : fkeys) o << k << "|f|" << std::setprecision(9) << p.get_float(k, 0.125f) << "|\n";
+        const char* bkeys[] = { "OverwriteResults", "SaveMap", "ReadStructure", "ScoringMask", "StoppingStatistics", "Missing", "UnitWeights",
+                                "GPUID", "XShift" };
+        for (const char* k : bkeys) o << k << "|b|" << p.get_bool(k, false) << p.get_bool(k, true) << "|\n";
+        const char* vkeys[] = { "scorer", "Mask", "BeamNumbers", "Missing", "EmptyList", "GPUID" };
+        for (const char* k : vkeys) {
+            o << k << "|v|";
+            for (const auto& t : p.get_string_vector(k, ",")) o << "[" << t << "]";
+            o << "|";
+            for (int t : p.get_int_vector(k, ",")) o << t << ";";
+            o << "|\n";
+        }
     }
     printf("ref_kat: wrote KATs to %s\n", g_dir.c_str());
     return 0;

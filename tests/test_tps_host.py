@@ -435,3 +435,19 @@ def test_output_writers_match_the_files_the_reference_writes(tmp_path, golden_di
     mf, rf = mine.read("format.npy"), ref.read("format.npy")
     assert np.load(io.BytesIO(mf)).tobytes() == b"csr" and np.load(io.BytesIO(rf)).tobytes() == b"csr"
     assert len(rf) > len(mf) == mf.index(b"csr") + 3
+
+
+def test_input_parameter_format_is_parsed_like_the_reference_parser(tmp_path, golden_dir):
+    """The moqui input-parameter file: the reference's own file_parser (mqi_file_handler.hpp:220-380, compiled from a
+    scratch cut of that header, oracle/build_ref.sh patch 4) answered 42 queries on a file with comments, tabs, odd
+    spacing, mixed-case and repeated keys, empty values and lists (oracle/ref_kat.cpp section 11 ->
+    tests/golden/fmt_writers.npz); this file_parser has to give the same answers, quirks included (a tab is not a
+    delimiter, the first of two keys that differ only in case wins, atoi / atof stop at the first odd character)."""
+    g = np.load(os.path.join(golden_dir, "fmt_writers.npz"))
+    inp = tmp_path / "in.txt"
+    inp.write_bytes(bytes(g["fmt_parser_in_txt"]))
+    r = subprocess.run([EXE, "--parse-selftest", str(inp)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    ref = bytes(g["fmt_parser_out_txt"]).decode()
+    assert len(ref.splitlines()) == 42
+    assert r.stdout.splitlines() == ref.splitlines()
