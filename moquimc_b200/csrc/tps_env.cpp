@@ -103,6 +103,21 @@ main(int argc, char* argv[]) {
                 o << "|\n";
             }
             return 0;
+        } else if (std::string(argv[i]) == "--mask-selftest" && i + 4 < argc) {
+            // mask files self-test for the CPU suite: --mask-selftest a.mha,b.mha nx ny nz reads the uint8 .mha masks,
+            // adds them and prints the run-length roi (the reference's own mask_reader did the same on the same files:
+            // oracle/ref_kat.cpp section 12)
+            std::vector<std::string> files;
+            std::stringstream        ss(argv[i + 1]);
+            for (std::string f; std::getline(ss, f, ',');) files.push_back(f);
+            const std::vector<uint8_t> m = mqib::read_mask_files(files, std::atoi(argv[i + 2]), std::atoi(argv[i + 3]), std::atoi(argv[i + 4]));
+            const mqib::RoiRuns        r = mqib::mask_to_roi(m.data(), m.size());
+            printf("runs %zu size %u\n", r.start.size(), r.size());
+            for (size_t k = 0; k < r.start.size(); ++k) printf("run %u %u %u\n", r.start[k], r.stride[k], r.acc_stride[k]);
+            printf("total");
+            for (uint8_t v : m) printf(" %u", (unsigned) v);
+            printf("\n");
+            return 0;
         } else if (std::string(argv[i]) == "--roi-selftest" && i + 1 < argc) {
             // run-length roi of a raw uint8 summed-mask file (CPU suite): prints "start stride acc_stride" per run,
             // then the compressed index of every 7th voxel

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include <moqui/base/environments/mqi_phantom_env.hpp>
+#include <moqui/base/mqi_file_handler.hpp>       // scratch copy cut before class file_parser (patch 3): mask_reader
 #include <moqui/base/mqi_file_parser_only.hpp>   // scratch header cut from mqi_file_handler.hpp by build_ref.sh (patch 4)
 
 static std::string g_dir;
@@ -402,6 +403,50 @@ main(int argc, char** argv) {
             for (int t : p.get_int_vector(k, ",")) o << t << ";";
             o << "|\n";
         }
+    }
+    // ---- 12. mask files: mask_reader::read_mha_file + read_mask_files + mask_to_roi (mqi_file_handler.hpp:38-217) on two
+    // overlapping uint8 .mha masks of a 7 x 5 x 4 volume written here (one header in the order ITK writes it, one with
+    // odd spacing and upper-case keys); the summed mask and the run-length roi are the vectors
+    {
+        const int nx = 7, ny = 5, nz = 4, n = nx * ny * nz;
+        std::vector<uint8_t> a(n, 0), b(n, 0);
+        for (int k = 0; k < nz; ++k)
+            for (int j = 0; j < ny; ++j)
+                for (int i = 0; i < nx; ++i) {
+                    const int v = (k * ny + j) * nx + i;
+                    a[v] = (i >= 1 && i <= 4 && j >= 1 && j <= 3 && k <= 2) ? 1 : 0;
+                    b[v] = ((i + j + k) % 3 == 0 || (i >= 4 && k >= 2)) ? 1 : 0;
+                }
+        a[0] = 1;        // a run that starts at voxel 0
+        b[n - 1] = 1;    // and one still open at the end of the volume
+        a[n - 1] = 0;
+        const std::string fa = g_dir + "/fmt_mask_a.mha", fb = g_dir + "/fmt_mask_b.mha";
+        {
+            std::ofstream f(fa, std::ios::binary);
+            f << "ObjectType = Image\nNDims = 3\nBinaryData = True\nBinaryDataByteOrderMSB = False\nCompressedData = False\n"
+              << "TransformMatrix = 1 0 0 0 1 0 0 0 1\nOffset = 0 0 0\nCenterOfRotation = 0 0 0\nAnatomicalOrientation = RAI\n"
+              << "ElementSpacing = 1 1 1\nDimSize = 7 5 4\nElementType = MET_UCHAR\nElementDataFile = LOCAL\n";
+            f.write((const char*) a.data(), n);
+        }
+        {
+            std::ofstream f(fb, std::ios::binary);
+            f << "NDims=3\nDIMSIZE =   7 5 4\n  ElementType = MET_UCHAR  \nelementdatafile =  local\n";
+            f.write((const char*) b.data(), n);
+        }
+        mqi::vec3<mqi::ijk_t>    dim(nx, ny, nz);
+        std::vector<std::string> files = { fa, fb };
+        mqi::mask_reader         mr(files, dim);
+        mr.read_mask_files();
+        mqi::roi_t*           roi = mr.mask_to_roi();
+        std::vector<uint32_t> runs;
+        runs.push_back(roi->length_);
+        for (uint32_t k = 0; k < roi->length_; ++k) {
+            runs.push_back(roi->start_[k]);
+            runs.push_back(roi->stride_[k]);
+        }
+        dump("mask_runs.u32", runs);
+        std::vector<uint32_t> tot(mr.mask_total, mr.mask_total + n);
+        dump("mask_total.u32", tot);
     }
     printf("ref_kat: wrote KATs to %s\n", g_dir.c_str());
     return 0;

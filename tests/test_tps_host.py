@@ -451,3 +451,32 @@ def test_input_parameter_format_is_parsed_like_the_reference_parser(tmp_path, go
     ref = bytes(g["fmt_parser_out_txt"]).decode()
     assert len(ref.splitlines()) == 42
     assert r.stdout.splitlines() == ref.splitlines()
+
+
+def test_mask_files_are_read_like_the_reference_mask_reader(tmp_path, golden_dir):
+    """ScoringMask / StatROIMaskFilename inputs: the reference's own mask_reader (read_mha_file, read_mask_files,
+    mask_to_roi; mqi_file_handler.hpp:38-217) read two overlapping uint8 .mha masks -- one with an ITK-ordered header, one
+    with upper-case keys and odd spacing -- in oracle/ref_kat.cpp section 12; the same files through this reader
+    (tps_env --mask-selftest) give the same summed mask and the same run-length roi.  The one designed difference: a
+    run still open at the end of the volume is closed there (the reference leaves that stride uninitialised)."""
+    g = np.load(os.path.join(golden_dir, "fmt_writers.npz"))
+    k = np.load(os.path.join(golden_dir, "kat_release.npz"))
+    a, b = tmp_path / "a.mha", tmp_path / "b.mha"
+    a.write_bytes(bytes(g["fmt_mask_a_mha"]))
+    b.write_bytes(bytes(g["fmt_mask_b_mha"]))
+    r = subprocess.run([EXE, "--mask-selftest", "%s,%s" % (a, b), "7", "5", "4"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    total = [int(x) for x in [ln for ln in lines if ln.startswith("total")][0].split()[1:]]
+    assert total == k["mask_total"].tolist() and max(total) == 2       # overlaps add up
+    runs = [tuple(int(x) for x in ln.split()[1:3]) for ln in lines if ln.startswith("run ")]
+    ref = k["mask_runs"]
+    n = int(ref[0])
+    ref_runs = [(int(ref[1 + 2 * i]), int(ref[2 + 2 * i])) for i in range(n)]
+    assert len(runs) == n == 29
+    assert runs[:-1] == ref_runs[:-1] and runs[-1][0] == ref_runs[-1][0]
+    assert runs[-1][0] + runs[-1][1] == 7 * 5 * 4                      # closed at the end of the volume
+    assert total[0] == 2 and runs[0][0] != 0                           # a voxel where both masks start does not open a run
+    # a mask of the wrong size is refused (the reference would read past its buffer)
+    bad = subprocess.run([EXE, "--mask-selftest", str(a), "7", "5", "5"], capture_output=True, text=True, timeout=60)
+    assert bad.returncode != 0
