@@ -40,6 +40,10 @@ grep -q 'mask_to_roi' "$TMP/moqui/base/mqi_file_handler.hpp" || { echo "patch 3 
   sed -n '/^class file_parser/,/string_to_scorer_type/p' "$REF/moqui/base/mqi_file_handler.hpp" | head -n -3;
   printf '};\n}\n'; } > "$TMP/moqui/base/mqi_file_parser_only.hpp"
 grep -q 'get_bool' "$TMP/moqui/base/mqi_file_parser_only.hpp" || { echo "patch 4 did not apply" >&2; exit 1; }
+#   5. moqui/base/mqi_dataset.hpp, the GDCM-backed DICOM access class, is shadowed by oracle/ref_dataset_stub.hpp (an
+#      in-memory stand-in written for this harness; GDCM is absent), so that treatment_machine_pbs / _ion and
+#      beam_module_ion compile unmodified for ref_tps_kat.  Nothing else built here includes that header.
+cp "$HERE/ref_dataset_stub.hpp" "$TMP/moqui/base/mqi_dataset.hpp"
 CXX=${CXX:-g++}
 FLAGS="-std=c++11 -O2 -w -DNDEBUG -I$TMP -I$REF"
 # phantom_env exactly as the reference's tests/mc/phantom CMake builds it (debug physics) ...
@@ -52,5 +56,8 @@ for v in debug release; do
     $CXX $FLAGS $D "$HERE/ref_kat.cpp" -o "$OUT/ref_kat_$v" -lz &
     $CXX $FLAGS $D "$HERE/ref_harness.cpp" -o "$OUT/ref_harness_$v" -lz &
 done
+# -O0: treatment_machine_ion::create_beamsource binds a reference to *nullptr for the last spot (characterize_beamlet_time
+# ignores it); optimised builds of that undefined behaviour crash
+$CXX -std=c++11 -O0 -w -I$TMP -I$REF "$HERE/ref_tps_kat.cpp" -o "$OUT/ref_tps_kat" &
 wait
 ls -la "$OUT"

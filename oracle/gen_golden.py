@@ -90,6 +90,32 @@ def g1_gauss(procs=8, per_proc=50000):
     print("g1", {k: getattr(v, "shape", None) for k, v in keep.items()})
 
 
+B1_ARGS = dict(pph=25000.0, snout=250.0, collimator=15.0, gantry=45.0, couch=10.0, iso=(1.5, -2.5, 40.0),
+               n_layers=4, pitch=10.0, half_width=20.0, seed=1)
+
+
+def b1_beam_model():
+    """The beam model at work: the reference's own mqi::pbs (beam data file, spot -> beamlet, histories per spot),
+    treatment_machine_ion::create_beamsource / create_coordinate_transform and beam_module_ion, unmodified, on the
+    synthetic machine file and a 52-spot plan built in memory (oracle/ref_tps_kat.cpp over oracle/ref_dataset_stub.hpp)."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from moquimc_b200 import synthetic as S
+    a = B1_ARGS
+    with tempfile.TemporaryDirectory() as d:
+        S.write_beam_model(os.path.join(d, "machine.txt"))
+        spots = S.spot_list(n_layers=a["n_layers"], pitch=a["pitch"], half_width=a["half_width"], seed=a["seed"])
+        with open(os.path.join(d, "spots.txt"), "w") as f:
+            f.write("".join("%.6g %.6g %.6g %.8g\n" % s for s in spots))   # as synthetic.write_plan prints them
+        out = subprocess.check_output([os.path.join(HERE, "_ref", "ref_tps_kat"), os.path.join(d, "machine.txt"),
+                                       os.path.join(d, "spots.txt"), "%g" % a["pph"], "%g" % a["snout"], "%g" % a["collimator"],
+                                       "%g" % a["gantry"], "%g" % a["couch"]] + ["%g" % v for v in a["iso"]]).decode()
+    lines = [ln for ln in out.splitlines() if ln.startswith(("angles", "trans", "spot "))]
+    assert len(lines) == len(spots) + 2
+    np.savez_compressed(os.path.join(GOLD, "b1_beam_model.npz"), text=np.frombuffer("\n".join(lines).encode(), dtype=np.uint8),
+                        meta=np.array(str(a)))
+    print("b1", len(lines), lines[0], lines[1])
+
+
 D1_SPOTS, D1_PITCH, D1_ENERGY, D1_SPOT = 3, 15.0, 120.0, 3.0
 
 
@@ -238,6 +264,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "f4":
         f4_roi()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "b1":
+        b1_beam_model()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "d1":
         d1_dij()

@@ -480,3 +480,38 @@ def test_mask_files_are_read_like_the_reference_mask_reader(tmp_path, golden_dir
     # a mask of the wrong size is refused (the reference would read past its buffer)
     bad = subprocess.run([EXE, "--mask-selftest", str(a), "7", "5", "5"], capture_output=True, text=True, timeout=60)
     assert bad.returncode != 0
+
+
+def test_beam_source_matches_the_reference_beam_model_code(tmp_path, golden_dir):
+    """The treatment_machines beam model at work: the reference's own mqi::pbs (beam data file, spot -> beamlet
+    interpolation, histories per spot), treatment_machine_ion::create_beamsource / create_coordinate_transform and
+    beam_module_ion ran UNMODIFIED on the synthetic machine file and a 52-spot plan (oracle/ref_tps_kat.cpp; only the
+    GDCM-backed dataset class below them is an in-memory stand-in) -> tests/golden/b1_beam_model.npz.  The C++ host code
+    of this framework, fed the same machine file and the same plan as text, has to build the same beamlets: energy and
+    its spread, start position 50 mm upstream of the snout, direction through the SAD, spot sizes and divergences,
+    histories per spot, the couch angle negated, the isocentre as translation."""
+    import ast
+    g = np.load(os.path.join(golden_dir, "b1_beam_model.npz"))
+    a = ast.literal_eval(str(g["meta"]))
+    lines = bytes(g["text"]).decode().splitlines()
+    ref_angles = [float(x) for x in lines[0].split()[1:]]
+    ref_trans = [float(x) for x in lines[1].split()[1:]]
+    ref_spots = [[float(x) for x in ln.split()[2:]] for ln in lines[2:]]
+    root = str(tmp_path)
+    hu, origin = S.head_ct((32, 32, 20), (4.0, 4.0, 6.0), 1)
+    S.write_mha(os.path.join(root, "ct.mha"), hu, origin, (4.0, 4.0, 6.0))
+    S.write_beam_model(os.path.join(root, "machine.txt"))
+    spots = S.spot_list(n_layers=a["n_layers"], pitch=a["pitch"], half_width=a["half_width"], seed=a["seed"])
+    S.write_plan(os.path.join(root, "plan.txt"), [{"name": "B0", "collimator": a["collimator"], "gantry": a["gantry"],
+                                                     "couch": a["couch"], "iso": a["iso"], "snout": a["snout"], "spots": spots}])
+    inp = os.path.join(root, "moqui_tps.in")
+    S.write_input(inp, root, os.path.join(root, "out"), ParticlesPerHistory=a["pph"])
+    beam = dry_run(inp)["beams"][0]
+    assert beam["sid"] == a["snout"] + 50.0 and len(beam["spots"]) == len(ref_spots) == 52
+    assert ref_angles == [a["collimator"], a["gantry"], -a["couch"], 0.0] and ref_trans == list(a["iso"])
+    for sp, ref in zip(beam["spots"], ref_spots):
+        assert sp["histories"] == int(ref[0])
+        mine = [sp["energy"], sp["sigma_energy"]] + sp["mean"] + sp["sigma"]
+        np.testing.assert_allclose(mine, ref[1:], rtol=2e-7, atol=1e-9)
+        np.testing.assert_allclose(sp["trans"], ref_trans, atol=1e-6)
+        np.testing.assert_allclose(np.array(sp["rot"]).reshape(3, 3), rot_matrix(a["collimator"], a["gantry"], a["couch"]), atol=3e-7)
