@@ -94,6 +94,14 @@ B1_ARGS = dict(pph=25000.0, snout=250.0, collimator=15.0, gantry=45.0, couch=10.
                n_layers=4, pitch=10.0, half_width=20.0, seed=1)
 
 
+B1_BLOCK = [(-10.0, -8.0), (10.0, -8.0), (10.0, 8.0), (-10.0, 8.0)]
+B1_BEAMLINES = {
+    "rs_id_block": ["--rs-id", "RS1", "--block", "20", "60"] + ["%g" % v for p in B1_BLOCK for v in p],
+    "rs_two_ids": ["--rs-id", "RS1", "RS1"],
+    "rs_wet": ["--rs-wet", "46", "120"],
+}
+
+
 def b1_beam_model():
     """The beam model at work: the reference's own mqi::pbs (beam data file, spot -> beamlet, histories per spot),
     treatment_machine_ion::create_beamsource / create_coordinate_transform and beam_module_ion, unmodified, on the
@@ -109,10 +117,27 @@ def b1_beam_model():
         out = subprocess.check_output([os.path.join(HERE, "_ref", "ref_tps_kat"), os.path.join(d, "machine.txt"),
                                        os.path.join(d, "spots.txt"), "%g" % a["pph"], "%g" % a["snout"], "%g" % a["collimator"],
                                        "%g" % a["gantry"], "%g" % a["couch"]] + ["%g" % v for v in a["iso"]]).decode()
-    lines = [ln for ln in out.splitlines() if ln.startswith(("angles", "trans", "spot "))]
-    assert len(lines) == len(spots) + 2
+        lines = [ln for ln in out.splitlines() if ln.startswith(("angles", "trans", "spot "))]
+        assert len(lines) == len(spots) + 2
+        # beamline devices through create_beamline (characterize_rangeshifter / characterize_aperture): range shifter by
+        # ID + one block; two range shifter IDs; range shifter by water-equivalent thickness (a machine file without
+        # the [rangeshifter_thickness] table selects that branch)
+        base = [os.path.join(HERE, "_ref", "ref_tps_kat"), os.path.join(d, "machine.txt"), os.path.join(d, "spots.txt"), "%g" % a["pph"],
+                "%g" % a["snout"], "%g" % a["collimator"], "%g" % a["gantry"], "%g" % a["couch"]] + ["%g" % v for v in a["iso"]]
+        geo = {}
+        for key, extra in B1_BEAMLINES.items():
+            cmd = list(base)
+            if key == "rs_wet":
+                text = open(os.path.join(d, "machine.txt")).read()
+                i, j = text.index("[rangeshifter_thickness]"), text.index("[spot]")
+                with open(os.path.join(d, "machine_nors.txt"), "w") as f:
+                    f.write(text[:i] + text[j:])
+                cmd[1] = os.path.join(d, "machine_nors.txt")
+            o = subprocess.check_output(cmd + extra, stderr=subprocess.DEVNULL).decode()
+            geo[key] = "\n".join(ln for ln in o.splitlines() if ln.startswith("geo "))
+            print("b1", key, geo[key].replace("\n", " | "))
     np.savez_compressed(os.path.join(GOLD, "b1_beam_model.npz"), text=np.frombuffer("\n".join(lines).encode(), dtype=np.uint8),
-                        meta=np.array(str(a)))
+                        meta=np.array(str(a)), **{"geo_" + k: np.frombuffer(v.encode(), dtype=np.uint8) for k, v in geo.items()})
     print("b1", len(lines), lines[0], lines[1])
 
 

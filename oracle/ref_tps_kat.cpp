@@ -82,6 +82,39 @@ main(int argc, char* argv[]) {
         i = j;
     }
     for (auto* c : cps) beam.add("ctrl", c);
+    // optional beamline devices: --rs-id ID... | --rs-wet WET DIST (RangeShifterSettingsSequence of the first control
+    // point) and --block THICKNESS TRAY_DISTANCE x y x y ... (one IonBlockSequence item per --block)
+    int n_rs = 0, n_blk = 0;
+    for (int a = 11; a < argc;) {
+        const std::string o = argv[a++];
+        if (o == "--rs-id") {
+            while (a < argc && argv[a][0] != '-') {
+                mqi::dataset* r = new mqi::dataset;
+                r->set("RangeShifterID", { argv[a++] });
+                beam.add("rs", r);
+                ++n_rs;
+            }
+        } else if (o == "--rs-wet" && a + 1 < argc) {
+            mqi::dataset* ss = new mqi::dataset;
+            ss->set("RangeShifterWaterEquivalentThickness", { argv[a] }).set("IsocenterToRangeShifterDistance", { argv[a + 1] });
+            a += 2;
+            cps[0]->add("rsss", ss);
+            mqi::dataset* r = new mqi::dataset;
+            r->set("RangeShifterID", { "unlisted" });
+            beam.add("rs", r);
+            ++n_rs;
+        } else if (o == "--block" && a + 1 < argc) {
+            mqi::dataset* b = new mqi::dataset;
+            b->set("BlockThickness", { argv[a] }).set("IsocenterToBlockTrayDistance", { argv[a + 1] });
+            a += 2;
+            std::vector<std::string> xy;
+            while (a < argc && std::string(argv[a]).compare(0, 2, "--") != 0) xy.push_back(argv[a++]);
+            b->set("BlockNumberOfPoints", { std::to_string(xy.size() / 2) }).set("BlockData", xy);
+            beam.add("blk", b);
+            ++n_blk;
+        }
+    }
+    beam.set("NumberOfRangeShifters", { std::to_string(n_rs) }).set("NumberOfBlocks", { std::to_string(n_blk) });
 
     mqi::pbs<R>                  machine(machine_file);
     mqi::coordinate_transform<R> pc = machine.create_coordinate_transform(&beam, mqi::IONPLAN);
@@ -96,6 +129,17 @@ main(int argc, char* argv[]) {
         for (int k = 0; k < 6; ++k) printf(" %.9g", bl.fluence->mean_[k]);
         for (int k = 0; k < 6; ++k) printf(" %.9g", bl.fluence->sigma_[k]);
         printf("\n");
+    }
+    // create_beamline: characterize_rangeshifter / characterize_aperture, sorted upstream first (tmi:238-276)
+    mqi::beamline<R> line = machine.create_beamline(&beam, mqi::IONPLAN);
+    for (mqi::geometry* g : line.get_geometries()) {
+        if (g->geotype == mqi::RANGESHIFTER) {
+            const mqi::rangeshifter* r = dynamic_cast<const mqi::rangeshifter*>(g);
+            printf("geo rangeshifter %.9g %.9g %.9g %.9g %.9g %.9g\n", r->volume.x, r->volume.y, r->volume.z, g->pos.x, g->pos.y, g->pos.z);
+        } else if (g->geotype == mqi::BLOCK) {
+            const mqi::aperture* ap = dynamic_cast<const mqi::aperture*>(g);
+            printf("geo block %.9g %.9g %.9g %.9g %.9g %.9g\n", ap->volume.x, ap->volume.y, ap->volume.z, g->pos.x, g->pos.y, g->pos.z);
+        }
     }
     return 0;
 }

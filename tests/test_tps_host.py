@@ -515,3 +515,50 @@ def test_beam_source_matches_the_reference_beam_model_code(tmp_path, golden_dir)
         np.testing.assert_allclose(mine, ref[1:], rtol=2e-7, atol=1e-9)
         np.testing.assert_allclose(sp["trans"], ref_trans, atol=1e-6)
         np.testing.assert_allclose(np.array(sp["rot"]).reshape(3, 3), rot_matrix(a["collimator"], a["gantry"], a["couch"]), atol=3e-7)
+
+
+def test_beamline_devices_match_the_reference_create_beamline(tmp_path, golden_dir):
+    """Range shifter and aperture of a beam as the reference's own create_beamline / characterize_rangeshifter /
+    characterize_aperture (tmi:238-276, pbs:279-397) built them, unmodified, from a plan held in memory
+    (oracle/ref_tps_kat.cpp -> tests/golden/b1_beam_model.npz geo_*): thickness from the RangeShifterID table (one and
+    two IDs) or from the water-equivalent thickness / 1.15 when the machine file has no table, position from the
+    snout position and gap or from the isocentre distance, block thickness and tray distance, devices sorted upstream
+    first.  tps_env builds its beamline nodes from the same quantities in the text plan."""
+    g = np.load(os.path.join(golden_dir, "b1_beam_model.npz"))
+
+    def ref(key):
+        return [(ln.split()[1], [float(x) for x in ln.split()[2:]]) for ln in bytes(g["geo_" + key]).decode().splitlines()]
+
+    block = [(-10.0, -8.0), (10.0, -8.0), (10.0, 8.0), (-10.0, 8.0)]
+    cases = {"rs_id_block": dict(rangeshifter_ids=["RS1"], blocks=[block], block_thickness=20.0, block_tray_distance=60.0),
+             "rs_two_ids": dict(rangeshifter_ids=["RS1", "RS1"]),
+             "rs_wet": dict(rangeshifter_wet=(46.0, 120.0))}
+    for key, extra in cases.items():
+        root = str(tmp_path / key)
+        os.makedirs(root)
+        hu, origin = S.head_ct((32, 32, 20), (4.0, 4.0, 6.0), 1)
+        S.write_mha(os.path.join(root, "ct.mha"), hu, origin, (4.0, 4.0, 6.0))
+        S.write_beam_model(os.path.join(root, "machine.txt"))
+        if key == "rs_wet":   # no [rangeshifter_thickness] table: the thickness comes from the plan
+            text = open(os.path.join(root, "machine.txt")).read()
+            i, j = text.index("[rangeshifter_thickness]"), text.index("[spot]")
+            open(os.path.join(root, "machine.txt"), "w").write(text[:i] + text[j:])
+        beam = {"name": "B0", "gantry": 45.0, "couch": 10.0, "collimator": 15.0, "iso": (1.5, -2.5, 40.0), "snout": 250.0,
+                "spots": S.spot_list(n_layers=1, pitch=20.0, half_width=10.0, seed=3)}
+        beam.update(extra)
+        S.write_plan(os.path.join(root, "plan.txt"), [beam])
+        inp = os.path.join(root, "moqui_tps.in")
+        S.write_input(inp, root, os.path.join(root, "out"), ParticlesPerHistory=1e4)
+        nodes = dry_run(inp)["beams"][0]["beamline"]
+        want = ref(key)
+        assert len(nodes) == len(want), key
+        for n, (kind, v) in zip(nodes, want):          # same order: upstream first
+            lx, ly, lz, px, py, pz = v
+            np.testing.assert_allclose(n["pos_z"], pz, rtol=1e-6)
+            np.testing.assert_allclose(n["ze"], [pz - lz / 2, pz + lz / 2], rtol=1e-6)
+            np.testing.assert_allclose(n["xe"], [-lx / 2, lx / 2], rtol=1e-6)
+            np.testing.assert_allclose(n["ye"], [-ly / 2, ly / 2], rtol=1e-6)
+            if kind == "block":
+                assert n["n"][2] == int(lz) and n["open_voxels"] == 20 * 16 * int(lz)   # 1 mm voxels, 20 x 16 mm opening
+            else:
+                assert n["n"] == [1, 1, 1]
