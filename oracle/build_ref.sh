@@ -45,7 +45,21 @@ grep -q 'get_bool' "$TMP/moqui/base/mqi_file_parser_only.hpp" || { echo "patch 4
 #      beam_module_ion compile unmodified for ref_tps_kat.  Nothing else built here includes that header.
 cp "$HERE/ref_dataset_stub.hpp" "$TMP/moqui/base/mqi_dataset.hpp"
 CXX=${CXX:-g++}
-FLAGS="-std=c++11 -O2 -w -DNDEBUG -I$TMP -I$REF"
+FLAGS="-std=c++11 -O2 -w -DNDEBUG -pthread -I$TMP -I$REF"
+# The reference's own CUDA path for sm_100a (nvcc cross-compiles without a GPU): phantom_env.cpp compiled as CUDA
+# exactly as tests/mc/phantom/CMakeLists.txt:13-20 does (-w --use_fast_math, source language CUDA), plus
+# -maxrregcount=128: the kernel needs 168 registers, so its default 512-thread block does not launch without the
+# cap.  ref_harness.cpp compiled the same way drives the same kernel with CUDA events around it
+# (GPU baseline of bench.py, high-statistics goldens generated on the GPU box by oracle/gen_golden_gpu.py).
+NVCC=${NVCC:-$(command -v nvcc || echo /usr/local/cuda/bin/nvcc)}
+if [ -x "$NVCC" ] && [ -z "${MQI_REF_SKIP_CUDA:-}" ]; then
+    NVFLAGS="-x cu -std=c++14 -w --use_fast_math -gencode arch=compute_100a,code=sm_100a -maxrregcount=128 -DNDEBUG -I$TMP -I$REF"
+    for v in debug release; do
+        D=""; [ $v = debug ] && D="-D__PHYSICS_DEBUG__"
+        $NVCC $NVFLAGS $D "$REF/tests/mc/phantom/phantom_env.cpp" -o "$OUT/phantom_env_gpu_$v" -lz &
+        $NVCC $NVFLAGS $D "$HERE/ref_harness.cpp" -o "$OUT/ref_harness_gpu_$v" -lz &
+    done
+fi
 # phantom_env exactly as the reference's tests/mc/phantom CMake builds it (debug physics) ...
 $CXX $FLAGS -D__PHYSICS_DEBUG__ "$REF/tests/mc/phantom/phantom_env.cpp" -o "$OUT/phantom_env_cpu_debug" -lz &
 # ... and with the tps CMake's physics (no __PHYSICS_DEBUG__).

@@ -4,8 +4,18 @@
 // calls mc::transport_particles_patient directly with a scorer_offset_vector, exactly as
 // mqi_tps_env.hpp:1119-1135 does.  Test infrastructure only (oracle/_ref/ref_harness_*).
 //
-//   ref_harness <phantom_env flags...> --scorers dose|edep|letd|lett|dose+letd|dij [--nspots N] [--spot_pitch mm]
+//   ref_harness <phantom_env flags...> --scorers dose|edep|letd|lett|dose+letd|dose+dose2|stat|dij [--nspots N] [--spot_pitch mm]
 //               [--gauss sx sy sxp syp sigmaE]
+//               [--spot_grid nx ny pitch]      nx*ny spots on a grid (overrides --nspots / --spot_pitch)
+//               [--energy_step dE]             spot s gets spot_energy + s * dE
+//               [--batches B]                  B passes of --histories each, vertices resampled per pass, scorer tables
+//                                              accumulate (the reference's own batching, mqi_tps_env.hpp:1086-1140)
+//               [--sample_threads T]           host threads that run the reference sampler (each with its own
+//                                              beamsource copy and std::default_random_engine)
+//               [--stat_threshold t]           "stat": Dose + the two stat scorers through transport_particles_patient_stat,
+//                                              then (CUDA build) calculate_standard_deviation + the host part of calculate_stat
+// The same file compiles with nvcc -x cu (oracle/build_ref.sh: ref_harness_gpu_<variant>): run() then uploads and
+// launches the reference's own CUDA kernel (mqi_phantom_env.hpp:337-412) with CUDA events around the launch.
 //               [--rangeshifter zlo zhi half density_g_cm3]      one-voxel slab, create_rangeshifter style
 //               [--aperture zlo zhi half open_hx open_hy]        1 mm voxels, 1e-8 open / 100 closed
 //               [--frame r00 .. r22 tx ty tz]                    rotation_matrix_fwd / translation of both
@@ -15,12 +25,16 @@
 // Output (into --output_prefix):
 //   0_<name>.raw            dense float64 [nz][ny][nx] per scorer (reference save_reshaped_files)
 //   dij_key1.raw/_key2.raw/_value.raw    occupied (voxel, spot, value) triplets in slot order
-//   harness_stats.txt       wall seconds of the transport call, histories
+//   harness_stats.txt       histories, transport_seconds (CPU: wall of the call; CUDA: sum of the kernel's event times),
+//                           init_threads_seconds, run_seconds (sampling + uploads + kernels), blocks, threads
+//   stat_sd.raw / stat_mean.raw / stat_sum.raw / stat_sumsq.raw   "stat" mode (CUDA build)
 #include <chrono>
 #include <cstring>
 #include <fstream>
+#include <iomanip>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <moqui/base/environments/mqi_phantom_env.hpp>
@@ -39,7 +53,28 @@ struct extra_opts {
     float       ap[5]  = { 0, 0, 0, 0, 0 };       // zlo zhi half open_hx open_hy
     float       frame[12] = { 1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0 };
     std::string roi_mask;
+    int         grid[2]     = { 0, 0 };
+    float       grid_pitch  = 5.f;
+    float       energy_step = 0.f;
+    int         batches     = 1;
+    int         sample_threads = 1;
+    float       stat_threshold = 0.5f;
 };
+
+// the reference's hit functions: host addresses, or (CUDA build) the device addresses held by the
+// reference's own __device__ pointer symbols, scorers/mqi_scorer_energy_deposit.hpp:180-189
+#if defined(__CUDACC__)
+#define MQI_HIT(host_fn, dev_sym) hit_from_symbol(dev_sym)
+template<typename S>
+mqi::fp_compute_hit<float>
+hit_from_symbol(const S& sym) {
+    mqi::fp_compute_hit<float> fp;
+    gpu_err_chk(cudaMemcpyFromSymbol(&fp, sym, sizeof(fp)));
+    return fp;
+}
+#else
+#define MQI_HIT(host_fn, dev_sym) (host_fn)
+#endif
 
 class harness_env : public mqi::phantom_env<float>
 {
@@ -136,23 +171,39 @@ public:
         delete[] ph->scorers[0]->data_;
         ph->scorers[0]->data_ = nullptr;
         std::vector<mqi::scorer<R>*> v;
+        const mqi::fp_compute_hit<R> f_dw    = MQI_HIT(mqi::dose_to_water<R>, mqi::Dw_pointer);
+        const mqi::fp_compute_hit<R> f_dw2   = MQI_HIT(mqi::dose_to_water_square<R>, mqi::Dw_square_pointer);
+        const mqi::fp_compute_hit<R> f_edep  = MQI_HIT(mqi::energy_deposit<R>, mqi::energy_deposit_pointer);
+        const mqi::fp_compute_hit<R> f_letd1 = MQI_HIT(mqi::LETd_weight1<R>, mqi::LETd_weight1_pointer);
+        const mqi::fp_compute_hit<R> f_letd2 = MQI_HIT(mqi::LETd_weight2<R>, mqi::LETd_weight2_pointer);
+        const mqi::fp_compute_hit<R> f_lett1 = MQI_HIT(mqi::LETt_weight1<R>, mqi::LETt_weight1_pointer);
+        const mqi::fp_compute_hit<R> f_lett2 = MQI_HIT(mqi::LETt_weight2<R>, mqi::LETt_weight2_pointer);
         if (opt.scorers == "edep") {
-            v.push_back(make_scorer("Edep", nvox, mqi::energy_deposit<R>, nvox));
+            v.push_back(make_scorer("Edep", nvox, f_edep, nvox));
         } else if (opt.scorers == "letd") {
-            v.push_back(make_scorer("LETd_numer", nvox, mqi::LETd_weight1<R>, nvox));
-            v.push_back(make_scorer("LETd_denom", nvox, mqi::LETd_weight2<R>, nvox));
+            v.push_back(make_scorer("LETd_numer", nvox, f_letd1, nvox));
+            v.push_back(make_scorer("LETd_denom", nvox, f_letd2, nvox));
         } else if (opt.scorers == "lett") {   // track-averaged LET, scorers/mqi_scorer_energy_deposit.hpp:141-177
-            v.push_back(make_scorer("LETt_numer", nvox, mqi::LETt_weight1<R>, nvox));
-            v.push_back(make_scorer("LETt_denom", nvox, mqi::LETt_weight2<R>, nvox));
+            v.push_back(make_scorer("LETt_numer", nvox, f_lett1, nvox));
+            v.push_back(make_scorer("LETt_denom", nvox, f_lett2, nvox));
         } else if (opt.scorers == "dose+letd") {   // 3 scorers: exercises the double-scoring quirk
-            v.push_back(make_scorer("Dose", nvox, mqi::dose_to_water<R>, nvox));
-            v.push_back(make_scorer("LETd_numer", nvox, mqi::LETd_weight1<R>, nvox));
-            v.push_back(make_scorer("LETd_denom", nvox, mqi::LETd_weight2<R>, nvox));
+            v.push_back(make_scorer("Dose", nvox, f_dw, nvox));
+            v.push_back(make_scorer("LETd_numer", nvox, f_letd1, nvox));
+            v.push_back(make_scorer("LETd_denom", nvox, f_letd2, nvox));
+        } else if (opt.scorers == "dose+dose2") {   // dose_to_water_square, :64-77 (two scorers: no double scoring)
+            v.push_back(make_scorer("Dose", nvox, f_dw, nvox));
+            v.push_back(make_scorer("Dose2", nvox, f_dw2, nvox));
+        } else if (opt.scorers == "stat") {
+            // the scorer list of a tps run with StoppingStatistics (mqi_tps_env.hpp:846-905): the user's Dose, then the
+            // stat pair (dose, dose^2) that transport_particles_patient_stat keys by roi_->get_mask_idx(cnb)
+            v.push_back(make_scorer("Dose", nvox, f_dw, nvox));
+            v.push_back(make_scorer("StatDose", nvox, f_dw, nvox));
+            v.push_back(make_scorer("StatDose2", nvox, f_dw2, nvox));
         } else if (opt.scorers == "dij") {
             // the reference hard-codes 512*512*300*5 slots (mqi_tps_env.hpp:922); a smaller table keeps
             // the CPU harness in memory while exercising the same hash + probe code
-            uint32_t cap = nvox / 4 * (uint32_t) opt.nspots + 1024;
-            v.push_back(make_scorer("Dij", cap, mqi::dose_to_water<R>, nvox));
+            uint32_t cap = nvox / 4 * (uint32_t) n_spots() + 1024;
+            v.push_back(make_scorer("Dij", cap, f_dw, nvox));
         } else {
             throw std::runtime_error("unknown --scorers");
         }
@@ -162,37 +213,90 @@ public:
             ph->scorers[i] = v[i];
     }
 
-    virtual void
-    setup_beamsource() {
+    int
+    n_spots() const { return opt.grid[0] > 0 ? opt.grid[0] * opt.grid[1] : opt.nspots; }
+
+    // the beamlets of the run, appended to `bs` (called once per sampling thread: the reference's pdf objects hold
+    // stateful std distributions, so every thread samples from its own copy)
+    void
+    build_beamsource(mqi::beamsource<R>& bs) {
         mqi::coordinate_transform<R> p_coord(spot_angles, { 0, 0, 0 });
-        size_t per_spot = n_histories / opt.nspots;
-        for (int s = 0; s < opt.nspots; ++s) {
-            float              off  = (s - 0.5f * (opt.nspots - 1)) * opt.spot_pitch;
-            std::array<R, 6>   mean = { spot_position[0] + off, spot_position[1], spot_position[2], 0, 0, -1 };
+        const int ns = n_spots();
+        size_t per_spot = n_histories / ns;
+        for (int s = 0; s < ns; ++s) {
+            float offx, offy = 0.f;
+            if (opt.grid[0] > 0) {
+                offx = (s % opt.grid[0] - 0.5f * (opt.grid[0] - 1)) * opt.grid_pitch;
+                offy = (s / opt.grid[0] - 0.5f * (opt.grid[1] - 1)) * opt.grid_pitch;
+            } else {
+                offx = (s - 0.5f * (opt.nspots - 1)) * opt.spot_pitch;
+            }
+            const R            e0   = spot_energy[0] + s * opt.energy_step;
+            std::array<R, 6>   mean = { spot_position[0] + offx, spot_position[1] + offy, spot_position[2], 0, 0, -1 };
             std::array<R, 2>   corr = { 0.0, 0.0 };
             mqi::pdf_Md<R, 6>* phsp;
             mqi::pdf_Md<R, 1>* energy;
             if (opt.gauss) {
                 std::array<R, 6> sig = { opt.g[0], opt.g[1], 0.0, opt.g[2], opt.g[3], 0.0 };
                 phsp                 = new mqi::phsp_6d<R>(mean, sig, corr);
-                energy               = new mqi::norm_1d<R>({ spot_energy[0] }, { opt.g[4] });
+                energy               = new mqi::norm_1d<R>({ e0 }, { opt.g[4] });
             } else {
                 std::array<R, 6> sig = { spot_size[0], spot_size[1], 0.0, 0.0, 0.0, 0.0 };
                 phsp                 = new mqi::phsp_6d_uniform<R>(mean, sig, corr);
-                energy               = new mqi::const_1d<R>({ spot_energy[0] }, { spot_energy[1] });
+                energy               = new mqi::const_1d<R>({ e0 }, { spot_energy[1] });
             }
-            this->beamsource.append_beamlet(mqi::beamlet<R>(energy, phsp), per_spot, p_coord);
+            bs.append_beamlet(mqi::beamlet<R>(energy, phsp), per_spot, p_coord);
         }
+    }
+
+    std::vector<mqi::beamsource<R>*>           thread_sources;
+    std::vector<std::default_random_engine*>   thread_rngs;
+
+    // beamsource(h)(rng) for every history of a pass, mqi_phantom_env.hpp:225-232; with --sample_threads T the
+    // history range is cut into T contiguous parts, each sampled by its own thread
+    void
+    sample_vertices(int pass) {
+        const uint32_t h1 = this->beamsource.total_histories();
+        const int      T  = std::max(1, opt.sample_threads);
+        if (T == 1) {
+            for (size_t i = 0; i < h1; ++i) {
+                auto bl           = this->beamsource(i);
+                this->vertices[i] = bl(&this->beam_rng);
+            }
+            return;
+        }
+        if (thread_sources.empty()) {
+            for (int t = 0; t < T; ++t) {
+                thread_sources.push_back(new mqi::beamsource<R>);
+                build_beamsource(*thread_sources.back());
+                thread_rngs.push_back(new std::default_random_engine);
+            }
+        }
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t) {
+            thread_rngs[t]->seed((unsigned) this->random_seed + 1000003u * (unsigned) pass + 7919u * (unsigned) t + 1u);
+            const size_t a = (size_t) h1 * t / T, b = (size_t) h1 * (t + 1) / T;
+            th.emplace_back([this, t, a, b]() {
+                for (size_t i = a; i < b; ++i) {
+                    auto bl           = (*thread_sources[t])(i);
+                    this->vertices[i] = bl(thread_rngs[t]);
+                }
+            });
+        }
+        for (auto& x : th) x.join();
+    }
+
+    virtual void
+    setup_beamsource() {
+        build_beamsource(this->beamsource);
         uint32_t h1    = this->beamsource.total_histories();
         this->vertices = new mqi::vertex_t<R>[h1];
-        for (size_t i = 0; i < h1; ++i) {
-            auto bl           = this->beamsource(i);
-            this->vertices[i] = bl(&this->beam_rng);
-        }
+        sample_vertices(0);
     }
 
     virtual void
     run() {
+        auto     r0     = std::chrono::high_resolution_clock::now();
         uint32_t h1     = this->beamsource.total_histories();
         this->num_spots = this->beamsource.total_beamlets();
         uint32_t  tracked = 0;
@@ -203,27 +307,150 @@ public:
             for (size_t k = 0; k < n; ++k)
                 spot_of[idx++] = s;
         }
+        const bool per_spot = opt.scorers == "dij";
+        const bool stat     = opt.scorers == "stat";
+        double     init_threads_seconds = 0;
+#if defined(__CUDACC__)
+        // the reference's own launch sequence, mqi_phantom_env.hpp:337-412, with CUDA events around the kernel
+        std::vector<int32_t>       seeds(h1);
+        std::default_random_engine tmp_rng;
+        tmp_rng.seed(this->random_seed);
+        mqi::key_t* d_spot = nullptr;
+        if (per_spot) mc::upload_scorer_offset_vector(spot_of.data(), d_spot, h1);
+        mqi::thrd_t* wt;
+        gpu_err_chk(cudaMalloc(&wt, (size_t) threads[1] * threads[0] * sizeof(mqi::thrd_t)));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0);
+        initialize_threads<<<threads[1], threads[0]>>>(wt, threads[1] * threads[0], 0);
+        cudaEventRecord(e1);
+        gpu_err_chk(cudaDeviceSynchronize());
+        {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            init_threads_seconds = ms * 1e-3;
+        }
+        int32_t*  d_seed;
+        uint32_t* d_tracked;
+        gpu_err_chk(cudaMalloc(&d_seed, sizeof(int32_t) * (size_t) h1));
+        gpu_err_chk(cudaMalloc(&d_tracked, sizeof(uint32_t)));
+        gpu_err_chk(cudaMemset(d_tracked, 0, sizeof(uint32_t)));
+        printf("blocks %d threads %d\n", threads[1], threads[0]);
+        for (int pass = 0; pass < opt.batches; ++pass) {
+            if (pass > 0) sample_vertices(pass);
+            for (uint32_t i = 0; i < h1; ++i) seeds[i] = tmp_rng();
+            gpu_err_chk(cudaMemcpy(d_seed, seeds.data(), sizeof(int32_t) * (size_t) h1, cudaMemcpyHostToDevice));
+            mc::upload_vertices(this->vertices, mc::mc_vertices, 0, h1);
+            cudaEventRecord(e0);
+            if (stat)
+                mc::transport_particles_patient_stat<R><<<threads[1], threads[0]>>>(
+                  wt, mc::mc_world, mc::mc_vertices, mc::mc_materials, h1, d_tracked, d_seed, d_spot);
+            else
+                mc::transport_particles_patient<R><<<threads[1], threads[0]>>>(
+                  wt, mc::mc_world, mc::mc_vertices, mc::mc_materials, h1, d_tracked, d_seed, d_spot);
+            cudaEventRecord(e1);
+            cudaError_t err = cudaDeviceSynchronize();
+            if (err != cudaSuccess) {
+                std::cout << "CUDA error (transport): " << cudaGetErrorString(err) << std::endl;
+                exit(-1);
+            }
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            transport_seconds += ms * 1e-3;
+            gpu_err_chk(cudaFree(mc::mc_vertices));
+        }
+        gpu_err_chk(cudaMemcpy(&tracked, d_tracked, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (stat) stat_on_device((int) tracked);
+        if (d_spot) gpu_err_chk(cudaFree(d_spot));
+        gpu_err_chk(cudaFree(wt));
+        gpu_err_chk(cudaFree(d_seed));
+        gpu_err_chk(cudaFree(d_tracked));
+#else
         std::vector<int32_t> seeds(h1, 0);   // unused on the CPU path
         mc::mc_world     = this->world;
         mc::mc_vertices  = this->vertices;
         mc::mc_materials = this->materials;
         mqi::thrd_t* wt  = new mqi::thrd_t[1];
         wt[0].rnd_generator.seed((unsigned) this->random_seed * 2654435761u + 12345u);
-        auto t0 = std::chrono::high_resolution_clock::now();
-        mc::transport_particles_patient<R>(wt,
-                                           mc::mc_world,
-                                           mc::mc_vertices,
-                                           mc::mc_materials,
-                                           h1,
-                                           &tracked,
-                                           seeds.data(),
-                                           opt.scorers == "dij" ? spot_of.data() : nullptr);
-        auto t1           = std::chrono::high_resolution_clock::now();
-        transport_seconds = std::chrono::duration<double>(t1 - t0).count();
+        for (int pass = 0; pass < opt.batches; ++pass) {
+            if (pass > 0) sample_vertices(pass);
+            auto t0 = std::chrono::high_resolution_clock::now();
+            if (stat)
+                mc::transport_particles_patient_stat<R>(wt, mc::mc_world, mc::mc_vertices, mc::mc_materials, h1, &tracked,
+                                                        seeds.data(), nullptr);
+            else
+                mc::transport_particles_patient<R>(wt, mc::mc_world, mc::mc_vertices, mc::mc_materials, h1, &tracked,
+                                                   seeds.data(), per_spot ? spot_of.data() : nullptr);
+            auto t1 = std::chrono::high_resolution_clock::now();
+            transport_seconds += std::chrono::duration<double>(t1 - t0).count();
+        }
+#endif
+        auto r1 = std::chrono::high_resolution_clock::now();
         std::cout << "Number of particles tracked " << tracked << std::endl;
         std::ofstream st(this->output_path + "/harness_stats.txt");
-        st << "histories " << h1 << "\ntransport_seconds " << transport_seconds << "\n";
+        st << "histories " << (size_t) h1 * opt.batches << "\ntransport_seconds " << transport_seconds
+           << "\ninit_threads_seconds " << init_threads_seconds
+           << "\nrun_seconds " << std::chrono::duration<double>(r1 - r0).count()
+           << "\nblocks " << threads[1] << "\nthreads " << threads[0] << "\ntracked " << tracked << "\n";
+        {
+            mqi::coordinate_transform<R> pc(spot_angles, { 0, 0, 0 });   // the beam frame of build_beamsource
+            const mqi::mat3x3<R>& m = pc.rotation;
+            const R e[9] = { m.xx, m.xy, m.xz, m.yx, m.yy, m.yz, m.zx, m.zy, m.zz };
+            st << "rot";
+            for (int i = 0; i < 9; ++i) st << " " << std::setprecision(9) << e[i];
+            st << "\n";
+        }
+        if (stat_value >= 0) st << "stat_value " << std::setprecision(17) << stat_value << "\nstat_count " << stat_count
+                                << "\nstat_dose_max " << stat_dose_max << "\n";
     }
+
+    double stat_value = -1, stat_dose_max = 0;
+    long   stat_count = 0;
+#if defined(__CUDACC__)
+    // calculate_stat of tps_env (mqi_tps_env.hpp:1340-1426; that class needs GDCM and cannot be built): the reference's
+    // own calculate_standard_deviation kernel (kernel_functions/mqi_variables.hpp:20-48) launched as calculate_stat
+    // launches it for num_total_threads < 0 (:1371-1379), then the host reduction of :1409-1425 restated here.
+    void
+    stat_on_device(int n_histories) {
+        const int c_ind = this->world->n_children - 1;
+        const int roi   = this->world->children[c_ind]->scorers[1]->roi_->get_mask_size();
+        std::vector<float> sd(roi, 0.f), mean(roi);   // dose_mean is uploaded uninitialised by the reference; zeros here
+        float *            d_sd, *d_mean;
+        gpu_err_chk(cudaMalloc(&d_sd, sizeof(float) * roi));
+        gpu_err_chk(cudaMalloc(&d_mean, sizeof(float) * roi));
+        gpu_err_chk(cudaMemset(d_sd, 0, sizeof(float) * roi));
+        gpu_err_chk(cudaMemset(d_mean, 0, sizeof(float) * roi));
+        uint32_t n_threads = mqi::thread_limit;
+        uint32_t n_blocks  = (int) std::ceil(roi * 1.0 / n_threads);
+        if (n_blocks > mqi::block_limit) n_blocks = mqi::block_limit;
+        uint32_t vpt = (int) std::ceil(roi * 1.0 / (n_threads * n_blocks));
+        if (roi % (n_threads * n_blocks * vpt) > 0) n_blocks += 1;
+        calculate_standard_deviation<R><<<n_blocks, n_threads>>>(mc::mc_world, d_sd, d_mean, n_histories, roi, c_ind);
+        gpu_err_chk(cudaDeviceSynchronize());
+        gpu_err_chk(cudaMemcpy(sd.data(), d_sd, sizeof(float) * roi, cudaMemcpyDeviceToHost));
+        gpu_err_chk(cudaMemcpy(mean.data(), d_mean, sizeof(float) * roi, cudaMemcpyDeviceToHost));
+        cudaFree(d_sd);
+        cudaFree(d_mean);
+        double current = 0, dmax = 0;
+        long   count = 0;
+        for (int i = 0; i < roi; ++i)
+            if (dmax < mean[i]) dmax = mean[i];
+        for (int i = 0; i < roi; ++i)
+            if (mean[i] > dmax * opt.stat_threshold) {
+                current += (sd[i] / mean[i]);
+                count += 1;
+            }
+        stat_value    = (float) (current / count);
+        stat_count    = count;
+        stat_dose_max = dmax;
+        std::ofstream a(this->output_path + "/stat_sd.raw", std::ios::binary);
+        a.write((const char*) sd.data(), sizeof(float) * roi);
+        std::ofstream b(this->output_path + "/stat_mean.raw", std::ios::binary);
+        b.write((const char*) mean.data(), sizeof(float) * roi);
+        printf("stat %.9g count %ld dose_max %.9g n %d\n", stat_value, count, dmax, n_histories);
+    }
+#endif
 
     void
     save_dij_triplets() {
@@ -273,6 +500,18 @@ main(int argc, char* argv[]) {
             o.has_frame = true;
             for (int k = 0; k < 12; ++k)
                 o.frame[k] = std::stof(argv[++i]);
+        } else if (a == "--spot_grid" && i + 3 < argc) {
+            o.grid[0]    = std::stoi(argv[++i]);
+            o.grid[1]    = std::stoi(argv[++i]);
+            o.grid_pitch = std::stof(argv[++i]);
+        } else if (a == "--energy_step" && i + 1 < argc) {
+            o.energy_step = std::stof(argv[++i]);
+        } else if (a == "--batches" && i + 1 < argc) {
+            o.batches = std::stoi(argv[++i]);
+        } else if (a == "--sample_threads" && i + 1 < argc) {
+            o.sample_threads = std::stoi(argv[++i]);
+        } else if (a == "--stat_threshold" && i + 1 < argc) {
+            o.stat_threshold = std::stof(argv[++i]);
         } else if (a == "--roi_mask" && i + 1 < argc) {
             o.roi_mask = argv[++i];
         } else if (a == "--gauss" && i + 5 < argc) {
