@@ -197,6 +197,9 @@ struct mqi_handle {
     // cudaMalloc / cudaFree (both synchronise the device) per run
     std::multimap<size_t, void*> pool;
     size_t                       pool_bytes = 0;
+    // this device's slice of the summed stat grids (mqi_stat_multi): sum | sum of squares, stat_slice_n doubles each
+    double*                      d_stat_slice = nullptr;
+    size_t                       stat_slice_n = 0;
     mqi_run_stats           stats {};
 };
 
@@ -555,6 +558,7 @@ mqi_destroy(mqi_handle* h) {
     }
     cudaFree(h->d_tab_a0); cudaFree(h->d_tab_a1); cudaFree(h->d_tab_bs); cudaFree(h->d_tab_n0); cudaFree(h->d_tab_n1); cudaFree(h->d_correction); cudaFree(h->d_counters);
     cudaFree(h->d_beamlets); cudaFree(h->d_cum); cudaFree(h->d_vertices); cudaFree(h->d_spot_ids);
+    cudaFree(h->d_stat_slice);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->own_stream);
     delete h;
@@ -865,7 +869,7 @@ mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t cou
         p.src.vertices = h->d_vertices + first_history;
         p.src.spot_ids = h->d_spot_ids ? h->d_spot_ids + first_history : nullptr;
     }
-    const size_t smem = transport_smem_bytes(p.n_edge_floats, p.n_nodes);
+    const size_t smem = transport_smem_bytes(p.n_edge_floats, p.n_nodes, p.dij_wc_scorer >= 0);
     if (smem > 200 * 1024) return fail(MQI_EINVAL, "the world's grid edges do not fit into shared memory");
     int          bps  = 0;
     CU(transport_occupancy(p, h->variant, smem, &bps));
@@ -1100,6 +1104,7 @@ struct NcclApi {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*ReduceScatter)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -1126,6 +1131,7 @@ load_nccl() {
     MQI_SYM(CommDestroy, "ncclCommDestroy");
     MQI_SYM(Reduce, "ncclReduce");
     MQI_SYM(AllReduce, "ncclAllReduce");
+    MQI_SYM(ReduceScatter, "ncclReduceScatter");
     MQI_SYM(GroupStart, "ncclGroupStart");
     MQI_SYM(GroupEnd, "ncclGroupEnd");
     MQI_SYM(GetErrorString, "ncclGetErrorString");
@@ -1140,17 +1146,21 @@ load_nccl() {
         if (r__ != 0) return fail(MQI_ECUDA, std::string(#call) + ": " + g_nccl.GetErrorString(r__));   \
     } while (0)
 
+// the handles of one multi-GPU group: distinct devices, the same grid, dense scorers; communicators are created
+// on first use and cached for the device list
 int
-reduce_impl(mqi_handle* const* handles, int n, int scorer, int root, bool all) {
+prepare_group(mqi_handle* const* handles, int n, const int* scorer_ids, int n_scorers, size_t* count_out) {
     if (!handles || n < 1) return fail(MQI_EINVAL, "no handles");
-    if (root < 0 || root >= n) return fail(MQI_EINVAL, "root out of range");
     std::vector<int> devs(n);
     size_t           count = 0;
     for (int i = 0; i < n; ++i) {
         mqi_handle* h = handles[i];
         if (!h) return fail(MQI_EINVAL, "null handle");
-        if (scorer < 0 || scorer >= (int) h->scorers.size()) return fail(MQI_EINVAL, "bad scorer index");
-        if (h->scorers[scorer].kind == MQI_SCORER_DIJ) return fail(MQI_EINVAL, "Dij tables are sharded by spot, not reduced");
+        for (int k = 0; k < n_scorers; ++k) {
+            const int scorer = scorer_ids[k];
+            if (scorer < 0 || scorer >= (int) h->scorers.size()) return fail(MQI_EINVAL, "bad scorer index");
+            if (h->scorers[scorer].kind == MQI_SCORER_DIJ) return fail(MQI_EINVAL, "Dij tables are sharded by spot, not reduced");
+        }
         if (!h->has_grid) return fail(MQI_ESTATE, "no grid set");
         if (i == 0) count = nvox(h);
         else if (nvox(h) != count) return fail(MQI_EINVAL, "handles have different grids");
@@ -1159,9 +1169,12 @@ reduce_impl(mqi_handle* const* handles, int n, int scorer, int root, bool all) {
             if (devs[j] == devs[i]) return fail(MQI_EINVAL, "two handles on the same device");
         int rc = activate(h);
         if (rc) return rc;
+        rc = collect_run(h);
+        if (rc) return rc;
         rc = ensure_scorer_buffers(h);
         if (rc) return rc;
     }
+    *count_out = count;
     if (n == 1) return MQI_OK;
     int rc = load_nccl();
     if (rc) return rc;
@@ -1171,6 +1184,15 @@ reduce_impl(mqi_handle* const* handles, int n, int scorer, int root, bool all) {
         NC(g_nccl.CommInitAll(g_comms.data(), n, devs.data()));
         g_comm_devices = devs;
     }
+    return MQI_OK;
+}
+
+int
+reduce_impl(mqi_handle* const* handles, int n, int scorer, int root, bool all) {
+    if (root < 0 || root >= std::max(n, 1)) return fail(MQI_EINVAL, "root out of range");
+    size_t count = 0;
+    int    rc    = prepare_group(handles, n, &scorer, 1, &count);
+    if (rc || n == 1) return rc;
     NC(g_nccl.GroupStart());
     for (int i = 0; i < n; ++i) {
         mqi_handle* h = handles[i];
@@ -1186,6 +1208,87 @@ reduce_impl(mqi_handle* const* handles, int n, int scorer, int root, bool all) {
     }
     return MQI_OK;
 }
+
+// The stopping criterion over several devices without moving whole grids to one of them: every device keeps its
+// own running sums; one ncclReduceScatter per stat grid leaves each device with the summed values of 1/n of the
+// voxels (each link carries 1/n of the grid, all links at once), on which it evaluates its part of
+// calculate_stat; the host combines n x 3 doubles.  The few voxels left over when n does not divide the grid go to
+// device 0 with one small ncclReduce.
+int
+stat_multi_impl(mqi_handle* const* handles, int n, int s_sum, int s_sq, uint64_t n_histories, double threshold_fraction,
+                double out[3]) {
+    if (!out) return fail(MQI_EINVAL, "null argument");
+    if (n_histories < 2) return fail(MQI_ESTATE, "the stopping criterion needs at least two histories");
+    const int ids[2] = { s_sum, s_sq };
+    size_t    count  = 0;
+    int       rc     = prepare_group(handles, n, ids, 2, &count);
+    if (rc) return rc;
+    if (n == 1) return mqi_stat_partial(handles[0], s_sum, s_sq, n_histories, threshold_fraction, -1.0, out);
+    const size_t per = count / (size_t) n, tail = count - per * (size_t) n, cap = per + tail;
+    for (int i = 0; i < n; ++i) {
+        mqi_handle* h = handles[i];
+        CU(cudaSetDevice(h->device));
+        if (h->stat_slice_n < cap) {
+            cudaFree(h->d_stat_slice);
+            h->d_stat_slice = nullptr;
+            h->stat_slice_n = 0;
+            CU(cudaMalloc(&h->d_stat_slice, (2 * cap + 3) * sizeof(double)));
+            h->stat_slice_n = cap;
+        }
+    }
+    NC(g_nccl.GroupStart());
+    for (int i = 0; i < n; ++i) {
+        mqi_handle* h = handles[i];
+        CU(cudaSetDevice(h->device));
+        const double* sum = h->scorers[s_sum].d_dense;
+        const double* sq  = h->scorers[s_sq].d_dense;
+        double*       a   = h->d_stat_slice;
+        double*       b   = h->d_stat_slice + h->stat_slice_n;
+        if (per) {
+            NC(g_nccl.ReduceScatter(sum, a, per, kNcclFloat64, kNcclSum, g_comms[i], h->stream));
+            NC(g_nccl.ReduceScatter(sq, b, per, kNcclFloat64, kNcclSum, g_comms[i], h->stream));
+        }
+        if (tail) {
+            NC(g_nccl.Reduce(sum + per * n, a + per, tail, kNcclFloat64, kNcclSum, 0, g_comms[i], h->stream));
+            NC(g_nccl.Reduce(sq + per * n, b + per, tail, kNcclFloat64, kNcclSum, 0, g_comms[i], h->stream));
+        }
+    }
+    NC(g_nccl.GroupEnd());
+    // pass 1: the largest mean dose; pass 2: sum of sigma / mu and the number of voxels above the threshold
+    std::vector<double> host(3 * (size_t) n, 0.0);
+    double              max_mean = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = 0; i < n; ++i) {
+            mqi_handle* h = handles[i];
+            CU(cudaSetDevice(h->device));
+            const size_t cnt = per + (i == 0 ? tail : 0);
+            double*      a   = h->d_stat_slice;
+            double*      b   = a + h->stat_slice_n;
+            double*      d3  = b + h->stat_slice_n;
+            if (pass == 0) {
+                CU(cudaMemsetAsync(d3, 0, 3 * sizeof(double), h->stream));
+                if (cnt) CU(launch_stat_max(a, cnt, 1.0 / (double) n_histories, d3 + 2, h->stream));
+                CU(cudaMemcpyAsync(&host[3 * i + 2], d3 + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            } else {
+                if (cnt) CU(launch_stat_partial(a, b, cnt, (double) n_histories, threshold_fraction * max_mean, d3, h->stream));
+                CU(cudaMemcpyAsync(&host[3 * i], d3, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            }
+        }
+        for (int i = 0; i < n; ++i) {
+            CU(cudaSetDevice(handles[i]->device));
+            CU(cudaStreamSynchronize(handles[i]->stream));
+        }
+        if (pass == 0)
+            for (int i = 0; i < n; ++i) max_mean = std::max(max_mean, host[3 * i + 2]);
+    }
+    out[0] = out[1] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        out[0] += host[3 * i];
+        out[1] += host[3 * i + 1];
+    }
+    out[2] = max_mean;
+    return MQI_OK;
+}
 }   // namespace
 
 extern "C" {
@@ -1196,6 +1299,11 @@ mqi_reduce_dense(mqi_handle* const* handles, int n, int scorer, int root) {
 int
 mqi_allreduce_dense(mqi_handle* const* handles, int n, int scorer) {
     return reduce_impl(handles, n, scorer, 0, true);
+}
+int
+mqi_stat_multi(mqi_handle* const* handles, int n, int scorer_sum, int scorer_sumsq, uint64_t n_histories,
+               double threshold_fraction, double out[3]) {
+    return stat_multi_impl(handles, n, scorer_sum, scorer_sumsq, n_histories, threshold_fraction, out);
 }
 }
 

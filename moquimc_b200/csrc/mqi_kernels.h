@@ -27,6 +27,10 @@
 #define MQI_K_MIN_BLOCKS 1   /* 24 warps/SM at <= 80 registers/thread in ONE CTA: one copy of the shared-memory tables leaves the most L1; measured best of 128x5 ... 768x1 on B200 (profiles/r1_experiments.md) */
 #endif
 
+#ifndef MQI_K_PARK_DEPTH
+#define MQI_K_PARK_DEPTH 4   /* parked (voxel, spot, value) pairs per lane in front of the Dij table, see park_dij */
+#endif
+
 #ifndef MQI_K_LATE_LUT
 #define MQI_K_LATE_LUT 1   /* delay the material LUT load behind the step's random numbers (see mqi_transport.cu) */
 #endif
@@ -42,7 +46,7 @@ struct MatEntry;
 struct BeamletDev;
 struct VertexDev;
 
-size_t      transport_smem_bytes(int n_edge_floats, int n_nodes);
+size_t      transport_smem_bytes(int n_edge_floats, int n_nodes, bool dij_park = false);
 bool        transport_is_simple(const Params& p);
 cudaError_t transport_occupancy(const Params& p, int variant, size_t smem, int* blocks_per_sm);
 cudaError_t launch_transport(const Params& p, int variant, int grid, size_t smem, cudaStream_t st);

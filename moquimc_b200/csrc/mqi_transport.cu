@@ -27,6 +27,11 @@ struct Smem {
     const float*  edges;   // node k: xe | ye | ze at edges + nodes[k].edge_off (single node: offset 0)
     const GridDev* nodes;  // multi-node launches only
     uint32_t*     queue;   // kQueueWords words per warp
+    // DIJWC launches: finished (voxel, spot, value) pairs parked per lane until the warp inserts them together,
+    // structure of arrays, entry d of thread t at [d * MQI_K_BLOCK + t]
+    uint32_t*     park_k1;
+    uint32_t*     park_k2;
+    double*       park_val;
 };
 
 // queue of pre-sampled primaries, one per warp, structure of arrays: field f of entry e at
@@ -37,6 +42,8 @@ constexpr int kQueueCap    = 32;
 enum QueueField { Q_PX = 0, Q_PY, Q_PZ, Q_DX, Q_DY, Q_DZ, Q_KE, Q_IX, Q_IY, Q_IZ, Q_H0, Q_H1, Q_SPOT, Q_NODE, Q_FIELDS };
 constexpr int kQueueWords  = Q_FIELDS * kQueueCap;
 constexpr size_t kTableBytes = kTableN * (2 * sizeof(float4) + sizeof(float2));
+constexpr int    kParkDepth  = MQI_K_PARK_DEPTH;   // parked Dij pairs per lane (DIJWC launches)
+constexpr size_t kParkBytes  = (size_t) kParkDepth * MQI_K_BLOCK * (2 * sizeof(uint32_t) + sizeof(double));
 
 __host__ __device__ __forceinline__ size_t
 smem_nodes_offset(int n_edge_floats) { return (kTableBytes + (size_t) n_edge_floats * sizeof(float) + 15) & ~(size_t) 15; }
@@ -55,6 +62,9 @@ smem_view(unsigned char* raw, int n_edge_floats, int n_nodes) {
     sm.edges = reinterpret_cast<float*>(bs + kTableN);
     sm.nodes = reinterpret_cast<const GridDev*>(raw + smem_nodes_offset(n_edge_floats));
     sm.queue = reinterpret_cast<uint32_t*>(raw + smem_queue_offset(n_edge_floats, n_nodes));
+    sm.park_val = reinterpret_cast<double*>(sm.queue + (MQI_K_BLOCK / 32) * kQueueWords);   // 16-byte aligned: kQueueWords % 4 == 0
+    sm.park_k1  = reinterpret_cast<uint32_t*>(sm.park_val + kParkDepth * MQI_K_BLOCK);
+    sm.park_k2  = sm.park_k1 + kParkDepth * MQI_K_BLOCK;
     return sm;
 }
 
@@ -362,30 +372,54 @@ dense_add(double* __restrict__ acc, unsigned cnb, double v, int accum_mode) {
 // open-addressing (voxel, spot) -> dose table with a single 64-bit CAS per claim.  Same hash
 // function, home slot and linear probing as insert_hashtable (mqi_transport.hpp:68-111), so the set
 // of occupied keys is identical; the reference's two independent 32-bit CAS (race B5) are replaced.
-__device__ __noinline__ void
-dij_add(DijSlot* table, unsigned long long capacity, uint32_t key1, uint32_t key2, double v,
-        unsigned long long* counters) {
+// Probing reads four consecutive slots at once (independent loads, two or three 32-byte sectors) and then takes the
+// first one in probe order that is free or holds the key: the same slot linear probing ends in -- a slot seen
+// occupied by another key stays so (keys are never removed), a slot seen free is claimed through the CAS, which
+// reports whoever won it -- with one dependent memory round trip for 85 % of the inserts at load factor 0.73
+// instead of 2.4.
+__device__ __forceinline__ void
+dij_add_inline(DijSlot* table, unsigned long long capacity, uint32_t key1, uint32_t key2, double v,
+               unsigned long long* counters) {
     unsigned long long slot;
     if (key2 == kEmptyKey32) {   // dense mode of the reference: slot = voxel, key2 := 0
         slot = key1;
         key2 = 0;
+        if (slot >= capacity) {   // a table smaller than the grid: count the hit instead of writing outside it
+            atomicAdd(counters + C_DIJ_FULL, 1ull);
+            return;
+        }
     } else {
         slot = hash_fun(key1, key2, capacity);
     }
     const unsigned long long key = ((unsigned long long) key2 << 32) | key1;
-    for (unsigned long long probes = 0; probes < capacity; ++probes) {
-        DijSlot*           e    = table + slot;
+    for (unsigned long long probes = 0; probes < capacity; probes += 4) {
+        unsigned long long sl[4], kk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            sl[i] = slot;
+            slot  = slot + 1 == capacity ? 0 : slot + 1;
+        }
         // L2 is the point of coherence of the table (the CAS and the adds are performed there): a cache-global
         // load sees every claimed key; a system-scope volatile load costs more and buys nothing
-        unsigned long long prev = __ldcg(&e->key);
-        if (prev == kEmptyKey64) prev = atomicCAS(&e->key, kEmptyKey64, key);
-        if (prev == kEmptyKey64 || prev == key) {
-            atomicAdd(&e->value, v);
-            return;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) kk[i] = __ldcg(&table[sl[i]].key);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            unsigned long long prev = kk[i];
+            if (prev == kEmptyKey64) prev = atomicCAS(&table[sl[i]].key, kEmptyKey64, key);
+            if (prev == kEmptyKey64 || prev == key) {
+                atomicAdd(&table[sl[i]].value, v);
+                return;
+            }
         }
-        slot = slot + 1 == capacity ? 0 : slot + 1;
     }
     atomicAdd(counters + C_DIJ_FULL, 1ull);   // the reference would spin forever here
+}
+
+__device__ __noinline__ void
+dij_add(DijSlot* table, unsigned long long capacity, uint32_t key1, uint32_t key2, double v,
+        unsigned long long* counters) {
+    dij_add_inline(table, capacity, key1, key2, v, counters);
 }
 
 struct StepResult {
@@ -422,33 +456,109 @@ lett_hit(int kind, float dE, float len, float rho) {
 struct DijCombine {
     uint32_t key;   // voxel of the pending hit, kEmptyKey32 = nothing pending
     double   val;
+    int      npark; // pairs this lane has parked in shared memory (<= kParkDepth)
 };
 
+// The finished pair of a lane -- its voxel changed, or its track ended -- is not inserted by that lane on its own
+// (a divergent region of 4.7 lanes in which the whole warp waited for a chain of DRAM round trips every turn,
+// profiles/r1_c4_dij_wc_source_hotspots.txt) but parked in the lane's shared-memory slots.  The warp empties all
+// slots together once a lane has filled its last one (the vote at the top of the turn): the probe sequences of
+// ~ 2.5 pairs per lane then run at full width and overlap their latencies.
 __device__ __forceinline__ void
-flush_dij(const Params& P, DijCombine& wc, uint32_t spot_ind) {
+park_dij(const Smem& sm, DijCombine& wc, uint32_t spot_ind) {
     if (wc.key != kEmptyKey32) {
-        const ScorerDev& S = P.sc[P.dij_wc_scorer];
-        dij_add(S.table, S.capacity, wc.key, spot_ind, wc.val, P.counters);
+        const int o = wc.npark * MQI_K_BLOCK + threadIdx.x;
+        sm.park_k1[o]  = wc.key;
+        sm.park_k2[o]  = spot_ind;
+        sm.park_val[o] = wc.val;
+        wc.npark += 1;
         wc.key = kEmptyKey32;
     }
 }
 
-template<int VARIANT, bool DIJWC>
+// called by the whole warp; returns with every lane's slots empty
+__device__ __noinline__ void
+flush_parked(const Params& P, int npark) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem       sm = smem_view(smem_raw, P.n_edge_floats, P.n_nodes);
+    const ScorerDev& S  = P.sc[P.dij_wc_scorer];
+    while (__any_sync(0xffffffffu, npark > 0)) {
+        if (npark > 0) {
+            npark -= 1;
+            const int o = npark * MQI_K_BLOCK + threadIdx.x;
+            dij_add_inline(S.table, S.capacity, sm.park_k1[o], sm.park_k2[o], sm.park_val[o], P.counters);
+        }
+    }
+}
+
+// Scorer sets known at compile time: the loop over P.sc with its kind dispatch, quirk and accumulation-mode tests
+// (~ 25 issue slots per scorer and step, and 30 spilled registers) is what the general kernel pays; the three
+// scorer lists the configs actually use get the same hit values from straight-line code.
+//   SET_DOSE       one dense Dose scorer, DIRECT roi                       (phantom_env; tps "Dose")
+//   SET_DOSE_LETD  Dose, LETd numerator, LETd denominator, DIRECT rois     (config 2; tps "Dose LETd")
+//   SET_DOSE_STAT  Dose, Dose (stat), Dose^2 (stat), any rois              (config 3: tps "Dose" with StoppingStatistics)
+//   SET_DIJ        one Dij scorer with write-combining (DIJWC)             (config 4: tps "Dij")
+enum ScorerSet { SET_GENERIC = 0, SET_DOSE = 1, SET_DOSE_LETD = 2, SET_DOSE_STAT = 3, SET_DIJ = 4 };
+
+// LETd_weight1 and LETd_weight2 of one step from one evaluation of the LET (same arithmetic as letd_hit)
+__device__ __noinline__ double
+letd_numer_hit(float dE, float len, float rho) {
+    const double let = (double) dE / (double) len / (double) (rho * 1000.0f);
+    if (!(let < 25.0)) return -1.0;   // neither scorer takes the step
+    return (double) dE * let;
+}
+
+// roi_->idx(cnb) > 0 (mqi_transport.hpp:205,216): a DIRECT roi returns cnb, so voxel 0 is never scored (B1); a
+// CONTOUR roi (mask_to_roi) accepts the voxels inside its runs
+__device__ __forceinline__ bool
+roi_accepts(const uint32_t* roi, unsigned cnb) {
+    return roi ? ((__ldg(roi + (cnb >> 5)) >> (cnb & 31u)) & 1u) != 0u : (int) cnb > 0;
+}
+
+template<int VARIANT, int SET, bool DIJWC>
 __device__ __forceinline__ void
-score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, float inv_vol, float rsp0,
+score_step(const Params& P, const Smem& sm, const MatEntry& M, unsigned cnb, uint32_t spot_ind, float inv_vol, float rsp0,
            const StepResult& r, DijCombine& wc) {
     // dose_to_water: (dE + local_dE) * 1.60218e-10 / (V * rho * rsp(rho, vtx0.ke))
     const float  kdose   = 1.60218e-10f * inv_vol * M.inv_rho;
     const double dose    = (double) ((r.dE + r.local_dE) * kdose / rsp0);
     const double dose_te = (VARIANT == MQI_K_DEBUG) ? (double) (r.te_debug * kdose * inv_rsp_at_zero_energy(M)) : 0.0;
+    if (SET == SET_DIJ) {
+        const double v = dose + dose_te;
+        if (!(v > 0.0) || !roi_accepts(P.sc[0].roi, cnb)) return;
+        if (wc.key == cnb) {
+            wc.val += v;
+        } else {
+            park_dij(sm, wc, spot_ind);
+            wc.key = cnb;
+            wc.val = v;
+        }
+        return;
+    }
+    if (SET == SET_DOSE_LETD) {
+        if ((int) cnb <= 0) return;
+        const double v = dose + dose_te;
+        if (v > 0.0) atomicAdd(P.sc[0].dense + cnb, v);
+        if (r.len > 0.f) {
+            const double numer = letd_numer_hit(r.dE, r.len, M.rho);
+            if (numer > 0.0) atomicAdd(P.sc[1].dense + cnb, numer);            // insert_hashtable: value <= 0 -> skip
+            if (numer >= 0.0 && r.dE > 0.f) atomicAdd(P.sc[2].dense + cnb, (double) r.dE);
+        }
+        return;
+    }
+    if (SET == SET_DOSE_STAT) {
+        const double v = dose + dose_te;
+        if (!(v > 0.0)) return;   // then the square is not positive either
+        if (roi_accepts(P.sc[0].roi, cnb)) atomicAdd(P.sc[0].dense + cnb, v);
+        if (roi_accepts(P.sc[1].roi, cnb)) atomicAdd(P.sc[1].dense + cnb, v);
+        if (roi_accepts(P.sc[2].roi, cnb)) atomicAdd(P.sc[2].dense + cnb, dose * dose + dose_te * dose_te);
+        return;
+    }
     const int    n       = P.n_scorers;
 #pragma unroll 1
     for (int s = 0; s < n; ++s) {
         const int kind = P.sc[s].kind;
-        // roi_->idx(cnb) > 0 (mqi_transport.hpp:205,216): a DIRECT roi returns cnb, so voxel 0 is never
-        // scored (B1); a CONTOUR roi (mask_to_roi) accepts the voxels inside its runs
-        const uint32_t* roi = P.sc[s].roi;
-        if (roi ? !((__ldg(roi + (cnb >> 5)) >> (cnb & 31u)) & 1u) : (int) cnb <= 0) continue;
+        if (!roi_accepts(P.sc[s].roi, cnb)) continue;
         double    v    = 0.0;
         if (kind == MQI_K_DOSE || kind == MQI_K_DIJ) v = dose + dose_te;
         else if (kind == MQI_K_DOSE_SQ) v = dose * dose + dose_te * dose_te;
@@ -463,7 +573,7 @@ score_step(const Params& P, const MatEntry& M, unsigned cnb, uint32_t spot_ind, 
                 if (wc.key == cnb) {
                     wc.val += v;
                 } else {
-                    flush_dij(P, wc, spot_ind);
+                    park_dij(sm, wc, spot_ind);
                     wc.key = cnb;
                     wc.val = v;
                 }
@@ -718,13 +828,16 @@ csda_row_fix(const float4* a1, int n, int n0, float r) {
 // ---------------------------------------------------------------------------------------------
 // the transport kernel
 // ---------------------------------------------------------------------------------------------
-// SIMPLE: exactly one dense Dose scorer with a DIRECT roi (phantom_env, and the tps "Dose" case): the
-// scorer loop and the other hit functions are compiled out of the voxel-step loop.
+// SET (ScorerSet): SET_DOSE -- exactly one dense Dose scorer with a DIRECT roi (phantom_env, and the tps "Dose"
+// case) -- compiles the scorer loop and the other hit functions out of the voxel-step loop; SET_DOSE_LETD and
+// SET_DOSE_STAT replace the loop by straight-line code; SET_GENERIC is the loop over P.sc.
 // MULTI: the world has beamline children (range shifter, aperture) in front of the scored grid; every
 // lane carries the index of the child it is in and reads that child's descriptor from shared memory.
-template<int VARIANT, bool SIMPLE, bool MULTI, bool DIJWC = false>
+template<int VARIANT, int SET, bool MULTI, bool DIJWC = false>
 __global__ void __launch_bounds__(MQI_K_BLOCK, MQI_K_MIN_BLOCKS)
 transport_kernel(const __grid_constant__ Params P) {
+    constexpr bool SIMPLE  = SET == SET_DOSE;
+    constexpr bool COUNTED = SET == SET_GENERIC;   // count_steps runs the general kernel
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem sm = smem_view(smem_raw, P.n_edge_floats, P.n_nodes);
     {
@@ -766,7 +879,7 @@ transport_kernel(const __grid_constant__ Params P) {
     const uint32_t k0 = (uint32_t) P.seed, k1 = (uint32_t) (P.seed >> 32);
     unsigned n_steps = 0;
     DijCombine wc;   // DIJWC instantiations only (a Dij scorer with write-combining): costs three registers
-    wc.key = kEmptyKey32; wc.val = 0.0;
+    wc.key = kEmptyKey32; wc.val = 0.0; wc.npark = 0;
 
     // the warp's queue of pre-sampled primaries: entries in the queue | history counter exhausted << 16
     // (warp-uniform; one register)
@@ -781,11 +894,19 @@ transport_kernel(const __grid_constant__ Params P) {
         // One vote is the join of the turn and the fast path in one: while every lane of the warp owns a track
         // (86 % of the turns at C1) the re-arm prologue -- two more votes and the tests around them, ~20 issue
         // slots -- is skipped altogether.
-        if (!__all_sync(0xffffffffu, fl & FL_ALIVE)) {
+        // (DIJWC: a lane whose last parking slot is taken sends the warp through the prologue as well, where all
+        // parked pairs are inserted)
+        if (!__all_sync(0xffffffffu, (fl & FL_ALIVE) && (!DIJWC || wc.npark < kParkDepth))) {
+        if (DIJWC) {
+            if (__any_sync(0xffffffffu, wc.npark == kParkDepth)) {
+                flush_parked(P, wc.npark);
+                wc.npark = 0;
+            }
+        }
         // ------------------------------------------------------------------ restart the lane
         bool need = false;   // the lane needs a new primary
         if (!(fl & (FL_ALIVE | FL_DONE))) {
-            if (DIJWC) flush_dij(P, wc, spot_ind);   // the track ended: insert its pending write-combined Dij hit
+            if (DIJWC) park_dij(sm, wc, spot_ind);   // the track ended: park its pending write-combined Dij hit
             if ((MULTI && (fl & FL_ADVANCE)) || sp > 0) {
                 TrackIO T;
                 T.px = px; T.py = py; T.pz = pz; T.dx = dx; T.dy = dy; T.dz = dz; T.ke = ke;
@@ -842,7 +963,7 @@ transport_kernel(const __grid_constant__ Params P) {
         // ------------------------------------------------------------------ one voxel step
         // the option "count_steps" runs the general kernel: the counter is a spilled register (LDL + IADD + STL
         // per step) that the single-Dose-scorer kernel does not pay for
-        if (!SIMPLE) ++n_steps;
+        if (COUNTED) ++n_steps;
         const GridDev& G  = node_ref<MULTI>(P, sm, node);
         const int      nx = G.nx, ny = G.ny, nz = G.nz;
         const float*   xe = sm.edges + (MULTI ? G.edge_off : 0);
@@ -1088,7 +1209,7 @@ transport_kernel(const __grid_constant__ Params P) {
                 asm("cvt.f64.f32 %0, %1;" : "=d"(v) : "f"(vf));
                 if (cnb != 0u && vf > 0.f) atomicAdd(P.sc[0].dense + cnb, v);   // warp-match accumulation runs the general kernel
             } else {
-                score_step<VARIANT, DIJWC>(P, M, cnb, spot_ind, inv_vol, rsp0, res, wc);
+                score_step<VARIANT, SET, DIJWC>(P, sm, M, cnb, spot_ind, inv_vol, rsp0, res, wc);
             }
         }
 
@@ -1108,8 +1229,9 @@ transport_kernel(const __grid_constant__ Params P) {
         }
     }
 
+    if (DIJWC) flush_parked(P, wc.npark);   // every track has ended and parked its last pair
     // per-lane step counter -> global (one atomic per lane per launch)
-    if (!SIMPLE && n_steps && P.count_steps) atomicAdd(P.counters + C_STEPS, (unsigned long long) n_steps);
+    if (COUNTED && n_steps && P.count_steps) atomicAdd(P.counters + C_STEPS, (unsigned long long) n_steps);
 }
 
 
@@ -1368,33 +1490,53 @@ static inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
 }
 
 size_t
-transport_smem_bytes(int n_edge_floats, int n_nodes) {
-    return smem_queue_offset(n_edge_floats, n_nodes) + (size_t) (MQI_K_BLOCK / 32) * kQueueWords * sizeof(uint32_t);
+transport_smem_bytes(int n_edge_floats, int n_nodes, bool dij_park) {
+    return smem_queue_offset(n_edge_floats, n_nodes) + (size_t) (MQI_K_BLOCK / 32) * kQueueWords * sizeof(uint32_t) +
+           (dij_park ? kParkBytes : 0);
 }
 
 typedef void (*transport_fn)(const Params);
-template<bool SIMPLE, bool MULTI, bool DIJWC>
+template<int SET, bool MULTI, bool DIJWC>
 static transport_fn
 pick_variant(int variant) {
-    return variant == MQI_K_DEBUG ? transport_kernel<MQI_K_DEBUG, SIMPLE, MULTI, DIJWC> : transport_kernel<MQI_K_RELEASE, SIMPLE, MULTI, DIJWC>;
+    return variant == MQI_K_DEBUG ? transport_kernel<MQI_K_DEBUG, SET, MULTI, DIJWC> : transport_kernel<MQI_K_RELEASE, SET, MULTI, DIJWC>;
 }
 static transport_fn
-pick_transport(int variant, bool simple, bool multi, bool dijwc) {
-    if (simple) return multi ? pick_variant<true, true, false>(variant) : pick_variant<true, false, false>(variant);
-    if (dijwc) return multi ? pick_variant<false, true, true>(variant) : pick_variant<false, false, true>(variant);
-    return multi ? pick_variant<false, true, false>(variant) : pick_variant<false, false, false>(variant);
+pick_transport(int variant, int set, bool multi, bool dijwc) {
+    if (dijwc && set == SET_DIJ) return multi ? pick_variant<SET_DIJ, true, true>(variant) : pick_variant<SET_DIJ, false, true>(variant);
+    if (dijwc) return multi ? pick_variant<SET_GENERIC, true, true>(variant) : pick_variant<SET_GENERIC, false, true>(variant);
+    switch (set) {
+    case SET_DOSE: return multi ? pick_variant<SET_DOSE, true, false>(variant) : pick_variant<SET_DOSE, false, false>(variant);
+    case SET_DOSE_LETD: return multi ? pick_variant<SET_DOSE_LETD, true, false>(variant) : pick_variant<SET_DOSE_LETD, false, false>(variant);
+    case SET_DOSE_STAT: return multi ? pick_variant<SET_DOSE_STAT, true, false>(variant) : pick_variant<SET_DOSE_STAT, false, false>(variant);
+    default: return multi ? pick_variant<SET_GENERIC, true, false>(variant) : pick_variant<SET_GENERIC, false, false>(variant);
+    }
+}
+
+// the compile-time scorer set a launch qualifies for (see ScorerSet)
+int
+transport_scorer_set(const Params& p) {
+    if ((p.quirks & MQI_K_QUIRK_B2) || p.accum_mode != MQI_K_ACCUM_ATOMIC || p.count_steps) return SET_GENERIC;
+    const ScorerDev* sc = p.sc;
+    if (p.n_scorers == 1 && sc[0].kind == MQI_K_DIJ && p.dij_wc_scorer == 0) return SET_DIJ;
+    if (p.n_scorers == 1 && sc[0].kind == MQI_K_DOSE && !sc[0].roi) return SET_DOSE;
+    if (p.n_scorers == 3 && sc[0].kind == MQI_K_DOSE && sc[1].kind == MQI_K_LETD_NUMER && sc[2].kind == MQI_K_LETD_DENOM &&
+        !sc[0].roi && !sc[1].roi && !sc[2].roi)
+        return SET_DOSE_LETD;
+    if (p.n_scorers == 3 && sc[0].kind == MQI_K_DOSE && sc[1].kind == MQI_K_DOSE && sc[2].kind == MQI_K_DOSE_SQ)
+        return SET_DOSE_STAT;
+    return SET_GENERIC;
 }
 
 // one dense Dose scorer with a DIRECT roi -> the kernels with the scorer loop compiled out
 bool
 transport_is_simple(const Params& p) {
-    return p.n_scorers == 1 && p.sc[0].kind == MQI_K_DOSE && !p.sc[0].roi && !(p.quirks & MQI_K_QUIRK_B2) &&
-           p.accum_mode == MQI_K_ACCUM_ATOMIC && !p.count_steps;
+    return transport_scorer_set(p) == SET_DOSE;
 }
 
 cudaError_t
 transport_occupancy(const Params& p, int variant, size_t smem, int* blocks_per_sm) {
-    transport_fn f = pick_transport(variant, transport_is_simple(p), p.n_nodes > 1, p.dij_wc_scorer >= 0);
+    transport_fn f = pick_transport(variant, transport_scorer_set(p), p.n_nodes > 1, p.dij_wc_scorer >= 0);
     cudaError_t  e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, f, MQI_K_BLOCK, smem);
@@ -1402,7 +1544,7 @@ transport_occupancy(const Params& p, int variant, size_t smem, int* blocks_per_s
 
 cudaError_t
 launch_transport(const Params& p, int variant, int grid, size_t smem, cudaStream_t st) {
-    pick_transport(variant, transport_is_simple(p), p.n_nodes > 1, p.dij_wc_scorer >= 0)<<<grid, MQI_K_BLOCK, smem, st>>>(p);
+    pick_transport(variant, transport_scorer_set(p), p.n_nodes > 1, p.dij_wc_scorer >= 0)<<<grid, MQI_K_BLOCK, smem, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -72,6 +72,47 @@ def gamma_2d(ref, ev, spacing_mm, dd=0.01, dta_mm=1.0, cut=0.10, window_mm=2.0, 
     return float((g[mask] <= 1.0).mean()), g, mask
 
 
+def gamma_3d(ref, ev, spacing_mm, dd=0.01, dta_mm=1.0, cut=0.10, step_mm=0.25, ref_max=None):
+    """Global 3-D gamma index of `ev` against `ref` (arrays [n0][n1][n2] on the same grid, spacing per axis) in the
+    voxels where ref > cut * max(ref): for every such reference voxel the minimum over the evaluated distribution,
+    linearly interpolated on a lattice of `step_mm` inside the distance-to-agreement sphere, of
+    sqrt((dose difference / (dd * max))^2 + (distance / dta)^2).  Voxels that agree at zero distance are settled
+    first; only the others are searched.  Returns (pass_rate, gamma array (nan outside the mask), mask)."""
+    from scipy.ndimage import map_coordinates
+    ref = np.asarray(ref, dtype=np.float64)
+    ev = np.asarray(ev, dtype=np.float64)
+    dmax = float(ref.max()) if ref_max is None else float(ref_max)
+    mask = ref > cut * dmax
+    tol = dd * dmax
+    g2 = np.full(ref.shape, np.nan)
+    g2[mask] = ((ev[mask] - ref[mask]) / tol) ** 2
+    pend = np.argwhere(mask & ~(g2 <= 1.0))   # nan-safe
+    if pend.size:
+        offs = []
+        r = [int(np.floor(dta_mm / step_mm))] * 3
+        for a in range(-r[0], r[0] + 1):
+            for b in range(-r[1], r[1] + 1):
+                for c in range(-r[2], r[2] + 1):
+                    d2 = (a * a + b * b + c * c) * step_mm ** 2
+                    if 0 < d2 < dta_mm ** 2:
+                        offs.append((d2 / dta_mm ** 2, a * step_mm / spacing_mm[0], b * step_mm / spacing_mm[1], c * step_mm / spacing_mm[2]))
+        offs.sort()
+        best = g2[tuple(pend.T)]
+        rv = ref[tuple(pend.T)]
+        alive = np.arange(len(pend))
+        for d2, a, b, c in offs:
+            if alive.size == 0:
+                break
+            p = pend[alive].T.astype(np.float64)
+            val = map_coordinates(ev, [p[0] + a, p[1] + b, p[2] + c], order=1, mode="nearest")
+            cand = d2 + ((val - rv[alive]) / tol) ** 2
+            best[alive] = np.minimum(best[alive], cand)
+            alive = alive[best[alive] > 1.0]
+        g2[tuple(pend.T)] = best
+    g = np.sqrt(g2)
+    return float((g[mask] <= 1.0).mean()), g, mask
+
+
 def fraction_within_sigma(a, a_se, b, b_se, nsig=2.0, cut=0.10):
     """Fraction of voxels (above cut * max) whose difference is within nsig combined standard errors."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)

@@ -1,0 +1,276 @@
+"""GPU parity tests against fixtures produced by the reference's OWN CUDA path on a B200 (oracle/_ref/ref_harness_gpu_*:
+the reference's transport_particles_patient / _stat kernels, scorers, host beam sampler and
+calculate_standard_deviation kernel compiled for sm_100a by oracle/build_ref.sh; fixtures generated on the GPU box by
+oracle/gen_golden_gpu.py, packed by oracle/pack_golden_gpu.py -- tests/golden/README.md).  Everything under test goes
+through the C ABI (moquimc_b200.capi -> libmqi_b200.so).
+
+  * C1 in 3-D at 1e9 / 6e8 reference histories: 3-D gamma 1 %/1 mm >= 99 % in the voxels above 10 % of the maximum,
+    R80 within 0.1 mm, >= 94.5 % of those voxels within 2 sigma of the combined statistical uncertainty;
+  * C2 in full: bone / lung slabs, 70 ... 230 MeV in steps of 10, Dose + LETd, 4e6 reference histories per energy;
+  * dose_to_water_square (the Dose^2 stat scorer), both physics variants;
+  * the stopping criterion: calculate_standard_deviation + calculate_stat evaluated by the reference's kernel on the
+    reference's own sums, against mqi_stat_partial on the same sums;
+  * a C3 / C4-like case: heterogeneous head CT, 20 oblique gaussian pbs beamlets, dense Dose in 3-D and Dij rows.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import dose_metrics as M
+from moquimc_b200 import capi, synthetic as S
+from test_gpu_parity import c1_beamlet, c1_engine
+from test_gpu_scorer_goldens import slab_hu
+
+pytestmark = pytest.mark.gpu
+
+
+def load(golden_dir, name):
+    path = os.path.join(golden_dir, name)
+    if not os.path.exists(path):
+        pytest.skip("fixture %s not generated" % name)
+    g = np.load(path)
+    return g, json.loads(str(g["meta"]))
+
+
+# ------------------------------------------------------------------------------------------------
+# C1, three-dimensional
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", ["debug", "release"])
+def test_c1_three_dimensional_gamma_against_reference_cuda(golden_dir, variant):
+    g, meta = load(golden_dir, "c1_water200_%s_3d.npz" % variant)
+    z0, z1, y0, y1, x0, x1 = meta["box"]
+    ref = g["q"].astype(np.float64) * (meta["dmax"] / meta["levels"])
+    ref_se = np.repeat(np.repeat(g["se_block"].astype(np.float64), 4, axis=1), 4, axis=2)
+    n_ref = float(meta["histories"])
+    e = c1_engine(capi.PHYSICS_DEBUG if variant == "debug" else capi.PHYSICS_RELEASE)
+    n = 1_000_000_000
+    per = 125_000_000
+    e.set_beamlets([c1_beamlet()], [n])
+    for b in range(n // per):
+        e.run(20261017, b * per, per)
+    full = e.get_dense(0) / n
+    mine = full[z0:z1, y0:y1, x0:x1]
+    idd = full.sum(axis=(1, 2))
+    # range and integral
+    assert abs(M.r80_mm(idd) - M.r80_mm(g["idd"])) < 0.1
+    assert abs(full.sum() / float(g["total"]) - 1.0) < 2e-3
+    # gamma 1 %/1 mm in every voxel above 10 % of the maximum dose
+    rate, gam, mask = M.gamma_3d(ref, mine, (1.0, 0.5, 0.5))
+    assert mask.sum() > 2_000_000
+    assert rate >= 0.99, rate
+    # per-voxel difference against the combined statistical uncertainty: same physics => the variance per history
+    # is the same, so this run's standard error is the reference's scaled by sqrt(n_ref / n)
+    se = ref_se * np.sqrt(1.0 + n_ref / n)
+    ok = mask & (ref_se > 0)
+    zscore = (mine - ref)[ok] / se[ok]
+    assert (np.abs(zscore) <= 2.0).mean() >= 0.945, (np.abs(zscore) <= 2.0).mean()
+    assert abs(zscore.mean()) < 0.1, zscore.mean()      # no systematic offset beyond a tenth of a sigma per voxel
+
+
+# ------------------------------------------------------------------------------------------------
+# C2, the whole energy sweep
+# ------------------------------------------------------------------------------------------------
+def test_c2_full_energy_sweep_against_reference_cuda(golden_dir):
+    g, meta = load(golden_dir, "c2_sweep_release.npz")
+    kinds = (capi.SCORER_DOSE, capi.SCORER_LETD_NUMER, capi.SCORER_LETD_DENOM)
+    # three scorers: the reference's non-stat kernel scores Dose twice per step (quirk B2)
+    e = c1_engine(capi.PHYSICS_RELEASE, hu=slab_hu(), scorers=kinds, quirks=capi.QUIRK_B2_DOUBLE_SCORE)
+    n_total, n_batches = 4_000_000, 8
+    per = n_total // n_batches
+    assert meta["energies"] == list(range(70, 231, 10))
+    for energy in meta["energies"]:
+        e.set_beamlets([c1_beamlet(float(energy), 10.0)], [n_total])
+        idd = {k: [] for k in range(3)}
+        xz = np.zeros((350, 200))
+        for b in range(n_batches):
+            e.clear_scorers()
+            e.run(1000 + energy, b * per, per)
+            for k in range(3):
+                d = e.get_dense(k) / per
+                idd[k].append(d.sum(axis=(1, 2)))
+                if k == 0 and ("E%d_Dose_xz" % energy) in g.files:
+                    xz += d.sum(axis=1) / n_batches
+        mean = {k: np.mean(idd[k], axis=0) for k in idd}
+        se = {k: np.std(idd[k], axis=0, ddof=1) / np.sqrt(n_batches) for k in idd}
+        pre = "E%d_" % energy
+        g_idd = g[pre + "Dose_idd"]
+        assert abs(M.r80_mm(mean[0]) - M.r80_mm(g_idd)) < 0.1, energy
+        assert abs(mean[0].sum() / float(g[pre + "Dose_total"]) - 1.0) < 2e-3, energy
+        rate, _, _ = M.gamma_1d(g_idd, mean[0], 1.0)
+        assert rate >= 0.99, (energy, rate)
+        if (pre + "Dose_xz") in g.files:
+            rate, _, _ = M.gamma_2d(g[pre + "Dose_xz"], xz, (1.0, 0.5))
+            assert rate >= 0.99, (energy, rate)
+        # depth bins within 2 sigma: both errors come from eight batches, so the ratio follows a t-like law with
+        # ~ 14 degrees of freedom, for which 93.6 % lie within two estimated sigmas
+        frac, z = M.fraction_within_sigma(g_idd, g[pre + "Dose_idd_se"], mean[0], se[0])
+        assert frac >= 0.90, (energy, frac)
+        # dose-averaged LET per depth bin where the beam deposits
+        gn, gd = g[pre + "LETd_numer_idd"], g[pre + "LETd_denom_idd"]
+        m = gd > 0.10 * gd.max()
+        let_ref, let_gpu = gn[m] / gd[m], mean[1][m] / mean[2][m]
+        rel_sigma = np.sqrt((g[pre + "LETd_numer_idd_se"][m] / gn[m]) ** 2 + (se[1][m] / mean[1][m]) ** 2)
+        dev = np.abs(let_gpu / let_ref - 1.0)
+        assert (dev < np.maximum(0.02, 4.0 * rel_sigma)).all(), (energy, dev.max(), rel_sigma[dev.argmax()])
+        assert np.median(dev) < 0.004, (energy, np.median(dev))
+        assert abs(mean[2].sum() / float(g[pre + "LETd_denom_total"]) - 1.0) < 2e-3, energy
+        assert abs(mean[1].sum() / float(g[pre + "LETd_numer_total"]) - 1.0) < max(5e-3, 4.0 * float(g[pre + "LETd_numer_total_se"]) / float(g[pre + "LETd_numer_total"])), energy
+
+
+# ------------------------------------------------------------------------------------------------
+# Dose^2 (dose_to_water_square, scorers/mqi_scorer_energy_deposit.hpp:64-77)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", ["release", "debug"])
+def test_dose_square_scorer_against_reference_cuda(golden_dir, variant):
+    g, meta = load(golden_dir, "c2_slabs150_dose2.npz")
+    phys = capi.PHYSICS_DEBUG if variant == "debug" else capi.PHYSICS_RELEASE
+    e = c1_engine(phys, hu=slab_hu(), scorers=(capi.SCORER_DOSE, capi.SCORER_DOSE_SQ))
+    n_total, n_batches = 4_000_000, 8
+    per = n_total // n_batches
+    e.set_beamlets([c1_beamlet(150.0, 10.0)], [n_total])
+    idd = {0: [], 1: []}
+    for b in range(n_batches):
+        e.clear_scorers()
+        e.run(55, b * per, per)
+        for k in (0, 1):
+            idd[k].append((e.get_dense(k) / per).sum(axis=(1, 2)))
+    mean = {k: np.mean(v, axis=0) for k, v in idd.items()}
+    se = {k: np.std(v, axis=0, ddof=1) / np.sqrt(n_batches) for k, v in idd.items()}
+    pre = variant + "_"
+    assert abs(mean[0].sum() / float(g[pre + "Dose_total"]) - 1.0) < 2e-3
+    assert abs(M.r80_mm(mean[0]) - M.r80_mm(g[pre + "Dose_idd"])) < 0.1
+    ref2, ref2_se = g[pre + "Dose2_idd"], g[pre + "Dose2_idd_se"]
+    # the sum of squared step doses is dominated by a few large deposits (delta electrons, the last steps): compare
+    # the total, then depth bin by depth bin within four combined sigmas or 3 %
+    tot_sig = np.hypot(float(g[pre + "Dose2_total_se"]), np.std([v.sum() for v in idd[1]], ddof=1) / np.sqrt(n_batches))
+    assert abs(mean[1].sum() - float(g[pre + "Dose2_total"])) < max(4.0 * tot_sig, 5e-3 * float(g[pre + "Dose2_total"]))
+    m = ref2 > 0.05 * ref2.max()
+    sig = np.hypot(ref2_se[m], se[1][m])
+    assert (np.abs(mean[1][m] - ref2[m]) < np.maximum(4.0 * sig, 0.03 * ref2[m])).all()
+    # and bin-wise unbiased: the mean signed deviation in units of sigma stays near zero
+    assert abs(np.mean((mean[1][m] - ref2[m]) / sig)) < 0.6
+
+
+# ------------------------------------------------------------------------------------------------
+# stopping criterion
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_stopping_criterion_against_the_reference_kernels(golden_dir, tag):
+    """The reference's transport_particles_patient_stat filled sum d / sum d^2, its calculate_standard_deviation
+    kernel (kernel_functions/mqi_variables.hpp:20-48) and the host reduction of calculate_stat
+    (mqi_tps_env.hpp:1409-1425) turned them into one number on a B200: the same sums loaded into a Dose and a Dose^2
+    scorer here must give that number through mqi_stat_partial."""
+    g, meta = load(golden_dir, "a15_stat_release.npz")
+    s1, s2 = g[tag + "_sum"], g[tag + "_sumsq"]
+    n, thr = int(g[tag + "_n"]), float(g[tag + "_threshold"])
+    nx, ny, nz = meta["nxyz"]
+    e = capi.Engine(0, physics=capi.PHYSICS_RELEASE)
+    lx, ly, lz = meta["lxyz"]
+    e.set_grid_hu(capi.uniform_edges(-lx / 2, lx / 2, nx), capi.uniform_edges(-ly / 2, ly / 2, ny), capi.uniform_edges(-lz, 0, nz),
+                  np.zeros((nz, ny, nx), dtype=np.int16))
+    a = e.add_scorer(capi.SCORER_DOSE, "Dose_stat")
+    b = e.add_scorer(capi.SCORER_DOSE_SQ, "DoseSquare_stat")
+    idx = np.nonzero(s1 > 0)[0].astype(np.uint32)
+    dense = np.full(idx.size, 0xFFFFFFFF, dtype=np.uint32)
+    e.dev_insert(a, idx, dense, s1[idx])
+    e.dev_insert(b, idx, dense, s2[idx])
+    np.testing.assert_array_equal(e.get_dense(a).ravel(), s1)
+    out = e.stat_partial(a, b, n, thr)
+    value = out[0] / out[1]
+    # the reference rounds sigma and the mean dose of every voxel to float before it divides them
+    np.testing.assert_allclose(value, float(g[tag + "_value"]), rtol=2e-6)
+    assert abs(out[1] - float(g[tag + "_count"])) <= 1        # a voxel exactly at the threshold may fall either way
+    np.testing.assert_allclose(out[2], float(g[tag + "_dose_max"]), rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# C3 / C4-like: heterogeneous CT, oblique gaussian beamlets
+# ------------------------------------------------------------------------------------------------
+def c3like_setup(meta, scorer, capacity=0):
+    nx, ny, nz = meta["nxyz"]
+    lx, ly, lz = meta["lxyz"]
+    hu, _ = S.head_ct(tuple(meta["nxyz"]), tuple(meta["spacing"]), seed=meta["hu_seed"])
+    e = capi.Engine(0, physics=capi.PHYSICS_RELEASE)
+    e.set_grid_hu(capi.uniform_edges(-lx / 2, lx / 2, nx), capi.uniform_edges(-ly / 2, ly / 2, ny),
+                  capi.uniform_edges(-lz / 2, lz / 2, nz), hu.astype(np.int16))
+    s = e.add_scorer(scorer, "s", capacity=capacity)
+    gx, gy, pitch = meta["grid"]
+    sx, sy, sxp, syp, se = meta["gauss"]
+    bl = []
+    for i in range(int(gx * gy)):
+        ox = (i % gx - 0.5 * (gx - 1)) * pitch
+        oy = (i // gx - 0.5 * (gy - 1)) * pitch
+        bl.append(capi.make_beamlet(meta["e0"] + i * meta["de"], [ox, oy, meta["spot_z"], 0, 0, -1], [sx, sy, 0, sxp, syp, 0],
+                                    uniform=False, sigma_energy=se, rot=np.array(meta["rot"], dtype=np.float32).reshape(3, 3)))
+    return e, s, bl
+
+
+def test_c3like_head_dense_dose_against_reference_cuda(golden_dir):
+    g, meta = load(golden_dir, "c3like_head_release.npz")
+    ref = g["dose_q"].astype(np.float64) * (meta["dose_max"] / meta["dose_levels"])
+    ref_se = g["dose_se"].astype(np.float64)
+    e, s, bl = c3like_setup(meta, capi.SCORER_DOSE)
+    per_spot = 2_000_000
+    n = per_spot * len(bl)
+    e.set_beamlets(bl, [per_spot] * len(bl))
+    e.run(seed=31, first=0, count=n)
+    mine = e.get_dense(s) / n
+    assert abs(mine.sum() / ref.sum() - 1.0) < 3e-3
+    rate, gam, mask = M.gamma_3d(ref, mine, (2.5, 1.0, 1.0))
+    assert mask.sum() > 20_000
+    assert rate >= 0.99, rate
+    se = ref_se * np.sqrt(1.0 + meta["histories_dose"] / n)
+    ok = mask & (ref_se > 0)
+    z = (mine - ref)[ok] / se[ok]
+    # eight reference runs per sigma estimate: 92.6 % of a t distribution with 7 degrees of freedom lie within 2
+    assert (np.abs(z) <= 2.0).mean() >= 0.90, (np.abs(z) <= 2.0).mean()
+    assert abs(np.median(z)) < 0.15, np.median(z)
+    # centre of mass of the dose (the beams come in obliquely through skull and air cavities)
+    zz, yy, xx = np.meshgrid(np.arange(ref.shape[0]), np.arange(ref.shape[1]), np.arange(ref.shape[2]), indexing="ij")
+    for ax, sp in ((zz, 2.5), (yy, 1.0), (xx, 1.0)):
+        assert abs((ax * mine).sum() / mine.sum() - (ax * ref).sum() / ref.sum()) * sp < 0.05
+
+
+def test_c3like_head_dij_rows_against_reference_cuda(golden_dir):
+    g, meta = load(golden_dir, "c3like_head_release.npz")
+    nx, ny, nz = meta["nxyz"]
+    e, s, bl = c3like_setup(meta, capi.SCORER_DIJ, capacity=40_000_001)
+    per_spot = 1_000_000
+    ns = len(bl)
+    e.set_beamlets(bl, [per_spot] * ns)
+    st = e.run(seed=32, first=0, count=per_spot * ns, per_spot=True)
+    assert st.dij_table_full == 0
+    k1, k2, v = e.get_sparse(s)
+    rows = np.zeros((ns, nz * ny * nx))
+    np.add.at(rows, (k2, k1), v / per_spot)
+    rows = rows.reshape(ns, nz, ny, nx)
+    n_ref = meta["histories_dij"] / ns
+    # row totals: dose per history of every spot (reference: 1e5 histories per spot)
+    tot, ref_tot = rows.reshape(ns, -1).sum(axis=1), g["dij_row_total"].astype(np.float64)
+    assert np.abs(tot / ref_tot - 1.0).max() < 0.01, np.abs(tot / ref_tot - 1.0).max()
+    assert abs(tot.sum() / ref_tot.sum() - 1.0) < 2e-3
+    # depth profile and beam's-eye projection of every row
+    idd, ref_idd = rows.sum(axis=(2, 3)), g["dij_row_idd"].astype(np.float64)
+    for i in range(ns):
+        assert M.gamma_1d(ref_idd[i], idd[i], 2.5, dd=0.02, dta_mm=2.5)[0] >= 0.97, i
+        a, b = rows[i].sum(axis=0), g["dij_row_xy"][i].astype(np.float64)
+        cy = lambda p: (np.arange(ny)[:, None] * p).sum() / p.sum()   # noqa: E731
+        cx = lambda p: (np.arange(nx)[None, :] * p).sum() / p.sum()   # noqa: E731
+        assert abs(cy(a) - cy(b)) < 0.15 and abs(cx(a) - cx(b)) < 0.15, i
+    # three rows voxel by voxel (the reference's row has 1e5 histories: compare where it is well populated)
+    full_ref = g["dij_rows_full_q"].astype(np.float64) * (meta["rows_max"] / meta["rows_levels"])
+    for j, i in enumerate(meta["rows_full"]):
+        r, m = full_ref[j], rows[i]
+        sel = r > 0.2 * r.max()
+        assert sel.sum() > 200
+        assert abs(m[sel].sum() / r[sel].sum() - 1.0) < 0.01, i
+        assert np.corrcoef(m[sel], r[sel])[0, 1] > 0.98, i
+    # the support of a row grows with the statistics; at equal statistics it would be equal: compare the number of
+    # voxels that hold 99 % of the row's dose instead
+    def support99(row):
+        srt = np.sort(row.ravel())[::-1]
+        return int(np.searchsorted(np.cumsum(srt), 0.99 * srt.sum())) + 1
+    for j, i in enumerate(meta["rows_full"]):
+        assert abs(support99(rows[i]) / support99(full_ref[j]) - 1.0) < 0.15, i
