@@ -89,6 +89,9 @@ def load():
         "mqi_stat_partial": [vp, i32, i32, u64, C.c_double, C.c_double, C.POINTER(C.c_double)],
         "mqi_stat_partial_buffers": [vp, vp, vp, u64, u64, C.c_double, C.c_double, C.POINTER(C.c_double)],
         "mqi_scale_scorer": [vp, i32, C.c_double],
+        "mqi_reduce_dense": [C.POINTER(vp), i32, i32, i32],
+        "mqi_allreduce_dense": [C.POINTER(vp), i32, i32],
+        "mqi_stat_multi": [C.POINTER(vp), i32, i32, i32, u64, C.c_double, C.POINTER(C.c_double)],
         "mqi_dev_hu_to_density": [vp, vp, u64, f32, vp],
         "mqi_dev_rsp": [vp, vp, vp, u64, vp, vp],
         "mqi_dev_grid_step": [vp, vp, vp, u64, vp, vp, vp, vp, vp, vp],
@@ -146,6 +149,29 @@ def make_beamlet(energy, mean, sigma, uniform=True, sigma_energy=0.0, corr=(0.0,
     b.rot = (C.c_float * 9)(*r)
     b.trans = (C.c_float * 3)(*trans)
     return b
+
+
+def _handles(engines):
+    return (C.c_void_p * len(engines))(*[e.h.value for e in engines])
+
+
+def reduce_dense(engines, scorer, root=0):
+    """Sum dense scorer `scorer` of the engines (one per GPU, one process) into engines[root]: one ncclReduce."""
+    L = load()
+    rc = L.mqi_reduce_dense(_handles(engines), len(engines), scorer, root)
+    if rc != 0:
+        raise MqiError(rc, L.mqi_last_error().decode())
+
+
+def stat_multi(engines, s_sum, s_sq, n_histories, threshold):
+    """calculate_stat over the summed stat grids of the engines without gathering them: reduce-scatter + slices.
+    Returns (sum of sigma/mu, selected voxels, largest mean dose)."""
+    L = load()
+    out = (C.c_double * 3)()
+    rc = L.mqi_stat_multi(_handles(engines), len(engines), s_sum, s_sq, n_histories, threshold, out)
+    if rc != 0:
+        raise MqiError(rc, L.mqi_last_error().decode())
+    return out[0], out[1], out[2]
 
 
 class Engine:
@@ -297,6 +323,11 @@ class Engine:
         assert out.size == self.nvox and out.dtype == np.float64
         self._check(self.L.mqi_get_dense(self.h, scorer, out.ctypes.data, scale))
         return out.reshape(self.shape)
+
+    def get_sparse_count(self, scorer):
+        nnz = C.c_uint64()
+        self._check(self.L.mqi_get_sparse_count(self.h, scorer, C.byref(nnz)))
+        return nnz.value
 
     def get_sparse(self, scorer, scale=1.0):
         nnz = C.c_uint64()

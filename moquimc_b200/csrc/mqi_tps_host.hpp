@@ -1087,7 +1087,10 @@ public:
             check(mqi_create(gpu_ids[d], &h), "mqi_create");
             handles.push_back(h);
             // tps_env is built without __PHYSICS_DEBUG__ (tests/mc/tps/CMakeLists.txt)
-            check(mqi_set_physics(h, MQI_PHYSICS_RELEASE, reference_quirks ? MQI_QUIRK_B2_DOUBLE_SCORE : 0u), "mqi_set_physics");
+            // B2 (scorers [0, n-2) scored twice) belongs to transport_particles_patient only: the _stat kernel a run
+            // with StoppingStatistics launches scores them once (mqi_transport.hpp:342-352)
+            check(mqi_set_physics(h, MQI_PHYSICS_RELEASE, reference_quirks && !record_statistics ? MQI_QUIRK_B2_DOUBLE_SCORE : 0u),
+                  "mqi_set_physics");
             check(mqi_set_grid_hu(h, grid.xe.data(), (int) grid.xe.size(), grid.ye.data(), (int) grid.ye.size(),
                                   grid.ze.data(), (int) grid.ze.size(), ct.hu.data(), density_scale, nullptr, nullptr),
                   "mqi_set_grid_hu");
@@ -1205,13 +1208,18 @@ public:
         for (size_t d = 1; d < handles.size(); ++d) check(mqi_clear_scorers(handles[d]), "mqi_clear_scorers");
     }
 
-    // calculate_stat: mean over the voxels with mean dose > StatThreshold * max of sigma / mu
+    // calculate_stat: mean over the voxels with mean dose > StatThreshold * max of sigma / mu.  The devices keep
+    // their own running sums; mqi_stat_multi reduce-scatters the stat pair and evaluates the criterion in slices, so
+    // no grid travels to one device between passes (the dense scorers are gathered once, after the last pass)
     float
     calculate_stat(uint64_t n_histories) {
-        double out[3] = { 0, 0, 0 };
-        check(mqi_stat_partial(handles[0], stat_sum, stat_sumsq, n_histories, stat_threshold, -1.0, out), "mqi_stat_partial");
+        double     out[3] = { 0, 0, 0 };
+        const auto t0     = std::chrono::high_resolution_clock::now();
+        check(mqi_stat_multi(handles.data(), (int) handles.size(), stat_sum, stat_sumsq, n_histories, stat_threshold, out), "mqi_stat_multi");
+        stat_ms_total += std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
         return out[1] > 0 ? (float) (out[0] / out[1]) : 0.f;
     }
+    double stat_ms_total = 0.0, gather_ms_total = 0.0;
 
     void
     run() {
@@ -1230,13 +1238,19 @@ public:
                 if (current_stat == 100.0f) printf("Running %lu histories for the first run\n", (unsigned long) total_histories);
                 else printf("Running additional %lu histories\n", (unsigned long) total_histories);
                 run_all(seed + (uint64_t) stat_passes);
-                gather_dense();
                 ++stat_passes;
                 current_stat = calculate_stat(tracked) * 100.0f;
                 printf("Number of particles tracked %lu\n", (unsigned long) tracked);
                 printf("Run %d: current uncertainty %f %%\n", stat_passes, current_stat);
             }
             last_stat_percent = current_stat;
+            {
+                const auto t0 = std::chrono::high_resolution_clock::now();
+                gather_dense();
+                gather_ms_total += std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+            }
+            printf("Stopping criterion: %d evaluations %f ms (reduce-scatter of the stat pair + partial sums), final gather of the dense scorers %f ms\n",
+                   stat_passes, stat_ms_total, gather_ms_total);
             // calculate_average_results: scorers [0, n-2) scaled by target / tracked histories
             const double w = (double) total_histories / (double) tracked;
             for (const auto& s : scorers)

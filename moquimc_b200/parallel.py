@@ -8,8 +8,9 @@ without a data-path collective:
     summed with ONE reduce per beam;
   * Dij: contiguous blocks of SPOTS per rank -- rows of the CSR are disjoint, no reduction;
   * robust scenarios: independent jobs, round-robin;
-  * statistical stopping: per pass, all-reduce the pass's sum / sum-of-squares grids, add them to the
-    running totals every rank keeps, evaluate calculate_stat (mqi_tps_env.hpp:1339-1426) on the totals.
+  * statistical stopping: every rank keeps the running sum / sum-of-squares grids of its own histories; per pass the
+    two grids are reduce-scattered, every rank evaluates calculate_stat (mqi_tps_env.hpp:1339-1426) on its slice of
+    the summed grids, three doubles are all-reduced.  The dose itself is reduced once, after the last pass.
 
 Nothing here computes physics; the transport itself is the CUDA library (capi.Engine).
 """
@@ -60,13 +61,44 @@ def criterion_from_partials(sum_ratio, count):
     return 100.0 * sum_ratio / count if count > 0 else 0.0
 
 
-class StoppingLoop:
-    """run_by_beam_stat (mqi_tps_env.hpp:1242-1336) across ranks.
+def slice_len(n, world):
+    """Elements per rank when n values are dealt to `world` ranks in equal slices (the last ones padded)."""
+    return (n + world - 1) // world
 
-    transport_pass(k, pass_sum, pass_sq) must ADD this rank's share of pass k into the two zeroed
-    grids and return the number of histories it transported; evaluate(total_sum, total_sq, n) returns
-    (sum of sigma/mu over selected voxels, number of selected voxels) -- on a GPU box this is
-    capi.Engine.stat_partial_buffers, the fused CUDA kernel."""
+
+def reduce_scatter_sum(out_slice, full, group=None):
+    """out_slice <- this rank's slice of the element-wise sum of `full` over the ranks.  `full` has
+    world * len(out_slice) elements.  NCCL: one ncclReduceScatter (every link carries 1/world of the grid);
+    gloo has no reduce-scatter, so the CPU tests all-reduce a copy and cut the slice out of it."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = out_slice.numel()
+    assert full.numel() == world * n
+    if world == 1:
+        out_slice.copy_(full)
+    elif dist.get_backend(group) == "nccl":
+        dist.reduce_scatter_tensor(out_slice, full, op=dist.ReduceOp.SUM, group=group)
+    else:
+        tmp = full.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        out_slice.copy_(tmp[rank * n:(rank + 1) * n])
+    return out_slice
+
+
+class StoppingLoop:
+    """run_by_beam_stat (mqi_tps_env.hpp:1242-1336) across ranks, without moving whole grids per pass.
+
+    Every rank keeps its OWN running sums (sum d, sum d^2 of the histories it transported: the scorers simply keep
+    accumulating).  After a pass the two grids are reduce-scattered, each rank evaluates calculate_stat
+    (mqi_tps_env.hpp:1339-1426) on its slice of the summed grids, and three numbers are all-reduced: the largest mean
+    dose (max), then the sum of sigma/mu and the number of voxels above the threshold (sum).
+
+    transport_pass(k) must ADD this rank's share of pass k into total_sum / total_sq and return the number of
+    histories it transported.  evaluate(sum_slice, sq_slice, n_histories, max_mean) returns (sum of sigma/mu over the
+    selected voxels, number of selected voxels, largest mean dose of the slice); with max_mean < 0 only the third
+    value is used.  On a GPU box evaluate is capi.Engine.stat_partial_buffers, the fused CUDA kernel.
+    total_sum / total_sq hold world * slice_len(nvox, world) elements (zero padding behind the grid)."""
 
     def __init__(self, criteria_percent, transport_pass, evaluate, max_passes=1000, group=None):
         self.criteria = criteria_percent
@@ -75,25 +107,38 @@ class StoppingLoop:
         self.max_passes = max_passes
         self.group = group
         self.history = []
+        self.stat_seconds = 0.0
 
-    def run(self, pass_sum, pass_sq, total_sum, total_sq):
+    def run(self, total_sum, total_sq):
+        import time
         import torch
         import torch.distributed as dist
         multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        world = dist.get_world_size(self.group) if multi else 1
+        n_slice = total_sum.numel() // world
+        assert n_slice * world == total_sum.numel() == total_sq.numel()
+        s_sum = torch.zeros(n_slice, dtype=total_sum.dtype, device=total_sum.device)
+        s_sq = torch.zeros_like(s_sum)
         tracked, current, k = 0, 100.0, 0
         while current > self.criteria and k < self.max_passes:
-            pass_sum.zero_()
-            pass_sq.zero_()
-            n = torch.tensor([self.transport_pass(k, pass_sum, pass_sq)], dtype=torch.int64, device=pass_sum.device)
+            n = torch.tensor([self.transport_pass(k)], dtype=torch.int64, device=total_sum.device)
+            if total_sum.is_cuda:
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
             if multi:
-                dist.all_reduce(pass_sum, op=dist.ReduceOp.SUM, group=self.group)
-                dist.all_reduce(pass_sq, op=dist.ReduceOp.SUM, group=self.group)
                 dist.all_reduce(n, op=dist.ReduceOp.SUM, group=self.group)
-            total_sum += pass_sum
-            total_sq += pass_sq
             tracked += int(n.item())
+            reduce_scatter_sum(s_sum, total_sum, self.group)
+            reduce_scatter_sum(s_sq, total_sq, self.group)
+            mx = torch.tensor([self.evaluate(s_sum, s_sq, tracked, -1.0)[2]], dtype=torch.float64, device=total_sum.device)
+            if multi:
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+            s, c, _ = self.evaluate(s_sum, s_sq, tracked, float(mx.item()))
+            part = torch.tensor([s, c], dtype=torch.float64, device=total_sum.device)
+            if multi:
+                dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
             k += 1
-            s, c = self.evaluate(total_sum, total_sq, tracked)
-            current = criterion_from_partials(s, c)
+            current = criterion_from_partials(float(part[0].item()), float(part[1].item()))
             self.history.append(current)
+            self.stat_seconds += time.perf_counter() - t0
         return tracked, current, k

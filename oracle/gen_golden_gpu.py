@@ -137,7 +137,8 @@ def c1(work, args):
         rate, th = best_rate(variant)
         K = 8
         per_batch = 12_500_000 if not args.tiny else 2000
-        total = min(args.c1_histories, rate * args.budget_s)
+        total = min(args.c1_histories_release if variant == "release" and args.c1_histories_release else args.c1_histories,
+                    rate * args.budget_s)
         B = max(1, int(round(total / (K * per_batch))))
         nx, ny, nz = C1["nxyz"]
         s1 = np.zeros(nx * ny * nz)
@@ -163,6 +164,7 @@ def c1(work, args):
         crop = mean[z0:z1, y0:y1, x0:x1]
         levels = 4095
         q = np.round(crop / dmax * levels).astype(np.uint16)
+        np.save(os.path.join(OUT, "c1_water200_%s_sums.npy" % variant), np.stack([s1, s2]).astype(np.float32)) if args.keep_sums else None
         vc = var[z0:z1, y0:y1, x0:x1]
         vb = vc.reshape(z1 - z0, (y1 - y0) // 4, 4, (x1 - x0) // 4, 4).mean(axis=(2, 4))
         meta = dict(variant=variant, histories=n_hist, runs=K, batches=B, per_batch=per_batch, energy=200.0, spot_size=30.0,
@@ -343,9 +345,11 @@ def main():
     ap.add_argument("what", nargs="+", choices=["probe", "c1", "c2sweep", "dose2", "stat", "c3like"])
     ap.add_argument("--budget-s", type=float, default=120.0, help="kernel seconds the C1 golden may take per variant")
     ap.add_argument("--c1-histories", type=float, default=1.0e9)
+    ap.add_argument("--c1-histories-release", type=float, default=0.0)
     ap.add_argument("--c1-variants", default="debug,release")
     ap.add_argument("--c2-histories", type=float, default=4.0e6)
     ap.add_argument("--probe-histories", type=float, default=1.0e7)
+    ap.add_argument("--keep-sums", action="store_true")
     ap.add_argument("--tiny", action="store_true", help="dry run of the script itself with a few thousand histories")
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)

@@ -4,7 +4,7 @@ The compute stand-in is the ORACLE (tests only): history h draws the same counte
 whoever transports it, so two ranks that shard a history range and sum-reduce their dense grids must
 reproduce the single-process grid to fp64 summation order -- the property the NCCL path of bench.py
 and tps_env relies on.  Also covered: whole-spot sharding for Dij (disjoint rows), the 21 robust
-scenarios round-robin, and the statistical stopping loop with per-pass all-reduces.
+scenarios round-robin, and the statistical stopping loop (rank-local running sums, reduce-scatter of the stat pair).
 """
 import os
 import sys
@@ -33,13 +33,16 @@ def small_setup():
     return O, g, keep, beamlets, [N_HIST // 3] * 3
 
 
-def numpy_criterion(total_sum, total_sq, n, threshold=0.5):
-    """calculate_standard_deviation + calculate_stat (mqi_variables.hpp:20-48, mqi_tps_env.hpp:1409-1425)"""
-    s, q = total_sum.numpy(), total_sq.numpy()
+def numpy_criterion(sum_slice, sq_slice, n, max_mean, threshold=0.5):
+    """calculate_standard_deviation + calculate_stat (mqi_variables.hpp:20-48, mqi_tps_env.hpp:1409-1425) on one
+    slice of the summed grids: (sum of sigma / mu, selected voxels, largest mean dose of the slice)"""
+    s, q = sum_slice.numpy(), sq_slice.numpy()
     mean = s / n
+    if max_mean < 0:
+        return 0.0, 0, float(mean.max())
     var = (q / n - mean * mean) / (n - 1.0)
-    sel = (mean > threshold * mean.max()) & (mean > 0)
-    return float((np.sqrt(np.maximum(var[sel], 0.0)) / mean[sel]).sum()), int(sel.sum())
+    sel = (mean > threshold * max_mean) & (mean > 0)
+    return float((np.sqrt(np.maximum(var[sel], 0.0)) / mean[sel]).sum()), int(sel.sum()), float(mean.max())
 
 
 def worker(rank, world, port, out_dir):
@@ -62,21 +65,23 @@ def worker(rank, world, port, out_dir):
         k1, k2, v = outs[0]["key1"], outs[0]["key2"], outs[0]["value"]
         assert len(k2) and k2.min() >= s0 and k2.max() < s0 + ns
         np.savez(os.path.join(out_dir, "dij_%d.npz" % rank), k1=k1, k2=k2, v=v)
-        # ---- statistical stopping: fresh streams per pass, per-pass all-reduce, identical decision on all ranks
+        # ---- statistical stopping: fresh streams per pass, rank-local running sums, reduce-scatter of the stat pair,
+        # identical decision on all ranks
+        n_pad = world * P.slice_len(nvox, world)
+        ts, tq = torch.zeros(n_pad, dtype=torch.float64), torch.zeros(n_pad, dtype=torch.float64)
 
-        def transport_pass(k, pass_sum, pass_sq):
+        def transport_pass(k):
             (a, b), _ = O.transport(g, O.VARIANT_RELEASE, beamlets, hps, seed=100 + k, h0=first, n=count,
                                     kinds=[O.SCORER_DOSE, O.SCORER_DOSE_SQ])
-            pass_sum += torch.from_numpy(np.ascontiguousarray(a.reshape(-1)))
-            pass_sq += torch.from_numpy(np.ascontiguousarray(b.reshape(-1)))
+            ts[:nvox] += torch.from_numpy(np.ascontiguousarray(a.reshape(-1)))
+            tq[:nvox] += torch.from_numpy(np.ascontiguousarray(b.reshape(-1)))
             return count
-        z = lambda: torch.zeros(nvox, dtype=torch.float64)   # noqa: E731
         loop = P.StoppingLoop(60.0, transport_pass, numpy_criterion, max_passes=6)
-        ts, tq = z(), z()
-        tracked, current, passes = loop.run(z(), z(), ts, tq)
+        tracked, current, passes = loop.run(ts, tq)
         np.save(os.path.join(out_dir, "stat_%d.npy" % rank), np.array([tracked, current, passes] + loop.history))
+        P.reduce_dense(ts, dst=0)          # the dose itself travels once, after the last pass
         if rank == 0:
-            np.save(os.path.join(out_dir, "stat_sum.npy"), ts.numpy())
+            np.save(os.path.join(out_dir, "stat_sum.npy"), ts[:nvox].numpy())
     finally:
         dist.destroy_process_group()
 
@@ -143,3 +148,10 @@ def test_stopping_loop_is_consistent_across_ranks(two_rank_outputs):
         (d,), _ = O.transport(g, O.VARIANT_RELEASE, beamlets, hps, seed=100 + k, h0=0, n=N_HIST, kinds=[O.SCORER_DOSE])
         tot += d.reshape(-1)
     np.testing.assert_allclose(np.load(os.path.join(two_rank_outputs, "stat_sum.npy")), tot, rtol=1e-12, atol=tot.max() * 1e-14)
+    # and the sliced criterion equals the criterion on whole grids
+    sq = np.zeros(NX * NY * NZ)
+    for k in range(int(passes)):
+        (d2,), _ = O.transport(g, O.VARIANT_RELEASE, beamlets, hps, seed=100 + k, h0=0, n=N_HIST, kinds=[O.SCORER_DOSE_SQ])
+        sq += d2.reshape(-1)
+    s, c, mx = numpy_criterion(torch.from_numpy(tot), torch.from_numpy(sq), int(tracked), float((tot / tracked).max()))
+    np.testing.assert_allclose(current, 100.0 * s / c, rtol=1e-9)
