@@ -22,6 +22,15 @@ are sharded by index range, no other collective: scaling is weak (per-GPU work f
   cpu_baseline  the reference's own CPU phantom_env (oracle/_ref, built from /root/reference with
          the two documented patches) on all host cores, bounded sample, rank 0, N = 1.
 
+  configs   (N = 1) short fixed-size legs of the other BASELINE configs after the headline: C2 (slabs, Dose + LETd),
+         C3 (head-and-neck CT through tps_env, Dose + the stat pair, one pass), C4 (Dij at the reference's table
+         size and at a table sized from the free HBM), range shifter + aperture; each with its kernel time and a
+         per-config roofline from its own steps/history (moquimc_b200/configs.py);
+  gpu_reference_baseline  (N = 1) the reference's own CUDA kernel compiled for sm_100a (oracle/_ref/ref_harness_gpu_debug,
+         -maxrregcount=128, its default launch shape) on the headline workload, CUDA-event time of its kernel;
+  strong    C3 with the 1 % statistical stopping criterion run to the criterion on N GPUs (strong scaling: the work is
+         fixed): time to criterion, passes, and the share of the collectives (moquimc_b200/parallel.py StoppingLoop).
+
 --impl reference times that CPU reference alone (all host cores, bounded sample per step).
 """
 import argparse
@@ -225,36 +234,185 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_issue(histories_per_launch, kernel_ms, sm_mhz, sm_count=148):
+def committed_capture(histories_per_launch):
+    """profiles/roofline_traffic.json (dram bytes and warp instructions per launch of the headline kernel from an
+    ncu --set full capture) if it was taken at this launch size AND from the kernel this library contains: the file
+    carries the SASS hash of the kernel it profiled (moquimc_b200.build.kernel_identity), a library built from other
+    source no longer matches and the capture is refused as stale instead of being quoted."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        d = json.load(open(p))
+    except Exception:
+        return None, "no committed capture"
+    if int(d.get("histories_per_launch", -1)) != int(histories_per_launch):
+        return None, "capture taken at another launch size"
+    from moquimc_b200 import build as B
+    ident = B.kernel_identity()
+    if ident is None:
+        return None, "cuobjdump unavailable: kernel identity unchecked, capture not used"
+    if d.get("sass_sha256") != ident["sass_sha256"]:
+        return None, "stale: the capture's kernel (%s...) is not the library's (%s...)" % (str(d.get("sass_sha256"))[:12], ident["sass_sha256"][:12])
+    return d, "profiles/roofline_traffic.json, kernel identity %s... verified" % ident["sass_sha256"][:12]
+
+
+def ncu_issue(capture, kernel_ms, sm_mhz, sm_count=148):
     """Issue-slot utilisation of the transport kernel, the bound that actually holds: warp
     instructions per launch from the committed ncu capture (smsp__inst_executed.sum at this launch size) over
     the live kernel time, against SMs x 4 schedulers x the SM clock sampled during the timed region."""
-    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    try:
-        d = json.load(open(p))
-        if int(d["histories_per_launch"]) != int(histories_per_launch) or not sm_mhz:
-            return None
-        achieved = float(d["warp_instructions_per_launch"]) / (kernel_ms * 1e-3)
-        peak = int(sm_count) * 4 * float(sm_mhz) * 1e6
-        return {"achieved_warp_inst_per_s": achieved, "peak_warp_inst_per_s": peak, "frac": achieved / peak,
-                "source": "smsp__inst_executed.sum of profiles/roofline_traffic.json over the live kernel time"}
-    except Exception:
+    if not capture or not sm_mhz:
         return None
+    achieved = float(capture["warp_instructions_per_launch"]) / (kernel_ms * 1e-3)
+    peak = int(sm_count) * 4 * float(sm_mhz) * 1e6
+    return {"achieved_warp_inst_per_s": achieved, "peak_warp_inst_per_s": peak, "frac": achieved / peak,
+            "source": "smsp__inst_executed.sum of profiles/roofline_traffic.json over the live kernel time"}
 
 
-def ncu_traffic(histories_per_launch):
-    """dram bytes per launch of the transport kernel from the committed ncu --set full capture, if it
-    was taken at this launch size (profiles/roofline_traffic.json), else None."""
-    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if not os.path.exists(p):
-        return None
+# --------------------------------------------------------------------------------------------------
+# the reference's own CUDA path on this GPU (oracle/_ref/ref_harness_gpu_debug): baseline, N = 1
+# --------------------------------------------------------------------------------------------------
+def gpu_reference_baseline(histories=10_000_000):
+    import numpy as np
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_harness_gpu_debug")
+    if not os.path.exists(exe):
+        return {"value": None, "kind": "reference-cuda", "note": "oracle/_ref/ref_harness_gpu_debug is missing (make -C oracle ref in the build container)"}
+    work = tempfile.mkdtemp(prefix="mqi_bench_refgpu_")
     try:
-        d = json.load(open(p))
-        if int(d["histories_per_launch"]) == int(histories_per_launch):
-            return float(d["dram_bytes_per_launch"])
-    except Exception:
-        pass
-    return None
+        ph = os.path.join(work, "phantom.raw")
+        np.zeros((NXYZ[2], NXYZ[1], NXYZ[0]), dtype=np.int16).tofile(ph)
+        cmd = [exe, "--lxyz", "100", "100", "350", "--pxyz", "0.0", "0.0", "-175", "--nxyz", "200", "200", "350",
+               "--spot_energy", str(ENERGY), "0.0", "--spot_position", "0", "0", "0.5", "--spot_size", str(SPOT), str(SPOT),
+               "--histories", str(int(histories)), "--phantom_path", ph, "--output_prefix", work, "--random_seed", "12345",
+               "--gpu_id", os.environ.get("LOCAL_RANK", "0"), "--scorers", "dose", "--sample_threads", str(min(host_cores(), 32))]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        if r.returncode != 0:
+            return {"value": None, "kind": "reference-cuda", "note": "failed rc=%d: %s" % (r.returncode, r.stdout[-300:])}
+        st = {}
+        for ln in open(os.path.join(work, "harness_stats.txt")):
+            t = ln.split()
+            if len(t) == 2:
+                st[t[0]] = float(t[1])
+        return {"value": st["histories"] / st["transport_seconds"], "unit": UNIT, "kind": "reference-cuda",
+                "threads": [int(st["threads"]), int(st["blocks"])], "regcap": 128, "histories": int(st["histories"]),
+                "kernel_s": st["transport_seconds"], "run_s": st["run_seconds"],
+                "value_incl_sampling_and_uploads": st["histories"] / st["run_seconds"],
+                "what": "the reference's transport_particles_patient<float> (nvcc -x cu --use_fast_math -maxrregcount=128, sm_100a, "
+                        "__PHYSICS_DEBUG__) on the bench workload, its default launch shape, CUDA events around its kernel "
+                        "(oracle/ref_harness.cpp); initialize_threads and the host vertex sampling are outside kernel_s"}
+    except Exception as ex:
+        return {"value": None, "kind": "reference-cuda", "note": "failed: %s" % ex}
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# the other BASELINE configs, N = 1 (moquimc_b200/configs.py)
+# --------------------------------------------------------------------------------------------------
+def config_legs(device, peak):
+    from moquimc_b200 import configs as K
+    legs = (("C2", lambda: K.c2(device)), ("C3", lambda: K.c3((device,))), ("C4_reference_table", lambda: K.c4(device, 393_216_001)),
+            ("C4_auto_table", lambda: K.c4(device, 1_600_000_001)), ("rangeshifter_aperture", lambda: K.rs_aperture(device)))
+    out = {}
+    for name, fn in legs:
+        try:
+            r = fn()
+            r.pop("passes", None)
+            if r.get("steps_per_history") and r.get("kernel_ms"):
+                alg = r["histories"] * r["steps_per_history"] * r["bytes_per_step"]
+                ach = alg / (r["kernel_ms"] * 1e-3) / 1e9
+                r["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                 "algorithmic_bytes_per_launch": alg,
+                                 "bytes_per_step": "4 B density + 16 B fp64 read-modify-write per dense scorer (SURVEY 8d)"}
+            out[name] = r
+        except Exception as ex:
+            out[name] = {"value": None, "note": "failed: %s" % str(ex)[-300:]}
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# strong scaling: C3 with the 1 % stopping criterion over the ranks
+# --------------------------------------------------------------------------------------------------
+def strong_c3(rank, world, local, dev, stream, seed, criteria=1.0):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from moquimc_b200 import capi, configs as K, parallel as P, synthetic as S
+    n3, sp3 = (512, 512, 200), (1.0, 1.0, 2.5)
+    hu, origin = S.head_ct(n3, sp3, seed=1)
+    edges = [(np.float32(origin[a] - sp3[a] / 2) + np.arange(n3[a] + 1, dtype=np.float32) * np.float32(sp3[a])).astype(np.float32) for a in range(3)]
+    spots = [None]
+    if rank == 0:   # the plan's beamlets as tps_env builds them (beam model, histories per spot): --dry-run, no GPU
+        root = tempfile.mkdtemp(prefix="mqi_strong_")
+        try:
+            K.c3_case(root)
+            inp = os.path.join(root, "c3.in")
+            S.write_input(inp, root, os.path.join(root, "out"), ParticlesPerHistory=400.0)
+            r = subprocess.run([K.TPS_ENV, "--dry-run", inp], capture_output=True, text=True, timeout=300)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("DRYRUN ")][-1]
+            spots[0] = json.loads(line[len("DRYRUN "):])["beams"][0]["spots"]
+        finally:
+            shutil.rmtree(root, ignore_errors=True)
+    if world > 1:
+        dist.broadcast_object_list(spots, src=0)
+    spots = spots[0]
+    bl = [capi.make_beamlet(s["energy"], s["mean"], s["sigma"], uniform=False, sigma_energy=s["sigma_energy"], rot=s["rot"],
+                            trans=s["trans"]) for s in spots]
+    hist = [s["histories"] for s in spots]
+    total = int(sum(hist))
+    nvox = n3[0] * n3[1] * n3[2]
+    n_pad = world * P.slice_len(nvox, world)
+    eng = capi.Engine(local, physics=capi.PHYSICS_RELEASE)
+    eng.set_stream(stream.cuda_stream)
+    d_hu = torch.from_numpy(hu.reshape(-1)).to(dev)
+    eng.set_grid_hu_device(edges[0], edges[1], edges[2], d_hu.data_ptr())
+    bufs = [torch.zeros(n_pad, dtype=torch.float64, device=dev) for _ in range(3)]
+    for kind, name, b in ((capi.SCORER_DOSE, "Dose", bufs[0]), (capi.SCORER_DOSE, "Dose_stat", bufs[1]), (capi.SCORER_DOSE_SQ, "DoseSquare_stat", bufs[2])):
+        eng.bind_scorer_buffer(eng.add_scorer(kind, name), b.data_ptr())
+    eng.set_beamlets(bl, hist)
+    first, count = P.history_shard(total, rank, world)
+    kernel_ms = []
+
+    def transport_pass(k):
+        st = eng.run(seed + k, first, count)
+        kernel_ms.append(st.kernel_ms)
+        return count
+
+    def evaluate(s, q, n, mx):
+        return eng.stat_partial_buffers(s.data_ptr(), q.data_ptr(), s.numel(), n, 0.5, mx)
+    eng.run(seed + 1000, first, min(count, 50_000))     # warm-up: module load, tables, NCCL channels
+    if world > 1:
+        w = torch.zeros(world * 1024, dtype=torch.float64, device=dev)
+        P.reduce_scatter_sum(w[:1024].clone(), w)
+        dist.reduce(w, dst=0)
+    for b in bufs:
+        b.zero_()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    loop = P.StoppingLoop(criteria, transport_pass, evaluate, max_passes=400)
+    tracked, current, passes = loop.run(bufs[1], bufs[2])
+    t1 = time.perf_counter()
+    if world > 1:
+        dist.reduce(bufs[0], dst=0, op=dist.ReduceOp.SUM)    # the dose travels once
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    tt = torch.tensor([t2 - t0, sum(kernel_ms) * 1e-3, loop.stat_seconds, t2 - t1], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_s, transport_s, stat_s, reduce_s = (float(x) for x in tt.tolist())
+    checksum = float(bufs[0][:nvox].sum().item()) if rank == 0 else 0.0
+    eng.set_stream(None)
+    eng.close()
+    return {"workload": "C3: synthetic head-and-neck CT 512x512x200, %d-spot PBS plan, Dose + the two stat scorers, release physics, "
+                        "statistical stopping at %g %% (StatThreshold 0.5), %d histories per pass" % (len(bl), criteria, total),
+            "scaling": "strong", "n_gpus": world, "criteria_percent": criteria, "uncertainty_percent": current, "passes": passes,
+            "histories": tracked, "time_to_criterion_s": total_s, "histories_per_s": tracked / total_s,
+            "transport_s": transport_s, "stat_s": stat_s, "final_reduce_s": reduce_s,
+            "collective_share": (stat_s + reduce_s) / total_s,
+            "collective": "per pass: ncclReduceScatter of the scored range of sum d and sum d^2 (%d of %d values) + three scalar "
+                          "all-reduces; once: ncclReduce of the dose grid" % (getattr(loop, "exchanged_values", 0), nvox) if world > 1
+                          else "none (1 GPU): the criterion is evaluated on the device",
+            "timer": "host wall clock between device synchronisations and barriers, max over ranks", "dose_checksum": checksum}
 
 
 def bench_b200(args):
@@ -321,7 +479,7 @@ def bench_b200(args):
         dist.barrier()
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    kernel_ms, launches = [], 0
+    kernel_ms, launches, overflows = [], 0, 0
     t_wall = time.perf_counter()
     for s in range(K):
         flush.fill_(s & 0xff)            # evict the dose / material volumes from L2 between steps (untimed)
@@ -331,6 +489,7 @@ def bench_b200(args):
         st = eng.run_stats()             # waits for the kernel; device time of this launch
         kernel_ms.append(st.kernel_ms)
         launches += st.launches
+        overflows += st.stack_overflows     # secondaries the per-lane stack had no room for (the reference drops them too, B10)
         assert st.histories == H, (st.histories, H)
     torch.cuda.synchronize()
     if world > 1:
@@ -397,8 +556,15 @@ def bench_b200(args):
     d2h = nvox * 8
     e2.close()
 
+    strong = None
+    if not args.no_strong:
+        try:
+            strong = strong_c3(rank, world, local, dev, stream, args.seed)
+        except Exception as ex:
+            strong = {"scaling": "strong", "n_gpus": world, "time_to_criterion_s": None, "note": "failed: %s" % str(ex)[-300:]}
     if rank == 0:
         peak, peak_src = measured_peaks()
+        capture, capture_note = committed_capture(H)
         k_ms = sum(kernel_ms) / len(kernel_ms)
         alg_bytes = H * STEPS_PER_HISTORY * BYTES_PER_STEP
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
@@ -419,12 +585,23 @@ def bench_b200(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(H), "peak_source": peak_src, "kernel": "transport_kernel<debug>",
+                         "traffic": float(capture["dram_bytes_per_launch"]) if capture else None, "traffic_source": capture_note,
+                         "peak_source": peak_src, "kernel": "transport_kernel<debug, SET_DOSE>",
                          "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "latency/issue bound, not HBM bound: the dose grid hot set stays in L2 (see DESIGN.md)",
-                         "issue_slots": ncu_issue(H, k_ms, (clocks or {}).get("sm_mhz"),
+                         "issue_slots": ncu_issue(capture, k_ms, (clocks or {}).get("sm_mhz"),
                                                   torch.cuda.get_device_properties(dev).multi_processor_count)},
+            "stack_overflows": overflows,
         }
+        if strong is not None:
+            line["strong"] = strong
+        if world == 1 and not args.no_configs:
+            line["configs"] = config_legs(local, peak)
+        if world == 1 and not args.no_gpu_baseline:
+            g = gpu_reference_baseline(args.gpu_ref_histories)
+            if g.get("value"):
+                g["this_over_reference_cuda"] = value / g["value"]
+            line["gpu_reference_baseline"] = g
         if world == 1 and not args.no_cpu_baseline:
             try:
                 procs = reference_procs()
@@ -453,6 +630,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--ref-histories-per-proc", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C2 / C3 / C4 / beamline legs (N = 1)")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference's own CUDA kernel (N = 1)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the C3 strong-scaling record")
+    ap.add_argument("--gpu-ref-histories", type=float, default=1e7)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

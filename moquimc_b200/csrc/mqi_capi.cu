@@ -156,6 +156,7 @@ struct mqi_handle {
     int          blocks_per_sm_override = 0;
     int          l2_persist = 0;               // option "l2_persist": pin the material volume in L2 with a persisting access window (measured: no gain at C1)
     size_t       l2_persist_max = 0, l2_window_max = 0;
+    bool         l2_window_set = false;   // this handle has put an access-policy window on its stream
     // physics tables
     float4* d_tab_a0 = nullptr;
     float4* d_tab_a1 = nullptr;
@@ -200,6 +201,7 @@ struct mqi_handle {
     // this device's slice of the summed stat grids (mqi_stat_multi): sum | sum of squares, stat_slice_n doubles each
     double*                      d_stat_slice = nullptr;
     size_t                       stat_slice_n = 0;
+    unsigned long long*          d_stat_range = nullptr;
     mqi_run_stats           stats {};
 };
 
@@ -486,6 +488,8 @@ mqi_device_memory(mqi_handle* h, uint64_t* free_bytes, uint64_t* total_bytes) {
     return MQI_OK;
 }
 
+static int create_impl(mqi_handle* h, int device_id);
+
 int
 mqi_create(int device_id, mqi_handle** out) {
     if (!out) return fail(MQI_EINVAL, "out is null");
@@ -500,6 +504,18 @@ mqi_create(int device_id, mqi_handle** out) {
     if (std::memcmp(k_tables_blob, "MQITBL1", 7) != 0) return fail(MQI_ESTATE, "embedded physics tables are corrupt");
     mqi_handle* h = new mqi_handle;
     h->device     = device_id;
+    const int rc  = create_impl(h, device_id);
+    if (rc != MQI_OK) {   // a failed step must not leak the handle, its stream and events or the tables already uploaded
+        const std::string why = g_err;
+        mqi_destroy(h);
+        return fail(rc, why);
+    }
+    *out = h;
+    return MQI_OK;
+}
+
+static int
+create_impl(mqi_handle* h, int device_id) {
     CU(cudaSetDevice(device_id));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device_id));
@@ -539,7 +555,6 @@ mqi_create(int device_id, mqi_handle** out) {
     CU(cudaMalloc(&h->d_counters, C_COUNT * sizeof(unsigned long long)));
     CU(cudaMemcpy(h->d_correction, correction_ptr(), 3996 * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaMemset(h->d_counters, 0, C_COUNT * sizeof(unsigned long long)));
-    *out = h;
     return MQI_OK;
 }
 
@@ -547,7 +562,7 @@ int
 mqi_destroy(mqi_handle* h) {
     if (!h) return MQI_OK;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     free_grid(h);
     pool_clear(h);
     free_beamline(h);
@@ -559,8 +574,11 @@ mqi_destroy(mqi_handle* h) {
     cudaFree(h->d_tab_a0); cudaFree(h->d_tab_a1); cudaFree(h->d_tab_bs); cudaFree(h->d_tab_n0); cudaFree(h->d_tab_n1); cudaFree(h->d_correction); cudaFree(h->d_counters);
     cudaFree(h->d_beamlets); cudaFree(h->d_cum); cudaFree(h->d_vertices); cudaFree(h->d_spot_ids);
     cudaFree(h->d_stat_slice);
-    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
-    cudaStreamDestroy(h->own_stream);
+    cudaFree(h->d_stat_range);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    cudaGetLastError();
     delete h;
     return MQI_OK;
 }
@@ -586,14 +604,18 @@ set_grid_hu_impl(mqi_handle* h, const float* xe, int n_xe, const float* ye, int 
     const size_t nv = nvox(h);
     CU(pool_alloc(h, &h->d_mat, nv * sizeof(uint16_t)));
     if (on_device) {
+        // the conversion kernel reads the volume as 16-byte vectors
+        if (reinterpret_cast<uintptr_t>(hu) & 15u) return fail(MQI_EINVAL, "the device HU volume must be 16-byte aligned");
         CU(launch_hu_to_material(static_cast<const int16_t*>(hu), h->d_mat, nv, h->stream));
     } else {
         int16_t* tmp = nullptr;   // staging buffer of the HU upload (the size differs from d_mat's by the +1 below, so the pool tells them apart)
         CU(pool_alloc(h, &tmp, nv * sizeof(int16_t) + 1));
-        CU(cudaMemcpyAsync(tmp, hu, nv * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream));
-        CU(launch_hu_to_material(tmp, h->d_mat, nv, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
+        // a failed copy or launch hands the staging buffer back before the error is returned
+        cudaError_t e = cudaMemcpyAsync(tmp, hu, nv * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = launch_hu_to_material(tmp, h->d_mat, nv, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         pool_free(h, tmp, nv * sizeof(int16_t) + 1);
+        if (e != cudaSuccess) return fail(MQI_ECUDA, std::string("HU volume upload: ") + cudaGetErrorString(e));
     }
     rc = upload_hu_lut(h, density_scale);
     if (rc) return rc;
@@ -847,6 +869,12 @@ mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t cou
         if (!h->d_beamlets) return fail(MQI_ESTATE, "no beam source set");
         if (first_history + count > h->total_histories) return fail(MQI_EINVAL, "history range exceeds the beam source");
     }
+    // a Dij scorer without spot ids runs in the reference's dense mode (slot = voxel, mqi_transport.hpp:78-81): the
+    // table must then cover the grid
+    if (!per_spot || (h->d_vertices && !h->d_spot_ids))
+        for (const auto& s : h->scorers)
+            if (s.kind == MQI_SCORER_DIJ && s.capacity < nvox(h))
+                return fail(MQI_EINVAL, "a Dij scorer run without per-spot keys uses slot = voxel: capacity must be >= the number of voxels");
     rc = collect_run(h);   // counters of a previous asynchronous launch are overwritten below
     if (rc) return rc;
     rc = ensure_scorer_buffers(h);
@@ -882,8 +910,11 @@ mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t cou
         // lane; keep it resident in L2 (persisting access window on the launching stream) while the fp64
         // dose grid streams through the rest.  Larger volumes than the persisting carve-out get a
         // proportional hit ratio.
+        // (the stream attribute is only touched when the option is on: the caller's own access-policy window on a
+        // stream bound with mqi_set_stream stays as it is otherwise)
         cudaStreamAttrValue attr;
         std::memset(&attr, 0, sizeof(attr));
+        bool set_window = false;
         if (h->l2_persist && h->l2_persist_max > 0 && h->l2_window_max > 0) {
             const size_t bytes  = std::min(nvox(h) * sizeof(uint16_t), h->l2_window_max);
             const size_t carve  = std::min(h->l2_persist_max, bytes);
@@ -893,11 +924,15 @@ mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t cou
                 attr.accessPolicyWindow.hitRatio  = (float) std::min(1.0, (double) carve / (double) bytes);
                 attr.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;
                 attr.accessPolicyWindow.missProp  = cudaAccessPropertyStreaming;
+                set_window = true;
             } else {
                 cudaGetLastError();
             }
         }
-        if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+        if (set_window || h->l2_window_set) {   // switching the option off clears the window this handle set before
+            if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+            h->l2_window_set = set_window;
+        }
     }
     CU(cudaMemsetAsync(h->d_counters, 0, C_COUNT * sizeof(unsigned long long), h->stream));
     CU(cudaEventRecord(h->ev0, h->stream));
@@ -1212,7 +1247,8 @@ reduce_impl(mqi_handle* const* handles, int n, int scorer, int root, bool all) {
 // The stopping criterion over several devices without moving whole grids to one of them: every device keeps its
 // own running sums; one ncclReduceScatter per stat grid leaves each device with the summed values of 1/n of the
 // voxels (each link carries 1/n of the grid, all links at once), on which it evaluates its part of
-// calculate_stat; the host combines n x 3 doubles.  The few voxels left over when n does not divide the grid go to
+// calculate_stat; the host combines n x 3 doubles.  Only the range of the grid that some device has scored into is
+// exchanged (the stat grids are zero outside the beam).  The few voxels left over when n does not divide the grid go to
 // device 0 with one small ncclReduce.
 int
 stat_multi_impl(mqi_handle* const* handles, int n, int s_sum, int s_sq, uint64_t n_histories, double threshold_fraction,
@@ -1224,12 +1260,37 @@ stat_multi_impl(mqi_handle* const* handles, int n, int s_sum, int s_sq, uint64_t
     int       rc     = prepare_group(handles, n, ids, 2, &count);
     if (rc) return rc;
     if (n == 1) return mqi_stat_partial(handles[0], s_sum, s_sq, n_histories, threshold_fraction, -1.0, out);
-    const size_t per = count / (size_t) n, tail = count - per * (size_t) n, cap = per + tail;
+    // the stat grids are zero outside the beam: find the range of chunks any device has touched and exchange only that
+    const size_t chunk = 4096;
+    for (int i = 0; i < n; ++i) {
+        mqi_handle* h = handles[i];
+        CU(cudaSetDevice(h->device));
+        if (!h->d_stat_range) CU(cudaMalloc(&h->d_stat_range, 2 * sizeof(unsigned long long)));
+        const unsigned long long init[2] = { ~0ull, 0ull };
+        CU(cudaMemcpyAsync(h->d_stat_range, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+        CU(launch_nonzero_range(h->scorers[s_sum].d_dense, count, chunk, h->d_stat_range, h->stream));
+    }
+    size_t lo = count, hi = 0;
+    for (int i = 0; i < n; ++i) {
+        mqi_handle* h = handles[i];
+        CU(cudaSetDevice(h->device));
+        unsigned long long r[2];
+        CU(cudaMemcpyAsync(r, h->d_stat_range, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (r[1] > r[0]) {
+            lo = std::min<size_t>(lo, (size_t) r[0] * chunk);
+            hi = std::max<size_t>(hi, std::min<size_t>(count, (size_t) r[1] * chunk));
+        }
+    }
+    if (hi <= lo) return fail(MQI_ESTATE, "stat scorers are empty");
+    const size_t span = hi - lo;
+    const size_t per = span / (size_t) n, tail = span - per * (size_t) n, cap = per + tail;
     for (int i = 0; i < n; ++i) {
         mqi_handle* h = handles[i];
         CU(cudaSetDevice(h->device));
         if (h->stat_slice_n < cap) {
             cudaFree(h->d_stat_slice);
+    cudaFree(h->d_stat_range);
             h->d_stat_slice = nullptr;
             h->stat_slice_n = 0;
             CU(cudaMalloc(&h->d_stat_slice, (2 * cap + 3) * sizeof(double)));
@@ -1240,8 +1301,8 @@ stat_multi_impl(mqi_handle* const* handles, int n, int s_sum, int s_sq, uint64_t
     for (int i = 0; i < n; ++i) {
         mqi_handle* h = handles[i];
         CU(cudaSetDevice(h->device));
-        const double* sum = h->scorers[s_sum].d_dense;
-        const double* sq  = h->scorers[s_sq].d_dense;
+        const double* sum = h->scorers[s_sum].d_dense + lo;
+        const double* sq  = h->scorers[s_sq].d_dense + lo;
         double*       a   = h->d_stat_slice;
         double*       b   = h->d_stat_slice + h->stat_slice_n;
         if (per) {
@@ -1419,9 +1480,14 @@ mqi_dev_insert(mqi_handle* h, int scorer, const uint32_t* key1, const uint32_t* 
     if (!key1 || !key2 || !value) return fail(MQI_EINVAL, "null argument");
     if (!h->has_grid) return fail(MQI_ESTATE, "no grid set");
     if (n == 0) return MQI_OK;
-    if (h->scorers[scorer].kind != MQI_SCORER_DIJ)
+    if (h->scorers[scorer].kind != MQI_SCORER_DIJ) {
         for (uint64_t i = 0; i < n; ++i)
             if (key1[i] >= nvox(h)) return fail(MQI_EINVAL, "voxel key out of range");
+    } else {   // the reference's dense mode inside a Dij table: slot = key1, which must lie inside the table
+        for (uint64_t i = 0; i < n; ++i)
+            if (key2[i] == 0xffffffffu && key1[i] >= h->scorers[scorer].capacity)
+                return fail(MQI_EINVAL, "dense-mode key (key2 = 0xffffffff) beyond the Dij table capacity");
+    }
     rc = ensure_scorer_buffers(h);
     if (rc) return rc;
     DevBuf<uint32_t> d1, d2;

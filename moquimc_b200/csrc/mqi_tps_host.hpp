@@ -117,7 +117,10 @@ public:
 };
 
 // ---------------------------------------------------------------------------------------------
-// CT volume from a MetaImage (.mha, ElementDataFile = LOCAL, float voxels cast to int16)
+// CT volume from a MetaImage (.mha, ElementDataFile = LOCAL).  The reference reads float voxels and casts them to
+// int16 (mqi_tps_env.hpp:615-701); MET_SHORT -- the common CT export -- is accepted as well, anything else, a
+// compressed payload or big-endian data is refused instead of being misread.  Values are clamped to int16 before
+// the cast (an out-of-range float -> int16 conversion is undefined behaviour).
 // ---------------------------------------------------------------------------------------------
 struct ct_volume {
     int                  nx = 0, ny = 0, nz = 0;
@@ -131,8 +134,9 @@ read_mha_ct(const std::string& path) {
     ct_volume     ct;
     std::ifstream fid(path, std::ios::binary);
     if (!fid) throw std::runtime_error("cannot open CT volume " + path);
-    std::string line;
+    std::string line, element_type = "MET_FLOAT";
     bool        local = false;
+    auto is_true = [](const std::string& v) { return strcasecmp(v.c_str(), "True") == 0 || v == "1"; };
     auto three = [](const std::string& v, double out[3]) {
         std::stringstream ss(v);
         ss >> out[0] >> out[1] >> out[2];
@@ -152,6 +156,12 @@ read_mha_ct(const std::string& path) {
         } else if (strcasecmp(key.c_str(), "DimSize") == 0) {
             three(value, t);
             ct.nx = (int) t[0]; ct.ny = (int) t[1]; ct.nz = (int) t[2];
+        } else if (strcasecmp(key.c_str(), "ElementType") == 0) {
+            element_type = value;
+        } else if (strcasecmp(key.c_str(), "CompressedData") == 0) {
+            if (is_true(value)) throw std::runtime_error("compressed .mha CT volumes are not supported: " + path);
+        } else if (strcasecmp(key.c_str(), "BinaryDataByteOrderMSB") == 0 || strcasecmp(key.c_str(), "ElementByteOrderMSB") == 0) {
+            if (is_true(value)) throw std::runtime_error("big-endian .mha CT volumes are not supported: " + path);
         } else if (strcasecmp(key.c_str(), "ElementDataFile") == 0) {
             if (strcasecmp(value.c_str(), "LOCAL") != 0) throw std::runtime_error("Mask files does not contain data.");
             local = true;
@@ -159,12 +169,22 @@ read_mha_ct(const std::string& path) {
         }
     }
     if (!local || ct.nx <= 0 || ct.ny <= 0 || ct.nz <= 0) throw std::runtime_error("bad .mha header in " + path);
-    const size_t       n = (size_t) ct.nx * ct.ny * ct.nz;
-    std::vector<float> tmp(n);
-    fid.read(reinterpret_cast<char*>(tmp.data()), n * sizeof(float));
-    if ((size_t) fid.gcount() != n * sizeof(float)) throw std::runtime_error("CT volume is truncated: " + path);
+    const size_t n = (size_t) ct.nx * ct.ny * ct.nz;
     ct.hu.resize(n);
-    for (size_t i = 0; i < n; ++i) ct.hu[i] = (int16_t) tmp[i];
+    if (strcasecmp(element_type.c_str(), "MET_SHORT") == 0) {
+        fid.read(reinterpret_cast<char*>(ct.hu.data()), n * sizeof(int16_t));
+        if ((size_t) fid.gcount() != n * sizeof(int16_t)) throw std::runtime_error("CT volume is truncated: " + path);
+    } else if (strcasecmp(element_type.c_str(), "MET_FLOAT") == 0) {
+        std::vector<float> tmp(n);
+        fid.read(reinterpret_cast<char*>(tmp.data()), n * sizeof(float));
+        if ((size_t) fid.gcount() != n * sizeof(float)) throw std::runtime_error("CT volume is truncated: " + path);
+        for (size_t i = 0; i < n; ++i) {
+            const float v = tmp[i];
+            ct.hu[i]      = v != v ? (int16_t) 0 : (int16_t) std::min(32767.0f, std::max(-32768.0f, v));
+        }
+    } else {
+        throw std::runtime_error("unsupported ElementType " + element_type + " in " + path + " (MET_FLOAT or MET_SHORT)");
+    }
     return ct;
 }
 

@@ -13,6 +13,8 @@
 #include "mqi_device.cuh"
 #include "mqi_kernels.h"
 
+#include <algorithm>
+
 namespace mqib
 {
 
@@ -1479,6 +1481,23 @@ stat_partial_kernel(const double* __restrict__ sum, const double* __restrict__ s
     }
 }
 
+// first and one-past-last chunk (of `chunk` elements) of a grid that holds a non-zero value: out[0] = min, out[1] = max
+// (initialised by the caller to ~0 and 0).  The stat grids are zero outside the beam, so a multi-GPU evaluation of the
+// stopping criterion only has to exchange this range.
+__global__ void
+nonzero_range_kernel(const double* __restrict__ a, size_t n, size_t chunk, unsigned long long* out) {
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    for (size_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const size_t b0 = c * chunk, b1 = min(n, b0 + chunk);
+        bool         any = false;
+        for (size_t i = b0 + threadIdx.x; i < b1 && !any; i += blockDim.x) any = a[i] != 0.0;
+        if (__syncthreads_or(any) && threadIdx.x == 0) {
+            atomicMin(out, (unsigned long long) c);
+            atomicMax(out + 1, (unsigned long long) c + 1ull);
+        }
+    }
+}
+
 // =============================================================================================
 // host launchers
 // =============================================================================================
@@ -1622,6 +1641,12 @@ cudaError_t
 launch_stat_partial(const double* sum, const double* sumsq, size_t n, double n_hist, double cut, double* d_out2,
                     cudaStream_t st) {
     stat_partial_kernel<<<grid_for(n), 256, 0, st>>>(sum, sumsq, n, n_hist, cut, d_out2);
+    return cudaGetLastError();
+}
+cudaError_t
+launch_nonzero_range(const double* a, size_t n, size_t chunk, unsigned long long* d_out2, cudaStream_t st) {
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    nonzero_range_kernel<<<(int) std::min<size_t>(nchunks, 148 * 8), 256, 0, st>>>(a, n, chunk, d_out2);
     return cudaGetLastError();
 }
 cudaError_t

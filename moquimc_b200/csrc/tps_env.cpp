@@ -61,6 +61,12 @@ dump_json(mqib::tps_env& env) {
         printf("]}");
     }
     printf("], \"scoring_roi_size\": %llu, \"stat_roi_size\": %llu", roi_scoring, roi_stat);
+    {
+        long long hu_sum = 0;
+        int       hu_min = 32767, hu_max = -32768;
+        for (int16_t v : env.ct.hu) { hu_sum += v; hu_min = std::min<int>(hu_min, v); hu_max = std::max<int>(hu_max, v); }
+        printf(", \"hu\": {\"sum\": %lld, \"min\": %d, \"max\": %d}", hu_sum, hu_min, hu_max);
+    }
     printf(", \"grid\": {\"n\": [%d, %d, %d], \"xe\": [%.9g, %.9g], \"ye\": [%.9g, %.9g], \"ze\": [%.9g, %.9g]}}\n", env.ct.nx, env.ct.ny,
            env.ct.nz, env.grid.xe.front(), env.grid.xe.back(), env.grid.ye.front(), env.grid.ye.back(), env.grid.ze.front(),
            env.grid.ze.back());

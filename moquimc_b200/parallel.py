@@ -98,7 +98,8 @@ class StoppingLoop:
     histories it transported.  evaluate(sum_slice, sq_slice, n_histories, max_mean) returns (sum of sigma/mu over the
     selected voxels, number of selected voxels, largest mean dose of the slice); with max_mean < 0 only the third
     value is used.  On a GPU box evaluate is capi.Engine.stat_partial_buffers, the fused CUDA kernel.
-    total_sum / total_sq hold world * slice_len(nvox, world) elements (zero padding behind the grid)."""
+    total_sum / total_sq hold world * slice_len(nvox, world) elements (zero padding behind the grid).  Only the
+    range of the grids that some rank has scored into is exchanged (scored_range)."""
 
     def __init__(self, criteria_percent, transport_pass, evaluate, max_passes=1000, group=None):
         self.criteria = criteria_percent
@@ -108,6 +109,32 @@ class StoppingLoop:
         self.group = group
         self.history = []
         self.stat_seconds = 0.0
+
+    CHUNK = 4096
+
+    def scored_range(self, total_sum, world):
+        """[lo, lo + span) with span a multiple of `world`: the part of the grid some rank has scored into, found in
+        chunks of CHUNK values (the stat grids are zero outside the beam, so only this range is exchanged)."""
+        import torch
+        import torch.distributed as dist
+        n = total_sum.numel()
+        m = n // self.CHUNK
+        lo, hi = n, 0
+        if m:
+            nz = torch.nonzero(total_sum[:m * self.CHUNK].view(m, self.CHUNK).amax(dim=1) > 0)
+            if nz.numel():
+                lo, hi = int(nz[0].item()) * self.CHUNK, (int(nz[-1].item()) + 1) * self.CHUNK
+        if m * self.CHUNK < n and bool((total_sum[m * self.CHUNK:].amax() > 0).item()):
+            lo, hi = min(lo, m * self.CHUNK), n
+        if world > 1:
+            r = torch.tensor([-lo, hi], dtype=torch.int64, device=total_sum.device)
+            dist.all_reduce(r, op=dist.ReduceOp.MAX, group=self.group)
+            lo, hi = -int(r[0].item()), int(r[1].item())
+        if hi <= lo:
+            lo, hi = 0, n
+        span = ((hi - lo + world - 1) // world) * world
+        lo = max(0, min(lo, n - span))
+        return lo, min(span, n - lo)
 
     def run(self, total_sum, total_sq):
         import time
@@ -128,17 +155,22 @@ class StoppingLoop:
             if multi:
                 dist.all_reduce(n, op=dist.ReduceOp.SUM, group=self.group)
             tracked += int(n.item())
-            reduce_scatter_sum(s_sum, total_sum, self.group)
-            reduce_scatter_sum(s_sq, total_sq, self.group)
-            mx = torch.tensor([self.evaluate(s_sum, s_sq, tracked, -1.0)[2]], dtype=torch.float64, device=total_sum.device)
+            lo, span = self.scored_range(total_sum, world)
+            per = span // world
+            reduce_scatter_sum(s_sum[:per], total_sum[lo:lo + span], self.group)
+            reduce_scatter_sum(s_sq[:per], total_sq[lo:lo + span], self.group)
+            mx = torch.tensor([self.evaluate(s_sum[:per], s_sq[:per], tracked, -1.0)[2]], dtype=torch.float64, device=total_sum.device)
             if multi:
                 dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
-            s, c, _ = self.evaluate(s_sum, s_sq, tracked, float(mx.item()))
+            s, c, _ = self.evaluate(s_sum[:per], s_sq[:per], tracked, float(mx.item()))
             part = torch.tensor([s, c], dtype=torch.float64, device=total_sum.device)
             if multi:
                 dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
             k += 1
             current = criterion_from_partials(float(part[0].item()), float(part[1].item()))
             self.history.append(current)
+            self.exchanged_values = span
+            if total_sum.is_cuda:
+                torch.cuda.synchronize()
             self.stat_seconds += time.perf_counter() - t0
         return tracked, current, k

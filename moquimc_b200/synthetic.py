@@ -34,17 +34,18 @@ def head_ct(n=(512, 512, 200), spacing=(1.0, 1.0, 2.5), seed=1):
     return hu, origin
 
 
-def write_mha(path, hu, origin, spacing):
-    """MetaImage with float voxels, the layout tps_env::read_ct_image parses (mqi_tps_env.hpp:615-701)."""
+def write_mha(path, hu, origin, spacing, element="MET_FLOAT"):
+    """MetaImage with float voxels, the layout tps_env::read_ct_image parses (mqi_tps_env.hpp:615-701); MET_SHORT is
+    the other element type the B200 front end accepts."""
     nz, ny, nx = hu.shape
     hdr = ("ObjectType = Image\nNDims = 3\nBinaryData = True\nBinaryDataByteOrderMSB = False\nCompressedData = False\n"
            "TransformMatrix = 1 0 0 0 1 0 0 0 1\nOffset = %.9g %.9g %.9g\nCenterOfRotation = 0 0 0\n"
            "AnatomicalOrientation = RAI\nElementSpacing = %.9g %.9g %.9g\nDimSize = %d %d %d\n"
-           "ElementType = MET_FLOAT\nElementDataFile = LOCAL\n"
-           % (origin[0], origin[1], origin[2], spacing[0], spacing[1], spacing[2], nx, ny, nz))
+           "ElementType = %s\nElementDataFile = LOCAL\n"
+           % (origin[0], origin[1], origin[2], spacing[0], spacing[1], spacing[2], nx, ny, nz, element))
     with open(path, "wb") as f:
         f.write(hdr.encode())
-        f.write(hu.astype(np.float32).tobytes())
+        f.write(hu.astype({"MET_FLOAT": np.float32, "MET_SHORT": np.int16, "MET_UCHAR": np.uint8}[element]).tobytes())
 
 
 def write_mask_mha(path, mask, origin=(0.0, 0.0, 0.0), spacing=(1.0, 1.0, 1.0)):

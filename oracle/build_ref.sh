@@ -70,6 +70,16 @@ for v in debug release; do
     $CXX $FLAGS $D "$HERE/ref_kat.cpp" -o "$OUT/ref_kat_$v" -lz &
     $CXX $FLAGS $D "$HERE/ref_harness.cpp" -o "$OUT/ref_harness_$v" -lz &
 done
+# drop-in proof from the reference's side (ref_dropin.cpp): the reference's own phantom_env, host compiler only, with
+# run() routed through the C ABI of libmqi_b200.so as INTEGRATION.md section 1 shows
+LIBDIR="$HERE/../moquimc_b200"
+if [ -f "$LIBDIR/libmqi_b200.so" ]; then
+    for v in debug release; do
+        D=""; [ $v = debug ] && D="-D__PHYSICS_DEBUG__"
+        $CXX $FLAGS $D -I"$HERE/../include" "$HERE/ref_dropin.cpp" -o "$OUT/ref_dropin_$v" -L"$LIBDIR" -lmqi_b200 \
+            -Wl,-rpath,'$ORIGIN/../../moquimc_b200' -lz &
+    done
+fi
 # -O0: treatment_machine_ion::create_beamsource binds a reference to *nullptr for the last spot (characterize_beamlet_time
 # ignores it); optimised builds of that undefined behaviour crash
 $CXX -std=c++11 -O0 -w -I$TMP -I$REF "$HERE/ref_tps_kat.cpp" -o "$OUT/ref_tps_kat" &

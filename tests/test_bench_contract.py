@@ -38,13 +38,27 @@ def test_b200_arm_refuses_to_run_without_a_device():
 
 
 def test_roofline_helpers_read_the_committed_profile():
+    """The committed ncu capture is quoted only for the launch size it was taken at and only while the library still
+    contains the kernel it profiled (SASS hash); anything else is reported as stale, never as a number."""
     sys.path.insert(0, ROOT)
     import bench
+    from moquimc_b200 import build as B
     peak, src = bench.measured_peaks()
     assert 3000.0 < peak < 9000.0 and ("measured" in src or "fallback" in src)
-    t = bench.ncu_traffic(10_000_000)
-    assert t is not None and 1e10 < t < bench.STEPS_PER_HISTORY * bench.BYTES_PER_STEP * 1e7   # below the algorithmic bytes: L2 hits
-    assert bench.ncu_traffic(12345) is None                  # only at the launch size of the capture
-    i = bench.ncu_issue(10_000_000, 76.0, 1965.0)
-    assert i is not None and 0.5 < i["frac"] < 1.0
-    assert bench.ncu_issue(10_000_000, 76.0, None) is None
+    prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    assert len(prof["sass_sha256"]) == 64 and prof["histories_per_launch"] == 10_000_000
+    cap, note = bench.committed_capture(12345)
+    assert cap is None and "launch size" in note            # only at the launch size of the capture
+    ident = B.kernel_identity()
+    if ident is None:
+        pytest.skip("cuobjdump or the library is missing")
+    cap, note = bench.committed_capture(10_000_000)
+    if ident["sass_sha256"] == prof["sass_sha256"]:
+        t = float(cap["dram_bytes_per_launch"])
+        assert 1e10 < t < bench.STEPS_PER_HISTORY * bench.BYTES_PER_STEP * 1e7   # below the algorithmic bytes: L2 hits
+        i = bench.ncu_issue(cap, 76.0, 1965.0)
+        assert i is not None and 0.5 < i["frac"] < 1.0
+        assert bench.ncu_issue(cap, 76.0, None) is None
+    else:
+        assert cap is None and note.startswith("stale")
+    assert bench.ncu_issue(None, 76.0, 1965.0) is None

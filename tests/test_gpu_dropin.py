@@ -1,0 +1,59 @@
+"""Drop-in proof from the reference's side (run on the B200 box with -m gpu): oracle/_ref/ref_dropin_<variant> is the
+reference's OWN phantom_env -- its command line, world and density set-up, host beam sampler, finalize() and
+save_reshaped_files() -- compiled with the host compiler only, with run() routed through the C ABI of
+libmqi_b200.so as INTEGRATION.md section 1 shows (oracle/ref_dropin.cpp, built by oracle/build_ref.sh).  The file it
+writes must be what the library gives for the same vertices, densities and seed through the ctypes binding."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import dose_metrics as M
+import oracle_lib as O
+from moquimc_b200 import capi
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("variant", ["debug", "release"])
+def test_reference_phantom_env_routed_through_the_c_abi(tmp_path, variant):
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_dropin_" + variant)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_dropin_%s not built" % variant)
+    nx, ny, nz = 100, 100, 200
+    hu = np.zeros((nz, ny, nx), dtype=np.int16)
+    hu[nz - 60:nz - 40] = 800       # a bone slab 40-60 mm deep
+    ph = str(tmp_path / "phantom.raw")
+    hu.tofile(ph)
+    out = str(tmp_path / "out")
+    os.makedirs(out)
+    n = 200_000
+    vfile = str(tmp_path / "vertices.raw")
+    cmd = [exe, "--lxyz", "100", "100", "200", "--pxyz", "0", "0", "-100", "--nxyz", str(nx), str(ny), str(nz),
+           "--spot_energy", "150", "0", "--spot_position", "0", "0", "0.5", "--spot_size", "20", "20", "--histories", str(n),
+           "--phantom_path", ph, "--output_prefix", out, "--random_seed", "4321", "--gpu_id", "0", "--dump_vertices", vfile]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "Number of particles tracked %d" % n in r.stdout
+    d = np.fromfile(os.path.join(out, "0_water_dE_total.raw"), dtype=np.float64).reshape(nz, ny, nx)
+    assert d.sum() > 0
+    # the same call sequence through ctypes: the reference's vertices, the reference's densities (hu_to_density is
+    # bit-exact, tests/test_oracle_kat.py), the same seed
+    v = np.fromfile(vfile, dtype=np.float32).reshape(n, 7)
+    lut = O.hu_to_density(np.arange(-1000, 2996))
+    rho = lut[hu.astype(np.int64) + 1000].astype(np.float32)
+    e = capi.Engine(0, physics=capi.PHYSICS_DEBUG if variant == "debug" else capi.PHYSICS_RELEASE)
+    e.set_grid_density(capi.uniform_edges(-50, 50, nx), capi.uniform_edges(-50, 50, ny), capi.uniform_edges(-200, 0, nz), rho)
+    s = e.add_scorer(capi.SCORER_DOSE, "water_dE_total")
+    e.set_vertices(v)
+    st = e.run(4321, 0, n)
+    assert st.histories == n and st.stack_overflows == 0
+    mine = e.get_dense(s)
+    # identical inputs and streams: only the order of the fp64 atomic additions differs
+    np.testing.assert_allclose(d, mine, rtol=1e-9, atol=mine.max() * 1e-13)
+    # and it is a proton depth dose: range of 150 MeV behind 20 mm of bone
+    r80 = M.r80_mm(d.sum(axis=(1, 2)))
+    assert 140.0 < r80 < 157.0, r80

@@ -562,3 +562,26 @@ def test_beamline_devices_match_the_reference_create_beamline(tmp_path, golden_d
                 assert n["n"][2] == int(lz) and n["open_voxels"] == 20 * 16 * int(lz)   # 1 mm voxels, 20 x 16 mm opening
             else:
                 assert n["n"] == [1, 1, 1]
+
+
+def test_ct_mha_element_types(tmp_path):
+    """MET_FLOAT (what the reference reads, mqi_tps_env.hpp:615-701) and MET_SHORT give the same HU volume; another
+    element type, a compressed or a big-endian payload is refused instead of being misread as float."""
+    root = str(tmp_path)
+    inp = S.make_case(root, n=(24, 20, 10), spacing=(4.0, 4.0, 6.0), n_layers=1)
+    hu, origin = S.head_ct((24, 20, 10), (4.0, 4.0, 6.0), 1)
+    a = dry_run(inp)["hu"]
+    assert a == {"sum": int(hu.astype(np.int64).sum()), "min": int(hu.min()), "max": int(hu.max())}
+    S.write_mha(os.path.join(root, "ct.mha"), hu, origin, (4.0, 4.0, 6.0), element="MET_SHORT")
+    assert dry_run(inp)["hu"] == a
+    S.write_mha(os.path.join(root, "ct.mha"), (hu % 200).astype(np.uint8), origin, (4.0, 4.0, 6.0), element="MET_UCHAR")
+    assert "unsupported ElementType" in dry_run(inp, expect_fail=True)
+    # out-of-range floats are clamped, not wrapped
+    big = hu.astype(np.float32)
+    big[0, 0, 0], big[0, 0, 1] = 1.0e9, -1.0e9
+    S.write_mha(os.path.join(root, "ct.mha"), big, origin, (4.0, 4.0, 6.0))
+    h = dry_run(inp)["hu"]
+    assert h["max"] == 32767 and h["min"] == -32768
+    text = open(os.path.join(root, "ct.mha"), "rb").read().replace(b"CompressedData = False", b"CompressedData = True")
+    open(os.path.join(root, "ct.mha"), "wb").write(text)
+    assert "compressed" in dry_run(inp, expect_fail=True)
