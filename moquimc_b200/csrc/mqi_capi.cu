@@ -153,6 +153,7 @@ struct mqi_handle {
     int          accum    = MQI_ACCUM_ATOMIC;
     int          count_steps = 0;
     int          dij_write_combine = 1;        // option "dij_write_combine": consecutive hits of a lane on one (voxel, spot) key are summed in registers and inserted once
+    int          rsp_exact = 0;                // option "rsp_exact": mqi_dev_rsp evaluates spr_default in the reference's precision (bit-exact KAT)
     int          blocks_per_sm_override = 0;
     int          l2_persist = 0;               // option "l2_persist": pin the material volume in L2 with a persisting access window (measured: no gain at C1)
     size_t       l2_persist_max = 0, l2_window_max = 0;
@@ -789,6 +790,7 @@ mqi_set_option(mqi_handle* h, const char* key, int64_t value) {
     else if (k == "blocks_per_sm") h->blocks_per_sm_override = (int) value;
     else if (k == "l2_persist") h->l2_persist = value != 0;
     else if (k == "dij_write_combine") h->dij_write_combine = value != 0;
+    else if (k == "rsp_exact") h->rsp_exact = value != 0;
     else return fail(MQI_EINVAL, "unknown option " + k);
     return MQI_OK;
 }
@@ -904,7 +906,8 @@ mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t cou
     if (bps < 1) return fail(MQI_ECUDA, "transport kernel does not fit on an SM");
     if (h->blocks_per_sm_override > 0) bps = std::min(bps, h->blocks_per_sm_override);
     // persistent grid: a whole number of CTAs per SM, never more lanes than histories
-    unsigned long long want = (count + MQI_K_BLOCK - 1) / MQI_K_BLOCK;
+    const unsigned long long blk = (unsigned long long) transport_block(p.n_nodes > 1);
+    unsigned long long want = (count + blk - 1) / blk;
     int                grid = (int) std::min<unsigned long long>((unsigned long long) h->sm_count * bps, want);
     {   // subsystem 3: the 16-bit material volume of the scored grid is read once per voxel step by every
         // lane; keep it resident in L2 (persisting access window on the launching stream) while the fp64
@@ -1398,7 +1401,7 @@ mqi_dev_rsp(mqi_handle* h, const float* rho, const float* ek, uint64_t n, float*
     CU(d_m.alloc(n)); CU(d_ek.alloc(n)); CU(d_rsp.alloc(n)); CU(d_rl.alloc(n));
     CU(cudaMemcpyAsync(d_m.p, m.data(), n * sizeof(MatEntry), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(d_ek.p, ek, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    CU(launch_dev_rsp(d_m.p, d_ek.p, n, d_rsp.p, d_rl.p, h->stream));
+    CU(launch_dev_rsp(d_m.p, d_ek.p, n, d_rsp.p, d_rl.p, h->stream, h->rsp_exact != 0));
     CU(cudaMemcpyAsync(rsp_out, d_rsp.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(rl_out, d_rl.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));

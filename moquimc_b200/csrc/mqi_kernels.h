@@ -23,12 +23,26 @@
 #ifndef MQI_K_BLOCK
 #define MQI_K_BLOCK 768
 #endif
+#ifndef MQI_K_BLOCK_MULTI
+#define MQI_K_BLOCK_MULTI 768   /* threads per CTA of the multi-node kernels (worlds with beamline children) */
+#endif
 #ifndef MQI_K_MIN_BLOCKS
 #define MQI_K_MIN_BLOCKS 1   /* 24 warps/SM at <= 80 registers/thread in ONE CTA: one copy of the shared-memory tables leaves the most L1; measured best of 128x5 ... 768x1 on B200 (profiles/r1_experiments.md) */
 #endif
 
 #ifndef MQI_K_PARK_DEPTH
 #define MQI_K_PARK_DEPTH 4   /* parked (voxel, spot, value) pairs per lane in front of the Dij table, see park_dij */
+#endif
+
+#ifndef MQI_K_ADV_BATCH
+#define MQI_K_ADV_BATCH 12   /* multi-node worlds: lanes of a warp that hand their track over to the next child together ... */
+#endif
+#ifndef MQI_K_ADV_TURNS
+#define MQI_K_ADV_TURNS 6    /* ... or after the first of them has waited this many turns */
+#endif
+
+#ifndef MQI_K_RSP_EXACT
+#define MQI_K_RSP_EXACT 0    /* 1: the transport kernel evaluates spr_default in the reference's precision (rsp_eval_exact) */
 #endif
 
 #ifndef MQI_K_LATE_LUT
@@ -46,6 +60,7 @@ struct MatEntry;
 struct BeamletDev;
 struct VertexDev;
 
+int         transport_block(bool multi);
 size_t      transport_smem_bytes(int n_edge_floats, int n_nodes, bool dij_park = false);
 bool        transport_is_simple(const Params& p);
 cudaError_t transport_occupancy(const Params& p, int variant, size_t smem, int* blocks_per_sm);
@@ -57,7 +72,7 @@ cudaError_t launch_hu_to_material(const int16_t* d_hu, uint16_t* d_mat, size_t n
 cudaError_t launch_hu_to_density(const int16_t* d_hu, float* d_rho, size_t n, const float* d_correction,
                                  float density_scale, cudaStream_t st);
 cudaError_t launch_dev_rsp(const MatEntry* lut_entries, const float* ek, size_t n, float* rsp, float* rl,
-                           cudaStream_t st);
+                           cudaStream_t st, bool exact = false);
 cudaError_t launch_dev_grid_step(const Params& p, const float* pin, const float* din, size_t n, int32_t* cell,
                                  unsigned long long* cnb, float* dist, float* dir_after, float* p_exit,
                                  int32_t* cell_after, cudaStream_t st);

@@ -30,7 +30,7 @@ struct Smem {
     const GridDev* nodes;  // multi-node launches only
     uint32_t*     queue;   // kQueueWords words per warp
     // DIJWC launches: finished (voxel, spot, value) pairs parked per lane until the warp inserts them together,
-    // structure of arrays, entry d of thread t at [d * MQI_K_BLOCK + t]
+    // structure of arrays, entry d of thread t at [d * blockDim.x + t]
     uint32_t*     park_k1;
     uint32_t*     park_k2;
     double*       park_val;
@@ -45,7 +45,7 @@ enum QueueField { Q_PX = 0, Q_PY, Q_PZ, Q_DX, Q_DY, Q_DZ, Q_KE, Q_IX, Q_IY, Q_IZ
 constexpr int kQueueWords  = Q_FIELDS * kQueueCap;
 constexpr size_t kTableBytes = kTableN * (2 * sizeof(float4) + sizeof(float2));
 constexpr int    kParkDepth  = MQI_K_PARK_DEPTH;   // parked Dij pairs per lane (DIJWC launches)
-constexpr size_t kParkBytes  = (size_t) kParkDepth * MQI_K_BLOCK * (2 * sizeof(uint32_t) + sizeof(double));
+constexpr size_t kParkBytesPerThread = (size_t) kParkDepth * (2 * sizeof(uint32_t) + sizeof(double));
 
 __host__ __device__ __forceinline__ size_t
 smem_nodes_offset(int n_edge_floats) { return (kTableBytes + (size_t) n_edge_floats * sizeof(float) + 15) & ~(size_t) 15; }
@@ -64,9 +64,9 @@ smem_view(unsigned char* raw, int n_edge_floats, int n_nodes) {
     sm.edges = reinterpret_cast<float*>(bs + kTableN);
     sm.nodes = reinterpret_cast<const GridDev*>(raw + smem_nodes_offset(n_edge_floats));
     sm.queue = reinterpret_cast<uint32_t*>(raw + smem_queue_offset(n_edge_floats, n_nodes));
-    sm.park_val = reinterpret_cast<double*>(sm.queue + (MQI_K_BLOCK / 32) * kQueueWords);   // 16-byte aligned: kQueueWords % 4 == 0
-    sm.park_k1  = reinterpret_cast<uint32_t*>(sm.park_val + kParkDepth * MQI_K_BLOCK);
-    sm.park_k2  = sm.park_k1 + kParkDepth * MQI_K_BLOCK;
+    sm.park_val = reinterpret_cast<double*>(sm.queue + (blockDim.x / 32) * kQueueWords);   // 16-byte aligned: kQueueWords % 4 == 0
+    sm.park_k1  = reinterpret_cast<uint32_t*>(sm.park_val + kParkDepth * blockDim.x);
+    sm.park_k2  = sm.park_k1 + kParkDepth * blockDim.x;
     return sm;
 }
 
@@ -395,22 +395,29 @@ dij_add_inline(DijSlot* table, unsigned long long capacity, uint32_t key1, uint3
     }
     const unsigned long long key = ((unsigned long long) key2 << 32) | key1;
     for (unsigned long long probes = 0; probes < capacity; probes += 4) {
-        unsigned long long sl[4], kk[4];
+        DijSlot*           e[4];
+        unsigned long long kk[4];
+        if (slot + 4 <= capacity) {   // no wrap-around inside this group of four (all but the last three home slots)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            sl[i] = slot;
-            slot  = slot + 1 == capacity ? 0 : slot + 1;
+            for (int i = 0; i < 4; ++i) e[i] = table + slot + i;
+            slot = slot + 4 == capacity ? 0 : slot + 4;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                e[i] = table + slot;
+                slot = slot + 1 == capacity ? 0 : slot + 1;
+            }
         }
         // L2 is the point of coherence of the table (the CAS and the adds are performed there): a cache-global
         // load sees every claimed key; a system-scope volatile load costs more and buys nothing
 #pragma unroll
-        for (int i = 0; i < 4; ++i) kk[i] = __ldcg(&table[sl[i]].key);
+        for (int i = 0; i < 4; ++i) kk[i] = __ldcg(&e[i]->key);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             unsigned long long prev = kk[i];
-            if (prev == kEmptyKey64) prev = atomicCAS(&table[sl[i]].key, kEmptyKey64, key);
+            if (prev == kEmptyKey64) prev = atomicCAS(&e[i]->key, kEmptyKey64, key);
             if (prev == kEmptyKey64 || prev == key) {
-                atomicAdd(&table[sl[i]].value, v);
+                red_add_f64(&e[i]->value, v);
                 return;
             }
         }
@@ -469,7 +476,7 @@ struct DijCombine {
 __device__ __forceinline__ void
 park_dij(const Smem& sm, DijCombine& wc, uint32_t spot_ind) {
     if (wc.key != kEmptyKey32) {
-        const int o = wc.npark * MQI_K_BLOCK + threadIdx.x;
+        const int o = wc.npark * blockDim.x + threadIdx.x;
         sm.park_k1[o]  = wc.key;
         sm.park_k2[o]  = spot_ind;
         sm.park_val[o] = wc.val;
@@ -484,10 +491,18 @@ flush_parked(const Params& P, int npark) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem       sm = smem_view(smem_raw, P.n_edge_floats, P.n_nodes);
     const ScorerDev& S  = P.sc[P.dij_wc_scorer];
+    // first the home slots of all parked pairs are requested into L2, then the pairs are inserted: the probe loads
+    // of a lane's second, third ... pair find their sector on the way instead of starting a DRAM round trip each
+    for (int d = 0; d < npark; ++d) {
+        const int o = d * blockDim.x + threadIdx.x;
+        const uint32_t k1 = sm.park_k1[o], k2 = sm.park_k2[o];
+        const unsigned long long home = k2 == kEmptyKey32 ? (unsigned long long) k1 : hash_fun(k1, k2, S.capacity);
+        if (home < S.capacity) prefetch_l2(S.table + home);
+    }
     while (__any_sync(0xffffffffu, npark > 0)) {
         if (npark > 0) {
             npark -= 1;
-            const int o = npark * MQI_K_BLOCK + threadIdx.x;
+            const int o = npark * blockDim.x + threadIdx.x;
             dij_add_inline(S.table, S.capacity, sm.park_k1[o], sm.park_k2[o], sm.park_val[o], P.counters);
         }
     }
@@ -836,7 +851,7 @@ csda_row_fix(const float4* a1, int n, int n0, float r) {
 // MULTI: the world has beamline children (range shifter, aperture) in front of the scored grid; every
 // lane carries the index of the child it is in and reads that child's descriptor from shared memory.
 template<int VARIANT, int SET, bool MULTI, bool DIJWC = false>
-__global__ void __launch_bounds__(MQI_K_BLOCK, MQI_K_MIN_BLOCKS)
+__global__ void __launch_bounds__(MULTI ? MQI_K_BLOCK_MULTI : MQI_K_BLOCK, MQI_K_MIN_BLOCKS)
 transport_kernel(const __grid_constant__ Params P) {
     constexpr bool SIMPLE  = SET == SET_DOSE;
     constexpr bool COUNTED = SET == SET_GENERIC;   // count_steps runs the general kernel
@@ -886,6 +901,8 @@ transport_kernel(const __grid_constant__ Params P) {
     // the warp's queue of pre-sampled primaries: entries in the queue | history counter exhausted << 16
     // (warp-uniform; one register)
     int q_state = 0;
+    int adv_wait = 0;   // MULTI: turns the oldest lane waiting for a node hand-over has waited (warp-uniform)
+    constexpr int kAdvBatch = MQI_K_ADV_BATCH, kAdvTurns = MQI_K_ADV_TURNS;
 
     // Warp-level reconvergence.  Restarting a lane is executed by the few lanes whose track just ended;
     // without an explicit join the compiler only reconverges them at the END of the iteration, i.e. the
@@ -906,8 +923,23 @@ transport_kernel(const __grid_constant__ Params P) {
             }
         }
         // ------------------------------------------------------------------ restart the lane
+        // Node-to-node hand-overs (MULTI) are batched: the tracks of a warp were started together, so they leave a
+        // beamline child within a few turns of each other.  A lane whose track has left its child waits (idle) until
+        // kAdvBatch lanes of the warp wait or the first of them has waited kAdvTurns turns; then all of them are
+        // mapped to the world frame and located in the next child in ONE pass of restart_lane.  One lane at a time
+        // (the whole warp waiting for ~ 300 instructions of a single lane, twice per history) this was 27 % of the
+        // issued warp instructions at 1.5 active lanes (profiles/r2_experiments.md).
+        bool hand_over = true;
+        if (MULTI) {
+            const unsigned adv = __ballot_sync(0xffffffffu, (fl & FL_ADVANCE) != 0u);
+            if (adv) {
+                adv_wait += 1;
+                hand_over = __popc(adv) >= kAdvBatch || adv_wait > kAdvTurns;
+                if (hand_over) adv_wait = 0;
+            }
+        }
         bool need = false;   // the lane needs a new primary
-        if (!(fl & (FL_ALIVE | FL_DONE))) {
+        if (!(fl & (FL_ALIVE | FL_DONE)) && !(MULTI && (fl & FL_ADVANCE) && !hand_over)) {
             if (DIJWC) park_dij(sm, wc, spot_ind);   // the track ended: park its pending write-combined Dij hit
             if ((MULTI && (fl & FL_ADVANCE)) || sp > 0) {
                 TrackIO T;
@@ -1273,9 +1305,9 @@ hu_to_density_kernel(const int16_t* __restrict__ hu, float* __restrict__ rho, si
 }
 
 __global__ void
-dev_rsp_kernel(const MatEntry* __restrict__ m, const float* __restrict__ ek, size_t n, float* rsp, float* rl) {
+dev_rsp_kernel(const MatEntry* __restrict__ m, const float* __restrict__ ek, size_t n, float* rsp, float* rl, int exact) {
     for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
-        rsp[i] = rsp_eval(m[i], ek[i]);
+        rsp[i] = exact ? rsp_eval_exact(m[i], ek[i]) : rsp_eval(m[i], ek[i]);
         rl[i]  = m[i].x0;
     }
 }
@@ -1510,9 +1542,15 @@ static inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
 
 size_t
 transport_smem_bytes(int n_edge_floats, int n_nodes, bool dij_park) {
-    return smem_queue_offset(n_edge_floats, n_nodes) + (size_t) (MQI_K_BLOCK / 32) * kQueueWords * sizeof(uint32_t) +
-           (dij_park ? kParkBytes : 0);
+    const size_t block = (size_t) transport_block(n_nodes > 1);
+    return smem_queue_offset(n_edge_floats, n_nodes) + (block / 32) * kQueueWords * sizeof(uint32_t) +
+           (dij_park ? kParkBytesPerThread * block : 0);
 }
+
+// threads per CTA of the kernels of a world with / without beamline children (the multi-node kernels carry a
+// per-lane node descriptor: fewer threads per CTA leave them more registers)
+int
+transport_block(bool multi) { return multi ? MQI_K_BLOCK_MULTI : MQI_K_BLOCK; }
 
 typedef void (*transport_fn)(const Params);
 template<int SET, bool MULTI, bool DIJWC>
@@ -1558,12 +1596,12 @@ transport_occupancy(const Params& p, int variant, size_t smem, int* blocks_per_s
     transport_fn f = pick_transport(variant, transport_scorer_set(p), p.n_nodes > 1, p.dij_wc_scorer >= 0);
     cudaError_t  e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, f, MQI_K_BLOCK, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, f, transport_block(p.n_nodes > 1), smem);
 }
 
 cudaError_t
 launch_transport(const Params& p, int variant, int grid, size_t smem, cudaStream_t st) {
-    pick_transport(variant, transport_scorer_set(p), p.n_nodes > 1, p.dij_wc_scorer >= 0)<<<grid, MQI_K_BLOCK, smem, st>>>(p);
+    pick_transport(variant, transport_scorer_set(p), p.n_nodes > 1, p.dij_wc_scorer >= 0)<<<grid, transport_block(p.n_nodes > 1), smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -1578,8 +1616,8 @@ launch_hu_to_density(const int16_t* d_hu, float* d_rho, size_t n, const float* d
     return cudaGetLastError();
 }
 cudaError_t
-launch_dev_rsp(const MatEntry* m, const float* ek, size_t n, float* rsp, float* rl, cudaStream_t st) {
-    dev_rsp_kernel<<<grid_for(n), 256, 0, st>>>(m, ek, n, rsp, rl);
+launch_dev_rsp(const MatEntry* m, const float* ek, size_t n, float* rsp, float* rl, cudaStream_t st, bool exact) {
+    dev_rsp_kernel<<<grid_for(n), 256, 0, st>>>(m, ek, n, rsp, rl, exact ? 1 : 0);
     return cudaGetLastError();
 }
 cudaError_t

@@ -108,6 +108,13 @@ def test_device_rsp_radiation_length(kat, variant):
     assert clin.sum() > 50 and ulp_diff(rsp[clin], k["rsp_out"][clin]).max() <= 4
     _, rl = e.dev_rsp(k["rl_rho"], np.full(len(k["rl_rho"]), 100.0, dtype=np.float32))
     assert (bits(rl) == bits(k["rl_out"])).all()
+    # spr_default in the reference's own precision (option rsp_exact: fp64 energy term, correctly rounded pow):
+    # bit for bit.  The transport kernel keeps the fp32 evaluation by default (measured cost).
+    e.set_option("rsp_exact", 1)
+    exact, _ = e.dev_rsp(k["rsp_rho"], k["rsp_ek"])
+    ok = np.isfinite(k["rsp_out"])
+    assert (bits(exact[ok]) == bits(k["rsp_out"][ok])).all(), ulp_diff(exact[ok], k["rsp_out"][ok]).max()
+    assert (np.isfinite(exact) == ok).all()
 
 
 def test_device_voxel_indices_bit_exact(kat):

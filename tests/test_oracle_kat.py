@@ -194,3 +194,22 @@ def test_philox2x32_known_answers():
                           ((0x243f6a88, 0x85a308d3), 0x13198a2e, (0xdd7ce038, 0xf62a4c12))):
         L.mqo_philox2x32_10((C.c_uint32 * 2)(*ctr), C.c_uint32(key), out)
         assert (out[0], out[1]) == exp
+
+
+def test_tables_blob_is_what_the_reference_headers_hold():
+    """moquimc_b200/data/mqi_tables_v1.bin (compiled into libmqi_b200.so) byte for byte against the tables the
+    reference's own headers hold, dumped by oracle/_ref/ref_kat_release (generator: oracle/gen_tables.py).  Needs the
+    reference build of the container; on a box without it the checksums in kat_release.npz pin the same arrays."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("gen_tables", os.path.join(here, "..", "oracle", "gen_tables.py"))
+    gt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gt)
+    blob = open(gt.BLOB, "rb").read()
+    assert blob[:8] == b"MQITBL1\0" and len(blob) == 16 + 4 * (3600 + 3996)
+    if os.path.exists(gt.KAT):
+        assert gt.build_blob() == blob
+    kat = np.load(os.path.join(here, "golden", "kat_release.npz"))
+    f = np.frombuffer(blob[16:], dtype="<f4")
+    np.testing.assert_allclose(f[:3600].astype(np.float64).sum(), float(kat["tables_sum"]), rtol=0, atol=0)
+    np.testing.assert_allclose(f[3600:].astype(np.float64).sum(), float(kat["density_correction_sum"]), rtol=0, atol=0)
