@@ -26,7 +26,7 @@ e = capi.Engine(0, physics=capi.PHYSICS_RELEASE)
 e.set_grid_hu(xe, ye, ze, hu)
 s = e.add_scorer(capi.SCORER_DIJ, "Dij", capacity=cap | 1)
 e.set_beamlets(bl, [per] * len(bl))
-e.set_option("count_steps", 1)
+e.set_option("count_steps", int(os.environ.get("MQI_COUNT_STEPS", "1")))   # 0: the SET_DIJ kernel (the counter runs the general one)
 wc = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 e.set_option("dij_write_combine", wc)
 for rep in range(2):
