@@ -107,9 +107,11 @@ make_mat_entry(float rho, int variant) {
         m.mode = 0;
         m.a    = d < 0.0012 ? 0.0f : lerp_ref(d, 0.0012f, 0.26f, 0.8815f, 0.9925f);
     } else {
-        m.P = (float) ((double) powf(d, -0.7f) - 1.0);
+        const float pd = powf(d, -0.7f);
+        m.P = (float) ((double) pd - 1.0);
         if (d >= 0.9) {
             m.mode = 1;
+            m.a    = pd;   // rsp_eval_exact: above 2.69 g/cm3 (pd < 0.5) pd - 1 is not representable in fp32
         } else {
             m.mode = 2;
             m.a    = d - 0.26f;

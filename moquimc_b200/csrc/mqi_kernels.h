@@ -45,6 +45,10 @@
 #define MQI_K_RSP_EXACT 0    /* 1: the transport kernel evaluates spr_default in the reference's precision (rsp_eval_exact) */
 #endif
 
+#ifndef MQI_K_FIRST_PROBE
+#define MQI_K_FIRST_PROBE 2  /* slots of every parked pair whose keys are loaded up front, see flush_parked */
+#endif
+
 #ifndef MQI_K_LATE_LUT
 #define MQI_K_LATE_LUT 1   /* delay the material LUT load behind the step's random numbers (see mqi_transport.cu) */
 #endif

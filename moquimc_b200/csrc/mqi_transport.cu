@@ -378,23 +378,11 @@ dense_add(double* __restrict__ acc, unsigned cnb, double v, int accum_mode) {
 // first one in probe order that is free or holds the key: the same slot linear probing ends in -- a slot seen
 // occupied by another key stays so (keys are never removed), a slot seen free is claimed through the CAS, which
 // reports whoever won it -- with one dependent memory round trip for 85 % of the inserts at load factor 0.73
-// instead of 2.4.
+// instead of 2.4.  `probes` slots of the sequence have already been rejected by the caller.
 __device__ __forceinline__ void
-dij_add_inline(DijSlot* table, unsigned long long capacity, uint32_t key1, uint32_t key2, double v,
-               unsigned long long* counters) {
-    unsigned long long slot;
-    if (key2 == kEmptyKey32) {   // dense mode of the reference: slot = voxel, key2 := 0
-        slot = key1;
-        key2 = 0;
-        if (slot >= capacity) {   // a table smaller than the grid: count the hit instead of writing outside it
-            atomicAdd(counters + C_DIJ_FULL, 1ull);
-            return;
-        }
-    } else {
-        slot = hash_fun(key1, key2, capacity);
-    }
-    const unsigned long long key = ((unsigned long long) key2 << 32) | key1;
-    for (unsigned long long probes = 0; probes < capacity; probes += 4) {
+dij_probe_from(DijSlot* table, unsigned long long capacity, unsigned long long slot, unsigned long long probes,
+               unsigned long long key, double v, unsigned long long* counters) {
+    for (; probes < capacity; probes += 4) {
         DijSlot*           e[4];
         unsigned long long kk[4];
         if (slot + 4 <= capacity) {   // no wrap-around inside this group of four (all but the last three home slots)
@@ -425,10 +413,40 @@ dij_add_inline(DijSlot* table, unsigned long long capacity, uint32_t key1, uint3
     atomicAdd(counters + C_DIJ_FULL, 1ull);   // the reference would spin forever here
 }
 
+// home slot of a (voxel, spot) pair; key2 = 0xffffffff is the reference's dense mode: slot = voxel, key2 := 0
+// (mqi_transport.hpp:78-81).  Returns false if that slot lies outside the table.
+__device__ __forceinline__ bool
+dij_home(unsigned long long capacity, uint32_t key1, uint32_t& key2, unsigned long long& slot) {
+    if (key2 == kEmptyKey32) {
+        slot = key1;
+        key2 = 0;
+        return slot < capacity;
+    }
+    slot = hash_fun(key1, key2, capacity);
+    return true;
+}
+
+__device__ __forceinline__ void
+dij_add_inline(DijSlot* table, unsigned long long capacity, uint32_t key1, uint32_t key2, double v,
+               unsigned long long* counters) {
+    unsigned long long slot;
+    if (!dij_home(capacity, key1, key2, slot)) {   // a table smaller than the grid: count the hit instead of writing outside it
+        atomicAdd(counters + C_DIJ_FULL, 1ull);
+        return;
+    }
+    dij_probe_from(table, capacity, slot, 0ull, ((unsigned long long) key2 << 32) | key1, v, counters);
+}
+
 __device__ __noinline__ void
 dij_add(DijSlot* table, unsigned long long capacity, uint32_t key1, uint32_t key2, double v,
         unsigned long long* counters) {
     dij_add_inline(table, capacity, key1, key2, v, counters);
+}
+
+__device__ __noinline__ void
+dij_probe_more(DijSlot* table, unsigned long long capacity, unsigned long long slot, unsigned long long probes,
+               unsigned long long key, double v, unsigned long long* counters) {
+    dij_probe_from(table, capacity, slot, probes, key, v, counters);
 }
 
 struct StepResult {
@@ -485,25 +503,67 @@ park_dij(const Smem& sm, DijCombine& wc, uint32_t spot_ind) {
     }
 }
 
-// called by the whole warp; returns with every lane's slots empty
+// Called by the whole warp; returns with every lane's slots empty.  The insert is a chain of dependent, uncoalesced
+// memory round trips (home slot -> key -> CAS -> add), and what bounds the sparse scorer is how many of them are in
+// flight: phase A computes the home slots of ALL parked pairs of the lane and issues the key loads of their first
+// kFirstProbe slots back to back (up to kParkDepth x kFirstProbe independent loads per lane, ~ 250 per warp), phase B
+// resolves the pairs from the loaded keys; the ~ 15 % that need to probe further do so one at a time (dij_probe_more).
+constexpr int kFirstProbe = MQI_K_FIRST_PROBE;
 __device__ __noinline__ void
 flush_parked(const Params& P, int npark) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem       sm = smem_view(smem_raw, P.n_edge_floats, P.n_nodes);
-    const ScorerDev& S  = P.sc[P.dij_wc_scorer];
-    // first the home slots of all parked pairs are requested into L2, then the pairs are inserted: the probe loads
-    // of a lane's second, third ... pair find their sector on the way instead of starting a DRAM round trip each
-    for (int d = 0; d < npark; ++d) {
-        const int o = d * blockDim.x + threadIdx.x;
-        const uint32_t k1 = sm.park_k1[o], k2 = sm.park_k2[o];
-        const unsigned long long home = k2 == kEmptyKey32 ? (unsigned long long) k1 : hash_fun(k1, k2, S.capacity);
-        if (home < S.capacity) prefetch_l2(S.table + home);
+    const Smem               sm  = smem_view(smem_raw, P.n_edge_floats, P.n_nodes);
+    const ScorerDev&         S   = P.sc[P.dij_wc_scorer];
+    DijSlot* const           tab = S.table;
+    const unsigned long long cap = S.capacity;
+    unsigned long long home[kParkDepth];
+    unsigned long long kk[kParkDepth][kFirstProbe];
+#pragma unroll
+    for (int d = 0; d < kParkDepth; ++d) {
+        home[d] = cap;   // "no pair" / "outside the table"
+        if (d < npark) {
+            const int o  = d * blockDim.x + threadIdx.x;
+            uint32_t  k2 = sm.park_k2[o];
+            unsigned long long h;
+            if (dij_home(cap, sm.park_k1[o], k2, h)) {
+                home[d] = h;
+                unsigned long long s = h;
+#pragma unroll
+                for (int i = 0; i < kFirstProbe; ++i) {
+                    kk[d][i] = __ldcg(&tab[s].key);
+                    s        = s + 1 == cap ? 0 : s + 1;
+                }
+            }
+        }
     }
-    while (__any_sync(0xffffffffu, npark > 0)) {
-        if (npark > 0) {
-            npark -= 1;
-            const int o = npark * blockDim.x + threadIdx.x;
-            dij_add_inline(S.table, S.capacity, sm.park_k1[o], sm.park_k2[o], sm.park_val[o], P.counters);
+#pragma unroll
+    for (int d = 0; d < kParkDepth; ++d) {
+        if (d < npark) {
+            const int      o  = d * blockDim.x + threadIdx.x;
+            const uint32_t k1 = sm.park_k1[o];
+            uint32_t       k2 = sm.park_k2[o];
+            const double   v  = sm.park_val[o];
+            if (k2 == kEmptyKey32) k2 = 0;
+            const unsigned long long key = ((unsigned long long) k2 << 32) | k1;
+            if (home[d] >= cap) {
+                atomicAdd(P.counters + C_DIJ_FULL, 1ull);
+            } else {
+                unsigned long long s    = home[d];
+                bool               done = false;
+#pragma unroll
+                for (int i = 0; i < kFirstProbe; ++i) {
+                    if (!done) {
+                        unsigned long long prev = kk[d][i];
+                        if (prev == kEmptyKey64) prev = atomicCAS(&tab[s].key, kEmptyKey64, key);
+                        if (prev == kEmptyKey64 || prev == key) {
+                            red_add_f64(&tab[s].value, v);
+                            done = true;
+                        }
+                        s = s + 1 == cap ? 0 : s + 1;
+                    }
+                }
+                if (!done) dij_probe_more(tab, cap, s, (unsigned long long) kFirstProbe, key, v, P.counters);
+            }
         }
     }
 }

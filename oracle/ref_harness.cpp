@@ -274,7 +274,11 @@ public:
         }
         std::vector<std::thread> th;
         for (int t = 0; t < T; ++t) {
-            thread_rngs[t]->seed((unsigned) this->random_seed + 1000003u * (unsigned) pass + 7919u * (unsigned) t + 1u);
+            // (run seed, pass, thread) -> one stream each: a seed sequence, so that runs whose seeds differ by a
+            // multiple of some stride never share a stream (an additive combination did: run k / thread t met run
+            // k + 1 / thread t - 1, and the "independent" runs of the first GPU fixtures shared most of their vertices)
+            std::seed_seq sq { (uint32_t) this->random_seed, (uint32_t) pass, (uint32_t) t, 0x6d716931u };
+            thread_rngs[t]->seed(sq);
             const size_t a = (size_t) h1 * t / T, b = (size_t) h1 * (t + 1) / T;
             th.emplace_back([this, t, a, b]() {
                 for (size_t i = a; i < b; ++i) {
