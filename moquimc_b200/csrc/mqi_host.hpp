@@ -16,6 +16,7 @@
 
 #include <array>
 #include <chrono>
+#include <sstream>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -148,73 +149,86 @@ struct grid_desc {
     int nz() const { return (int) ze.size() - 1; }
 };
 
+// voxel spacing and centre of voxel (0, 0, 0) as the reference derives them from the first two edges: the spacing is
+// a float difference, the centre is formed in double (the 0.5 literal) and rounded to float (mqi_io.hpp:497-503)
+struct voxel_frame {
+    float spacing[3], centre0[3];
+    int   n[3];
+};
+
+inline voxel_frame
+frame_of(const grid_desc& g) {
+    voxel_frame              f;
+    const std::vector<float>* e[3] = { &g.xe, &g.ye, &g.ze };
+    for (int a = 0; a < 3; ++a) {
+        f.spacing[a] = (*e[a])[1] - (*e[a])[0];
+        f.centre0[a] = (float) ((double) (*e[a])[0] + (double) f.spacing[a] * 0.5);
+        f.n[a]       = (int) e[a]->size() - 1;
+    }
+    return f;
+}
+
+// The MetaImage header of a dose file.  The text is an output contract: the two flavours the reference writes differ in
+// more than the data line (mqi_io.hpp:493-591) -- the detached .mhd header omits '=' after TransformMatrix and
+// CenterOfRotation, calls the origin "Offset" and prints floats with the stream's default precision; the .mha header
+// says "Origin", adds HeaderSize and prints nine significant digits -- and readers of the reference's files get
+// exactly those bytes (tests/golden/fmt_writers.npz).
+inline std::string
+meta_image_header(const voxel_frame& f, bool embedded, const std::string& data_file) {
+    std::ostringstream h;
+    if (embedded) h << std::setprecision(9);
+    const char* sep = embedded ? " = " : " ";
+    h << "ObjectType = Image\nNDims = 3\nBinaryData = True\nBinaryDataByteOrderMSB = False\nCompressedData = False\n"
+      << "TransformMatrix" << sep << "1 0 0 0 1 0 0 0 1\n"
+      << (embedded ? "Origin = " : "Offset ") << f.centre0[0] << " " << f.centre0[1] << " " << f.centre0[2] << "\n"
+      << "CenterOfRotation" << sep << "0 0 0\n"
+      << "AnatomicOrientation = RAI\n"
+      << "DimSize = " << f.n[0] << " " << f.n[1] << " " << f.n[2] << "\n"
+      << "ElementType = MET_DOUBLE\n";
+    if (embedded) h << "HeaderSize = -1\n";
+    h << "ElementSpacing = " << f.spacing[0] << " " << f.spacing[1] << " " << f.spacing[2] << "\n"
+      << "ElementDataFile = " << data_file << "\n";
+    return h.str();
+}
+
+// header text (may be empty) followed by length doubles times scale
+inline void
+write_dose_file(const std::string& path, const std::string& header, const double* src, double scale, size_t length) {
+    std::vector<double> scaled;
+    if (src && scale != 1.0) {
+        scaled.assign(src, src + length);
+        for (auto& v : scaled) v *= scale;
+        src = scaled.data();
+    }
+    std::ofstream out(path, std::ios::out | std::ios::binary);
+    if (!out) {
+        std::cout << "Cannot write :" << path << std::endl;
+        return;
+    }
+    out.write(header.data(), (std::streamsize) header.size());
+    if (src) out.write(reinterpret_cast<const char*>(src), (std::streamsize) (length * sizeof(double)));
+    out.close();
+    if (!out.good()) std::cout << "Error occurred at writing time!" << std::endl;
+}
+
 inline void
 save_to_bin(const double* src, double scale, const std::string& filepath, const std::string& filename, size_t length) {
-    std::vector<double> dest(src, src + length);
-    if (scale != 1.0) for (auto& v : dest) v *= scale;
-    std::ofstream fid_bin(filepath + "/" + filename + ".raw", std::ios::out | std::ios::binary);
-    if (!fid_bin) std::cout << "Cannot write :" << filepath + "/" + filename + ".raw" << std::endl;
-    fid_bin.write(reinterpret_cast<const char*>(dest.data()), length * sizeof(double));
-    fid_bin.close();
+    write_dose_file(filepath + "/" + filename + ".raw", "", src, scale, length);
 }
 
 inline void
 save_to_mhd(const grid_desc& g, const double* src, double scale, const std::string& filepath, const std::string& filename,
             size_t length) {
-    float dx = g.xe[1]; dx -= g.xe[0];
-    float dy = g.ye[1]; dy -= g.ye[0];
-    float dz = g.ze[1]; dz -= g.ze[0];
-    const float x0 = g.xe[0] + dx * 0.5, y0 = g.ye[0] + dy * 0.5, z0 = g.ze[0] + dz * 0.5;
-    std::ofstream fid_header(filepath + "/" + filename + ".mhd", std::ios::out);
-    if (!fid_header) std::cout << "Cannot open file!" << std::endl;
-    fid_header << "ObjectType = Image\n";
-    fid_header << "NDims = 3\n";
-    fid_header << "BinaryData = True\n";
-    fid_header << "BinaryDataByteOrderMSB = False\n";
-    fid_header << "CompressedData = False\n";
-    fid_header << "TransformMatrix 1 0 0 0 1 0 0 0 1\n";
-    fid_header << "Offset " << x0 << " " << y0 << " " << z0 << std::endl;
-    fid_header << "CenterOfRotation 0 0 0\n";
-    fid_header << "AnatomicOrientation = RAI\n";
-    fid_header << "DimSize = " << g.nx() << " " << g.ny() << " " << g.nz() << "\n";
-    fid_header << "ElementType = MET_DOUBLE\n";
-    fid_header << "ElementSpacing = " << dx << " " << dy << " " << dz << "\n";
-    fid_header << "ElementDataFile = " << filename << ".raw"
-               << "\n";
-    fid_header.close();
-    if (!fid_header.good()) std::cout << "Error occurred at writing time!" << std::endl;
+    write_dose_file(filepath + "/" + filename + ".mhd", meta_image_header(frame_of(g), false, filename + ".raw"), nullptr, 1.0, 0);
     save_to_bin(src, scale, filepath, filename, length);
 }
 
 inline void
 save_to_mha(const grid_desc& g, const double* src, double scale, const std::string& filepath, const std::string& filename,
             size_t length) {
-    float dx = g.xe[1]; dx -= g.xe[0];
-    float dy = g.ye[1]; dy -= g.ye[0];
-    float dz = g.ze[1]; dz -= g.ze[0];
-    const float x0 = g.xe[0] + dx * 0.5, y0 = g.ye[0] + dy * 0.5, z0 = g.ze[0] + dz * 0.5;
-    std::cout << "x0 " << std::setprecision(9) << x0 << " y0 " << y0 << " z0 " << z0 << std::endl;
-    std::vector<double> dest(src, src + length);
-    if (scale != 1.0) for (auto& v : dest) v *= scale;
-    std::ofstream fid_header(filepath + "/" + filename + ".mha", std::ios::out | std::ios::binary);
-    if (!fid_header) std::cout << "Cannot open file!" << std::endl;
-    fid_header << "ObjectType = Image\n";
-    fid_header << "NDims = 3\n";
-    fid_header << "BinaryData = True\n";
-    fid_header << "BinaryDataByteOrderMSB = False\n";
-    fid_header << "CompressedData = False\n";
-    fid_header << "TransformMatrix = 1 0 0 0 1 0 0 0 1\n";
-    fid_header << "Origin = " << std::setprecision(9) << x0 << " " << y0 << " " << z0 << "\n";
-    fid_header << "CenterOfRotation = 0 0 0\n";
-    fid_header << "AnatomicOrientation = RAI\n";
-    fid_header << "DimSize = " << g.nx() << " " << g.ny() << " " << g.nz() << "\n";
-    fid_header << "ElementType = MET_DOUBLE\n";
-    fid_header << "HeaderSize = -1\n";
-    fid_header << "ElementSpacing = " << std::setprecision(9) << dx << " " << dy << " " << dz << "\n";
-    fid_header << "ElementDataFile = LOCAL\n";
-    fid_header.write(reinterpret_cast<const char*>(dest.data()), length * sizeof(double));
-    fid_header.close();
-    if (!fid_header.good()) std::cout << "Error occurred at writing time!" << std::endl;
+    const voxel_frame f = frame_of(g);
+    printf("x0 %.9g y0 %.9g z0 %.9g\n", f.centre0[0], f.centre0[1], f.centre0[2]);   // the reference prints the origin, :553
+    write_dose_file(filepath + "/" + filename + ".mha", meta_image_header(f, true, "LOCAL"), src, scale, length);
 }
 
 // ---------------------------------------------------------------------------------------------
