@@ -31,7 +31,11 @@
 #endif
 
 #ifndef MQI_K_PARK_DEPTH
-#define MQI_K_PARK_DEPTH 4   /* parked (voxel, spot, value) pairs per lane in front of the Dij table, see park_dij */
+#define MQI_K_PARK_DEPTH 0   /* > 0: finished (voxel, spot, value) pairs are parked per lane in shared memory and inserted by the whole warp
+                                at once (flush_parked); 0: the lane inserts at once.  Measured (profiles/r2_experiments.md): parking runs
+                                the probe code at 13 - 17 lanes instead of 5, but one insert per lane and turn keeps more table accesses in
+                                flight than a burst every sixth turn, and the 49 kB of parking slots come out of L1: 6.4e7 histories/s parked
+                                against 6.9e7 (round 1) at the reference's table size */
 #endif
 
 #ifndef MQI_K_ADV_BATCH
@@ -45,6 +49,9 @@
 #define MQI_K_RSP_EXACT 0    /* 1: the transport kernel evaluates spr_default in the reference's precision (rsp_eval_exact) */
 #endif
 
+#ifndef MQI_K_PROBE_WIDTH
+#define MQI_K_PROBE_WIDTH 4  /* consecutive slots of the Dij table whose keys one probe step loads together, see dij_probe_from */
+#endif
 #ifndef MQI_K_FIRST_PROBE
 #define MQI_K_FIRST_PROBE 2  /* slots of every parked pair whose keys are loaded up front, see flush_parked */
 #endif

@@ -44,7 +44,7 @@ constexpr int kQueueCap    = 32;
 enum QueueField { Q_PX = 0, Q_PY, Q_PZ, Q_DX, Q_DY, Q_DZ, Q_KE, Q_IX, Q_IY, Q_IZ, Q_H0, Q_H1, Q_SPOT, Q_NODE, Q_FIELDS };
 constexpr int kQueueWords  = Q_FIELDS * kQueueCap;
 constexpr size_t kTableBytes = kTableN * (2 * sizeof(float4) + sizeof(float2));
-constexpr int    kParkDepth  = MQI_K_PARK_DEPTH;   // parked Dij pairs per lane (DIJWC launches)
+constexpr int    kParkDepth  = MQI_K_PARK_DEPTH;   // parked Dij pairs per lane (DIJWC launches); 0 = insert at once
 constexpr size_t kParkBytesPerThread = (size_t) kParkDepth * (2 * sizeof(uint32_t) + sizeof(double));
 
 __host__ __device__ __forceinline__ size_t
@@ -374,24 +374,25 @@ dense_add(double* __restrict__ acc, unsigned cnb, double v, int accum_mode) {
 // open-addressing (voxel, spot) -> dose table with a single 64-bit CAS per claim.  Same hash
 // function, home slot and linear probing as insert_hashtable (mqi_transport.hpp:68-111), so the set
 // of occupied keys is identical; the reference's two independent 32-bit CAS (race B5) are replaced.
-// Probing reads four consecutive slots at once (independent loads, two or three 32-byte sectors) and then takes the
+// Probing reads kProbeWidth (four) consecutive slots at once (independent loads, two or three 32-byte sectors) and then takes the
 // first one in probe order that is free or holds the key: the same slot linear probing ends in -- a slot seen
 // occupied by another key stays so (keys are never removed), a slot seen free is claimed through the CAS, which
 // reports whoever won it -- with one dependent memory round trip for 85 % of the inserts at load factor 0.73
 // instead of 2.4.  `probes` slots of the sequence have already been rejected by the caller.
+constexpr int kProbeWidth = MQI_K_PROBE_WIDTH;
 __device__ __forceinline__ void
 dij_probe_from(DijSlot* table, unsigned long long capacity, unsigned long long slot, unsigned long long probes,
                unsigned long long key, double v, unsigned long long* counters) {
-    for (; probes < capacity; probes += 4) {
-        DijSlot*           e[4];
-        unsigned long long kk[4];
-        if (slot + 4 <= capacity) {   // no wrap-around inside this group of four (all but the last three home slots)
+    for (; probes < capacity; probes += kProbeWidth) {
+        DijSlot*           e[kProbeWidth];
+        unsigned long long kk[kProbeWidth];
+        if (slot + kProbeWidth <= capacity) {   // no wrap-around inside this group (all but the last home slots)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) e[i] = table + slot + i;
-            slot = slot + 4 == capacity ? 0 : slot + 4;
+            for (int i = 0; i < kProbeWidth; ++i) e[i] = table + slot + i;
+            slot = slot + kProbeWidth == capacity ? 0 : slot + kProbeWidth;
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kProbeWidth; ++i) {
                 e[i] = table + slot;
                 slot = slot + 1 == capacity ? 0 : slot + 1;
             }
@@ -399,9 +400,9 @@ dij_probe_from(DijSlot* table, unsigned long long capacity, unsigned long long s
         // L2 is the point of coherence of the table (the CAS and the adds are performed there): a cache-global
         // load sees every claimed key; a system-scope volatile load costs more and buys nothing
 #pragma unroll
-        for (int i = 0; i < 4; ++i) kk[i] = __ldcg(&e[i]->key);
+        for (int i = 0; i < kProbeWidth; ++i) kk[i] = __ldcg(&e[i]->key);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < kProbeWidth; ++i) {
             unsigned long long prev = kk[i];
             if (prev == kEmptyKey64) prev = atomicCAS(&e[i]->key, kEmptyKey64, key);
             if (prev == kEmptyKey64 || prev == key) {
@@ -492,13 +493,19 @@ struct DijCombine {
 // slots together once a lane has filled its last one (the vote at the top of the turn): the probe sequences of
 // ~ 2.5 pairs per lane then run at full width and overlap their latencies.
 __device__ __forceinline__ void
-park_dij(const Smem& sm, DijCombine& wc, uint32_t spot_ind) {
+park_dij(const Params& P, const Smem& sm, DijCombine& wc, uint32_t spot_ind) {
     if (wc.key != kEmptyKey32) {
+#if MQI_K_PARK_DEPTH > 0
         const int o = wc.npark * blockDim.x + threadIdx.x;
         sm.park_k1[o]  = wc.key;
         sm.park_k2[o]  = spot_ind;
         sm.park_val[o] = wc.val;
         wc.npark += 1;
+#else
+        // MQI_K_PARK_DEPTH 0 (the default, see mqi_kernels.h): the lane inserts its finished pair at once
+        const ScorerDev& S = P.sc[P.dij_wc_scorer];
+        dij_add(S.table, S.capacity, wc.key, spot_ind, wc.val, P.counters);
+#endif
         wc.key = kEmptyKey32;
     }
 }
@@ -508,6 +515,7 @@ park_dij(const Smem& sm, DijCombine& wc, uint32_t spot_ind) {
 // flight: phase A computes the home slots of ALL parked pairs of the lane and issues the key loads of their first
 // kFirstProbe slots back to back (up to kParkDepth x kFirstProbe independent loads per lane, ~ 250 per warp), phase B
 // resolves the pairs from the loaded keys; the ~ 15 % that need to probe further do so one at a time (dij_probe_more).
+#if MQI_K_PARK_DEPTH > 0
 constexpr int kFirstProbe = MQI_K_FIRST_PROBE;
 __device__ __noinline__ void
 flush_parked(const Params& P, int npark) {
@@ -568,6 +576,11 @@ flush_parked(const Params& P, int npark) {
     }
 }
 
+#else
+__device__ __forceinline__ void
+flush_parked(const Params&, int) {}
+#endif
+
 // Scorer sets known at compile time: the loop over P.sc with its kind dispatch, quirk and accumulation-mode tests
 // (~ 25 issue slots per scorer and step, and 30 spilled registers) is what the general kernel pays; the three
 // scorer lists the configs actually use get the same hit values from straight-line code.
@@ -606,7 +619,7 @@ score_step(const Params& P, const Smem& sm, const MatEntry& M, unsigned cnb, uin
         if (wc.key == cnb) {
             wc.val += v;
         } else {
-            park_dij(sm, wc, spot_ind);
+            park_dij(P, sm, wc, spot_ind);
             wc.key = cnb;
             wc.val = v;
         }
@@ -650,7 +663,7 @@ score_step(const Params& P, const Smem& sm, const MatEntry& M, unsigned cnb, uin
                 if (wc.key == cnb) {
                     wc.val += v;
                 } else {
-                    park_dij(sm, wc, spot_ind);
+                    park_dij(P, sm, wc, spot_ind);
                     wc.key = cnb;
                     wc.val = v;
                 }
@@ -975,8 +988,8 @@ transport_kernel(const __grid_constant__ Params P) {
         // slots -- is skipped altogether.
         // (DIJWC: a lane whose last parking slot is taken sends the warp through the prologue as well, where all
         // parked pairs are inserted)
-        if (!__all_sync(0xffffffffu, (fl & FL_ALIVE) && (!DIJWC || wc.npark < kParkDepth))) {
-        if (DIJWC) {
+        if (!__all_sync(0xffffffffu, (fl & FL_ALIVE) && (!(DIJWC && kParkDepth > 0) || wc.npark < kParkDepth))) {
+        if (DIJWC && kParkDepth > 0) {
             if (__any_sync(0xffffffffu, wc.npark == kParkDepth)) {
                 flush_parked(P, wc.npark);
                 wc.npark = 0;
@@ -1000,7 +1013,7 @@ transport_kernel(const __grid_constant__ Params P) {
         }
         bool need = false;   // the lane needs a new primary
         if (!(fl & (FL_ALIVE | FL_DONE)) && !(MULTI && (fl & FL_ADVANCE) && !hand_over)) {
-            if (DIJWC) park_dij(sm, wc, spot_ind);   // the track ended: park its pending write-combined Dij hit
+            if (DIJWC) park_dij(P, sm, wc, spot_ind);   // the track ended: park its pending write-combined Dij hit
             if ((MULTI && (fl & FL_ADVANCE)) || sp > 0) {
                 TrackIO T;
                 T.px = px; T.py = py; T.pz = pz; T.dx = dx; T.dy = dy; T.dz = dz; T.ke = ke;
@@ -1323,7 +1336,7 @@ transport_kernel(const __grid_constant__ Params P) {
         }
     }
 
-    if (DIJWC) flush_parked(P, wc.npark);   // every track has ended and parked its last pair
+    if (DIJWC && kParkDepth > 0) flush_parked(P, wc.npark);   // every track has ended and parked its last pair
     // per-lane step counter -> global (one atomic per lane per launch)
     if (COUNTED && n_steps && P.count_steps) atomicAdd(P.counters + C_STEPS, (unsigned long long) n_steps);
 }
@@ -1604,7 +1617,7 @@ size_t
 transport_smem_bytes(int n_edge_floats, int n_nodes, bool dij_park) {
     const size_t block = (size_t) transport_block(n_nodes > 1);
     return smem_queue_offset(n_edge_floats, n_nodes) + (block / 32) * kQueueWords * sizeof(uint32_t) +
-           (dij_park ? kParkBytesPerThread * block : 0);
+           (dij_park && kParkDepth > 0 ? kParkBytesPerThread * block : 0);
 }
 
 // threads per CTA of the kernels of a world with / without beamline children (the multi-node kernels carry a
