@@ -181,8 +181,8 @@ MQI_API int mqi_get_run_stats(mqi_handle* h, mqi_run_stats* out);
  * "l2_persist" (0/1: persisting L2 access window over the material volume; off by default, it measured
  * -0.25 % on the C1 workload whose hot part of the volume is cache resident anyway),
  * "dij_write_combine" (0/1, default 1: consecutive hits of a track on one (voxel, spot) key are summed in
- * registers, parked in the lane's shared-memory slots when the voxel changes and inserted into the Dij table by the
- * whole warp at once; +46 % histories/s on the 5 000-spot configuration),
+ * registers and inserted into the Dij table once, when the voxel changes or the track ends; +46 % histories/s on the
+ * 5 000-spot configuration),
  * "rsp_exact" (0/1: mqi_dev_rsp evaluates spr_default in the reference's own precision -- fp64 energy term, correctly
  * rounded pow -- and is then bit-exact against the reference; the transport kernel keeps the fp32 evaluation, within
  * 4 ulp, because the exact one costs 46 % of the C1 throughput: DESIGN.md section 6) */

@@ -368,6 +368,7 @@ fill_params(const mqi_handle* h, Params& p) {
         p.sc[i].dense    = h->scorers[i].d_dense;
         p.sc[i].table    = h->scorers[i].d_table;
         p.sc[i].capacity = h->scorers[i].capacity;
+        p.sc[i].cap_magic = remainder_magic(h->scorers[i].capacity);
         p.sc[i].roi      = h->scorers[i].d_roi;
     }
     p.quirks      = h->quirks;
@@ -901,7 +902,7 @@ mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t cou
         p.src.vertices = h->d_vertices + first_history;
         p.src.spot_ids = h->d_spot_ids ? h->d_spot_ids + first_history : nullptr;
     }
-    const size_t smem = transport_smem_bytes(p.n_edge_floats, p.n_nodes, p.dij_wc_scorer >= 0);
+    const size_t smem = transport_smem_bytes(p.n_edge_floats, p.n_nodes);
     if (smem > 200 * 1024) return fail(MQI_EINVAL, "the world's grid edges do not fit into shared memory");
     int          bps  = 0;
     CU(transport_occupancy(p, h->variant, smem, &bps));

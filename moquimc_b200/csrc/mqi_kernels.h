@@ -24,25 +24,21 @@
 #define MQI_K_BLOCK 768
 #endif
 #ifndef MQI_K_BLOCK_MULTI
-#define MQI_K_BLOCK_MULTI 768   /* threads per CTA of the multi-node kernels (worlds with beamline children) */
+#define MQI_K_BLOCK_MULTI 640   /* threads per CTA of the multi-node kernels (worlds with beamline children): 96 registers per thread
+                                   instead of 80 take the per-lane node descriptor without spilling (8 B against 84 B); measured on
+                                   the range shifter + aperture workload 768: 1.12e8, 640: 1.15e8, 512: 1.07e8 histories/s */
 #endif
 #ifndef MQI_K_MIN_BLOCKS
 #define MQI_K_MIN_BLOCKS 1   /* 24 warps/SM at <= 80 registers/thread in ONE CTA: one copy of the shared-memory tables leaves the most L1; measured best of 128x5 ... 768x1 on B200 (profiles/r1_experiments.md) */
 #endif
 
-#ifndef MQI_K_PARK_DEPTH
-#define MQI_K_PARK_DEPTH 0   /* > 0: finished (voxel, spot, value) pairs are parked per lane in shared memory and inserted by the whole warp
-                                at once (flush_parked); 0: the lane inserts at once.  Measured (profiles/r2_experiments.md): parking runs
-                                the probe code at 13 - 17 lanes instead of 5, but one insert per lane and turn keeps more table accesses in
-                                flight than a burst every sixth turn, and the 49 kB of parking slots come out of L1: 6.4e7 histories/s parked
-                                against 6.9e7 (round 1) at the reference's table size */
-#endif
 
 #ifndef MQI_K_ADV_BATCH
-#define MQI_K_ADV_BATCH 12   /* multi-node worlds: lanes of a warp that hand their track over to the next child together ... */
+#define MQI_K_ADV_BATCH 6    /* multi-node worlds: lanes of a warp that hand their track over to the next child together ... */
 #endif
 #ifndef MQI_K_ADV_TURNS
-#define MQI_K_ADV_TURNS 6    /* ... or after the first of them has waited this many turns */
+#define MQI_K_ADV_TURNS 10   /* ... or after the first of them has waited this many turns (1 / 0: 1.04e8, 12 / 6: 1.12e8, 6 / 10: 1.18e8
+                                with 640 threads per CTA, profiles/r2_experiments.md) */
 #endif
 
 #ifndef MQI_K_RSP_EXACT
@@ -50,10 +46,8 @@
 #endif
 
 #ifndef MQI_K_PROBE_WIDTH
-#define MQI_K_PROBE_WIDTH 4  /* consecutive slots of the Dij table whose keys one probe step loads together, see dij_probe_from */
-#endif
-#ifndef MQI_K_FIRST_PROBE
-#define MQI_K_FIRST_PROBE 2  /* slots of every parked pair whose keys are loaded up front, see flush_parked */
+#define MQI_K_PROBE_WIDTH 2  /* consecutive slots of the Dij table whose keys one probe step loads together (dij_probe_from); C4 at the
+                                reference's table size: 1: 6.3e7, 2: 8.4e7, 4: 7.3e7 histories/s (profiles/r2_experiments.md) */
 #endif
 
 #ifndef MQI_K_LATE_LUT
@@ -72,7 +66,7 @@ struct BeamletDev;
 struct VertexDev;
 
 int         transport_block(bool multi);
-size_t      transport_smem_bytes(int n_edge_floats, int n_nodes, bool dij_park = false);
+size_t      transport_smem_bytes(int n_edge_floats, int n_nodes);
 bool        transport_is_simple(const Params& p);
 cudaError_t transport_occupancy(const Params& p, int variant, size_t smem, int* blocks_per_sm);
 cudaError_t launch_transport(const Params& p, int variant, int grid, size_t smem, cudaStream_t st);

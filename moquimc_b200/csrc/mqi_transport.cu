@@ -29,11 +29,6 @@ struct Smem {
     const float*  edges;   // node k: xe | ye | ze at edges + nodes[k].edge_off (single node: offset 0)
     const GridDev* nodes;  // multi-node launches only
     uint32_t*     queue;   // kQueueWords words per warp
-    // DIJWC launches: finished (voxel, spot, value) pairs parked per lane until the warp inserts them together,
-    // structure of arrays, entry d of thread t at [d * blockDim.x + t]
-    uint32_t*     park_k1;
-    uint32_t*     park_k2;
-    double*       park_val;
 };
 
 // queue of pre-sampled primaries, one per warp, structure of arrays: field f of entry e at
@@ -44,8 +39,6 @@ constexpr int kQueueCap    = 32;
 enum QueueField { Q_PX = 0, Q_PY, Q_PZ, Q_DX, Q_DY, Q_DZ, Q_KE, Q_IX, Q_IY, Q_IZ, Q_H0, Q_H1, Q_SPOT, Q_NODE, Q_FIELDS };
 constexpr int kQueueWords  = Q_FIELDS * kQueueCap;
 constexpr size_t kTableBytes = kTableN * (2 * sizeof(float4) + sizeof(float2));
-constexpr int    kParkDepth  = MQI_K_PARK_DEPTH;   // parked Dij pairs per lane (DIJWC launches); 0 = insert at once
-constexpr size_t kParkBytesPerThread = (size_t) kParkDepth * (2 * sizeof(uint32_t) + sizeof(double));
 
 __host__ __device__ __forceinline__ size_t
 smem_nodes_offset(int n_edge_floats) { return (kTableBytes + (size_t) n_edge_floats * sizeof(float) + 15) & ~(size_t) 15; }
@@ -64,9 +57,6 @@ smem_view(unsigned char* raw, int n_edge_floats, int n_nodes) {
     sm.edges = reinterpret_cast<float*>(bs + kTableN);
     sm.nodes = reinterpret_cast<const GridDev*>(raw + smem_nodes_offset(n_edge_floats));
     sm.queue = reinterpret_cast<uint32_t*>(raw + smem_queue_offset(n_edge_floats, n_nodes));
-    sm.park_val = reinterpret_cast<double*>(sm.queue + (blockDim.x / 32) * kQueueWords);   // 16-byte aligned: kQueueWords % 4 == 0
-    sm.park_k1  = reinterpret_cast<uint32_t*>(sm.park_val + kParkDepth * blockDim.x);
-    sm.park_k2  = sm.park_k1 + kParkDepth * blockDim.x;
     return sm;
 }
 
@@ -417,21 +407,21 @@ dij_probe_from(DijSlot* table, unsigned long long capacity, unsigned long long s
 // home slot of a (voxel, spot) pair; key2 = 0xffffffff is the reference's dense mode: slot = voxel, key2 := 0
 // (mqi_transport.hpp:78-81).  Returns false if that slot lies outside the table.
 __device__ __forceinline__ bool
-dij_home(unsigned long long capacity, uint32_t key1, uint32_t& key2, unsigned long long& slot) {
+dij_home(unsigned long long capacity, unsigned long long magic, uint32_t key1, uint32_t& key2, unsigned long long& slot) {
     if (key2 == kEmptyKey32) {
         slot = key1;
         key2 = 0;
         return slot < capacity;
     }
-    slot = hash_fun(key1, key2, capacity);
+    slot = hash_fun_magic(key1, key2, capacity, magic);
     return true;
 }
 
 __device__ __forceinline__ void
-dij_add_inline(DijSlot* table, unsigned long long capacity, uint32_t key1, uint32_t key2, double v,
+dij_add_inline(DijSlot* table, unsigned long long capacity, unsigned long long magic, uint32_t key1, uint32_t key2, double v,
                unsigned long long* counters) {
     unsigned long long slot;
-    if (!dij_home(capacity, key1, key2, slot)) {   // a table smaller than the grid: count the hit instead of writing outside it
+    if (!dij_home(capacity, magic, key1, key2, slot)) {   // a table smaller than the grid: count the hit instead of writing outside it
         atomicAdd(counters + C_DIJ_FULL, 1ull);
         return;
     }
@@ -439,15 +429,8 @@ dij_add_inline(DijSlot* table, unsigned long long capacity, uint32_t key1, uint3
 }
 
 __device__ __noinline__ void
-dij_add(DijSlot* table, unsigned long long capacity, uint32_t key1, uint32_t key2, double v,
-        unsigned long long* counters) {
-    dij_add_inline(table, capacity, key1, key2, v, counters);
-}
-
-__device__ __noinline__ void
-dij_probe_more(DijSlot* table, unsigned long long capacity, unsigned long long slot, unsigned long long probes,
-               unsigned long long key, double v, unsigned long long* counters) {
-    dij_probe_from(table, capacity, slot, probes, key, v, counters);
+dij_add(const ScorerDev& S, uint32_t key1, uint32_t key2, double v, unsigned long long* counters) {
+    dij_add_inline(S.table, S.capacity, S.cap_magic, key1, key2, v, counters);
 }
 
 struct StepResult {
@@ -484,102 +467,19 @@ lett_hit(int kind, float dE, float len, float rho) {
 struct DijCombine {
     uint32_t key;   // voxel of the pending hit, kEmptyKey32 = nothing pending
     double   val;
-    int      npark; // pairs this lane has parked in shared memory (<= kParkDepth)
 };
 
-// The finished pair of a lane -- its voxel changed, or its track ended -- is not inserted by that lane on its own
-// (a divergent region of 4.7 lanes in which the whole warp waited for a chain of DRAM round trips every turn,
-// profiles/r1_c4_dij_wc_source_hotspots.txt) but parked in the lane's shared-memory slots.  The warp empties all
-// slots together once a lane has filled its last one (the vote at the top of the turn): the probe sequences of
-// ~ 2.5 pairs per lane then run at full width and overlap their latencies.
+// The finished pair of a lane -- its voxel changed, or its track ended -- is inserted by that lane at once.  Parking the
+// pairs in per-lane shared-memory slots and letting the whole warp insert them together (round 2 experiment,
+// profiles/r2_experiments.md) ran the probe code at 13 - 17 lanes instead of 5 but was slower: one insert per lane and
+// turn keeps more table accesses in flight than a burst every sixth turn, and 49 kB of parking slots came out of L1.
 __device__ __forceinline__ void
-park_dij(const Params& P, const Smem& sm, DijCombine& wc, uint32_t spot_ind) {
+flush_dij(const Params& P, DijCombine& wc, uint32_t spot_ind) {
     if (wc.key != kEmptyKey32) {
-#if MQI_K_PARK_DEPTH > 0
-        const int o = wc.npark * blockDim.x + threadIdx.x;
-        sm.park_k1[o]  = wc.key;
-        sm.park_k2[o]  = spot_ind;
-        sm.park_val[o] = wc.val;
-        wc.npark += 1;
-#else
-        // MQI_K_PARK_DEPTH 0 (the default, see mqi_kernels.h): the lane inserts its finished pair at once
-        const ScorerDev& S = P.sc[P.dij_wc_scorer];
-        dij_add(S.table, S.capacity, wc.key, spot_ind, wc.val, P.counters);
-#endif
+        dij_add(P.sc[P.dij_wc_scorer], wc.key, spot_ind, wc.val, P.counters);
         wc.key = kEmptyKey32;
     }
 }
-
-// Called by the whole warp; returns with every lane's slots empty.  The insert is a chain of dependent, uncoalesced
-// memory round trips (home slot -> key -> CAS -> add), and what bounds the sparse scorer is how many of them are in
-// flight: phase A computes the home slots of ALL parked pairs of the lane and issues the key loads of their first
-// kFirstProbe slots back to back (up to kParkDepth x kFirstProbe independent loads per lane, ~ 250 per warp), phase B
-// resolves the pairs from the loaded keys; the ~ 15 % that need to probe further do so one at a time (dij_probe_more).
-#if MQI_K_PARK_DEPTH > 0
-constexpr int kFirstProbe = MQI_K_FIRST_PROBE;
-__device__ __noinline__ void
-flush_parked(const Params& P, int npark) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Smem               sm  = smem_view(smem_raw, P.n_edge_floats, P.n_nodes);
-    const ScorerDev&         S   = P.sc[P.dij_wc_scorer];
-    DijSlot* const           tab = S.table;
-    const unsigned long long cap = S.capacity;
-    unsigned long long home[kParkDepth];
-    unsigned long long kk[kParkDepth][kFirstProbe];
-#pragma unroll
-    for (int d = 0; d < kParkDepth; ++d) {
-        home[d] = cap;   // "no pair" / "outside the table"
-        if (d < npark) {
-            const int o  = d * blockDim.x + threadIdx.x;
-            uint32_t  k2 = sm.park_k2[o];
-            unsigned long long h;
-            if (dij_home(cap, sm.park_k1[o], k2, h)) {
-                home[d] = h;
-                unsigned long long s = h;
-#pragma unroll
-                for (int i = 0; i < kFirstProbe; ++i) {
-                    kk[d][i] = __ldcg(&tab[s].key);
-                    s        = s + 1 == cap ? 0 : s + 1;
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int d = 0; d < kParkDepth; ++d) {
-        if (d < npark) {
-            const int      o  = d * blockDim.x + threadIdx.x;
-            const uint32_t k1 = sm.park_k1[o];
-            uint32_t       k2 = sm.park_k2[o];
-            const double   v  = sm.park_val[o];
-            if (k2 == kEmptyKey32) k2 = 0;
-            const unsigned long long key = ((unsigned long long) k2 << 32) | k1;
-            if (home[d] >= cap) {
-                atomicAdd(P.counters + C_DIJ_FULL, 1ull);
-            } else {
-                unsigned long long s    = home[d];
-                bool               done = false;
-#pragma unroll
-                for (int i = 0; i < kFirstProbe; ++i) {
-                    if (!done) {
-                        unsigned long long prev = kk[d][i];
-                        if (prev == kEmptyKey64) prev = atomicCAS(&tab[s].key, kEmptyKey64, key);
-                        if (prev == kEmptyKey64 || prev == key) {
-                            red_add_f64(&tab[s].value, v);
-                            done = true;
-                        }
-                        s = s + 1 == cap ? 0 : s + 1;
-                    }
-                }
-                if (!done) dij_probe_more(tab, cap, s, (unsigned long long) kFirstProbe, key, v, P.counters);
-            }
-        }
-    }
-}
-
-#else
-__device__ __forceinline__ void
-flush_parked(const Params&, int) {}
-#endif
 
 // Scorer sets known at compile time: the loop over P.sc with its kind dispatch, quirk and accumulation-mode tests
 // (~ 25 issue slots per scorer and step, and 30 spilled registers) is what the general kernel pays; the three
@@ -619,7 +519,7 @@ score_step(const Params& P, const Smem& sm, const MatEntry& M, unsigned cnb, uin
         if (wc.key == cnb) {
             wc.val += v;
         } else {
-            park_dij(P, sm, wc, spot_ind);
+            flush_dij(P, wc, spot_ind);
             wc.key = cnb;
             wc.val = v;
         }
@@ -663,12 +563,12 @@ score_step(const Params& P, const Smem& sm, const MatEntry& M, unsigned cnb, uin
                 if (wc.key == cnb) {
                     wc.val += v;
                 } else {
-                    park_dij(P, sm, wc, spot_ind);
+                    flush_dij(P, wc, spot_ind);
                     wc.key = cnb;
                     wc.val = v;
                 }
             } else {
-                dij_add(P.sc[s].table, P.sc[s].capacity, cnb, spot_ind, v, P.counters);
+                dij_add(P.sc[s], cnb, spot_ind, v, P.counters);
             }
         } else {
             dense_add(P.sc[s].dense, cnb, v, P.accum_mode);
@@ -969,7 +869,7 @@ transport_kernel(const __grid_constant__ Params P) {
     const uint32_t k0 = (uint32_t) P.seed, k1 = (uint32_t) (P.seed >> 32);
     unsigned n_steps = 0;
     DijCombine wc;   // DIJWC instantiations only (a Dij scorer with write-combining): costs three registers
-    wc.key = kEmptyKey32; wc.val = 0.0; wc.npark = 0;
+    wc.key = kEmptyKey32; wc.val = 0.0;
 
     // the warp's queue of pre-sampled primaries: entries in the queue | history counter exhausted << 16
     // (warp-uniform; one register)
@@ -986,15 +886,7 @@ transport_kernel(const __grid_constant__ Params P) {
         // One vote is the join of the turn and the fast path in one: while every lane of the warp owns a track
         // (86 % of the turns at C1) the re-arm prologue -- two more votes and the tests around them, ~20 issue
         // slots -- is skipped altogether.
-        // (DIJWC: a lane whose last parking slot is taken sends the warp through the prologue as well, where all
-        // parked pairs are inserted)
-        if (!__all_sync(0xffffffffu, (fl & FL_ALIVE) && (!(DIJWC && kParkDepth > 0) || wc.npark < kParkDepth))) {
-        if (DIJWC && kParkDepth > 0) {
-            if (__any_sync(0xffffffffu, wc.npark == kParkDepth)) {
-                flush_parked(P, wc.npark);
-                wc.npark = 0;
-            }
-        }
+        if (!__all_sync(0xffffffffu, fl & FL_ALIVE)) {
         // ------------------------------------------------------------------ restart the lane
         // Node-to-node hand-overs (MULTI) are batched: the tracks of a warp were started together, so they leave a
         // beamline child within a few turns of each other.  A lane whose track has left its child waits (idle) until
@@ -1013,7 +905,7 @@ transport_kernel(const __grid_constant__ Params P) {
         }
         bool need = false;   // the lane needs a new primary
         if (!(fl & (FL_ALIVE | FL_DONE)) && !(MULTI && (fl & FL_ADVANCE) && !hand_over)) {
-            if (DIJWC) park_dij(P, sm, wc, spot_ind);   // the track ended: park its pending write-combined Dij hit
+            if (DIJWC) flush_dij(P, wc, spot_ind);   // the track ended: insert its pending write-combined Dij hit
             if ((MULTI && (fl & FL_ADVANCE)) || sp > 0) {
                 TrackIO T;
                 T.px = px; T.py = py; T.pz = pz; T.dx = dx; T.dy = dy; T.dz = dz; T.ke = ke;
@@ -1336,7 +1228,6 @@ transport_kernel(const __grid_constant__ Params P) {
         }
     }
 
-    if (DIJWC && kParkDepth > 0) flush_parked(P, wc.npark);   // every track has ended and parked its last pair
     // per-lane step counter -> global (one atomic per lane per launch)
     if (COUNTED && n_steps && P.count_steps) atomicAdd(P.counters + C_STEPS, (unsigned long long) n_steps);
 }
@@ -1473,7 +1364,7 @@ dev_insert_kernel(ScorerDev sc, const uint32_t* __restrict__ k1, const uint32_t*
                   const double* __restrict__ v, size_t n, unsigned long long* counters) {
     for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
         if (!(v[i] > 0.0)) continue;
-        if (sc.kind == MQI_K_DIJ) dij_add(sc.table, sc.capacity, k1[i], k2[i], v[i], counters);
+        if (sc.kind == MQI_K_DIJ) dij_add(sc, k1[i], k2[i], v[i], counters);
         else atomicAdd(sc.dense + k1[i], v[i]);
     }
 }
@@ -1614,10 +1505,9 @@ static inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
 }
 
 size_t
-transport_smem_bytes(int n_edge_floats, int n_nodes, bool dij_park) {
+transport_smem_bytes(int n_edge_floats, int n_nodes) {
     const size_t block = (size_t) transport_block(n_nodes > 1);
-    return smem_queue_offset(n_edge_floats, n_nodes) + (block / 32) * kQueueWords * sizeof(uint32_t) +
-           (dij_park && kParkDepth > 0 ? kParkBytesPerThread * block : 0);
+    return smem_queue_offset(n_edge_floats, n_nodes) + (block / 32) * kQueueWords * sizeof(uint32_t);
 }
 
 // threads per CTA of the kernels of a world with / without beamline children (the multi-node kernels carry a

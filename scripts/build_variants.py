@@ -8,10 +8,10 @@ from moquimc_b200 import build as B
 
 VARIANTS = {
     "m640": (768, 1, 0, "-DMQI_K_BLOCK_MULTI=640"), "m512": (768, 1, 0, "-DMQI_K_BLOCK_MULTI=512"), "m768": (768, 1, 0),
-    "rspx": (768, 1, 0, "-DMQI_K_RSP_EXACT=1"), "park3": (768, 1, 0, "-DMQI_K_PARK_DEPTH=3"), "park6": (768, 1, 0, "-DMQI_K_PARK_DEPTH=6"),
+    "rspx": (768, 1, 0, "-DMQI_K_RSP_EXACT=1"), "pw3": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=3"),
     "adv1": (768, 1, 0, "-DMQI_K_ADV_BATCH=1", "-DMQI_K_ADV_TURNS=0"), "adv10": (768, 1, 0, "-DMQI_K_ADV_BATCH=6", "-DMQI_K_ADV_TURNS=10", "-DMQI_K_BLOCK_MULTI=640"),
-    "fp4": (768, 1, 0, "-DMQI_K_FIRST_PROBE=4"), "pw1": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=1"), "pw2": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=2"),
-    "park4": (768, 1, 0, "-DMQI_K_PARK_DEPTH=4"), "adv10b": (768, 1, 0, "-DMQI_K_ADV_BATCH=6", "-DMQI_K_ADV_TURNS=10"),
+    "pw1": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=1"), "pw2": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=2"),
+    "pw4": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=4"), "adv10b": (768, 1, 0, "-DMQI_K_ADV_BATCH=6", "-DMQI_K_ADV_TURNS=10"),
     "cur": (768, 1, 0), "ph10": (768, 1, 0, "-DMQI_K_PHILOX_ROUNDS=10"),
     "b256": (256, 4, 0), "b512": (512, 2, 0), "b128": (128, 8, 0), "b256_3": (256, 3, 0),
     "early_lut": (256, 4, 0, "-DMQI_K_LATE_LUT=0"), "base": (256, 4, 0),

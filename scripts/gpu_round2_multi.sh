@@ -5,7 +5,12 @@ N=${1:-2}
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi -L | head -8
-timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_tps.py -m gpu -q -k "multi or devices or two_devices" > gpurun_out/r2m${N}_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/r2m${N}_tests.log
+if [ -n "$FULL_SUITE" ]; then
+  timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r2m${N}_tests.log 2>&1; echo "tests rc=$?"; grep -E "passed|failed|FAILED" gpurun_out/r2m${N}_tests.log | head
+  timeout 300 python scripts/config_bench.py c4 c4big rs 2>&1 | cut -c1-50,100-330
+else
+  timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_tps.py -m gpu -q > gpurun_out/r2m${N}_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/r2m${N}_tests.log
+fi
 for n in $( [ "$N" = 8 ] && echo "8 4 2" || echo "$N" ); do
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) bench.py --gpus $n --steps 5 --warmup 3 \
       > gpurun_out/r2m_bench_${n}gpu.json 2> gpurun_out/r2m_bench_${n}gpu.err; echo "bench $n rc=$?"; cut -c1-200 gpurun_out/r2m_bench_${n}gpu.json

@@ -15,11 +15,14 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
         'l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_local_op_st.sum',
         'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_red.sum.pct_of_peak_sustained_elapsed',
-        'lts__t_sectors_op_red.sum', 'lts__t_sectors_srcunit_tex_op_red.sum']
+        'lts__t_sectors_op_red.sum', 'lts__t_sectors_srcunit_tex_op_red.sum', 'lts__t_sectors_srcunit_tex_op_atom.sum',
+        'l1tex__t_requests_pipe_lsu_mem_global_op_red.sum', 'l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_red.sum',
+        'lts__t_sectors_srcunit_tex_op_read.sum', 'launch__shared_mem_per_block_dynamic']
 
 
 def main(rep, out, note):
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    # a .csv argument is the raw page already exported on the GPU box (scripts/gpu_ncu_cmd.sh keeps only the CSV pages)
+    raw = open(rep).read() if rep.endswith('.csv') else subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     r = list(csv.reader(raw.splitlines()))
     h, u, v = r[0], r[1], r[2]
     d = {}

@@ -298,10 +298,12 @@ def test_c3like_head_dij_rows_against_reference_cuda(golden_dir):
     idd, ref_idd = rows.sum(axis=(2, 3)), g["dij_row_idd"].astype(np.float64)
     for i in range(ns):
         assert M.gamma_1d(ref_idd[i], idd[i], 2.5, dd=0.02, dta_mm=2.5)[0] >= 0.97, i
+        # centroid of the beam's-eye projection where the fixture (stored as float16 of the largest value) resolves it
         a, b = rows[i].sum(axis=0), g["dij_row_xy_rel"][i].astype(np.float64)
-        cy = lambda p: (np.arange(ny)[:, None] * p).sum() / p.sum()   # noqa: E731
-        cx = lambda p: (np.arange(nx)[None, :] * p).sum() / p.sum()   # noqa: E731
-        assert abs(cy(a) - cy(b)) < 0.15 and abs(cx(a) - cx(b)) < 0.15, i
+        core = b > 0.01 * b.max()
+        cy = lambda p: (np.arange(ny)[:, None] * p * core).sum() / (p * core).sum()   # noqa: E731
+        cx = lambda p: (np.arange(nx)[None, :] * p * core).sum() / (p * core).sum()   # noqa: E731
+        assert abs(cy(a) - cy(b)) < 0.15 and abs(cx(a) - cx(b)) < 0.15, (i, cy(a) - cy(b), cx(a) - cx(b))
     # three rows voxel by voxel (the reference's row has 1e5 histories: compare where it is well populated)
     full_ref = g["dij_rows_full_q"].astype(np.float64) * (meta["rows_max"] / meta["rows_levels"])
     for j, i in enumerate(meta["rows_full"]):
