@@ -296,6 +296,7 @@ def test_c3like_head_dij_rows_against_reference_cuda(golden_dir):
     assert abs(tot.sum() / ref_tot.sum() - 1.0) < 2e-3
     # depth profile and beam's-eye projection of every row
     idd, ref_idd = rows.sum(axis=(2, 3)), g["dij_row_idd"].astype(np.float64)
+    dcx = []
     for i in range(ns):
         assert M.gamma_1d(ref_idd[i], idd[i], 2.5, dd=0.02, dta_mm=2.5)[0] >= 0.97, i
         # centroid of the beam's-eye projection where the fixture (stored as float16 of the largest value) resolves it
@@ -303,7 +304,12 @@ def test_c3like_head_dij_rows_against_reference_cuda(golden_dir):
         core = b > 0.01 * b.max()
         cy = lambda p: (np.arange(ny)[:, None] * p * core).sum() / (p * core).sum()   # noqa: E731
         cx = lambda p: (np.arange(nx)[None, :] * p * core).sum() / (p * core).sum()   # noqa: E731
-        assert abs(cy(a) - cy(b)) < 0.15 and abs(cx(a) - cx(b)) < 0.15, (i, cy(a) - cy(b), cx(a) - cx(b))
+        # the beams lie obliquely in the xz plane (gantry 30 degrees): the projection along z maps the noise of the depth
+        # dose into x, where a row of the reference's 1e5 histories scatters by 0.06 voxels (1 sigma, measured with
+        # the restatement); in y by 0.02
+        dcx.append(cx(a) - cx(b))
+        assert abs(cy(a) - cy(b)) < 0.15 and abs(dcx[-1]) < 0.35, (i, cy(a) - cy(b), dcx[-1])
+    assert abs(np.mean(dcx)) < 0.06, np.mean(dcx)     # twenty rows: no common shift
     # three rows voxel by voxel (the reference's row has 1e5 histories: compare where it is well populated)
     full_ref = g["dij_rows_full_q"].astype(np.float64) * (meta["rows_max"] / meta["rows_levels"])
     for j, i in enumerate(meta["rows_full"]):
