@@ -791,7 +791,7 @@ mqi_set_option(mqi_handle* h, const char* key, int64_t value) {
     const std::string k(key);
     if (k == "count_steps") h->count_steps = value != 0;
     else if (k == "blocks_per_sm") h->blocks_per_sm_override = (int) value;
-    else if (k == "l2_persist") h->l2_persist = value != 0;
+    else if (k == "l2_persist") h->l2_persist = (int) value;   // 0 off, 1 material volume, 2 the first dense scorer's grid
     else if (k == "dij_write_combine") h->dij_write_combine = value != 0;
     else if (k == "rsp_exact") h->rsp_exact = value != 0;
     else return fail(MQI_EINVAL, "unknown option " + k);
@@ -922,10 +922,16 @@ mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t cou
         std::memset(&attr, 0, sizeof(attr));
         bool set_window = false;
         if (h->l2_persist && h->l2_persist_max > 0 && h->l2_window_max > 0) {
-            const size_t bytes  = std::min(nvox(h) * sizeof(uint16_t), h->l2_window_max);
+            const void* base  = h->d_mat;
+            size_t      bytes = nvox(h) * sizeof(uint16_t);
+            if (h->l2_persist == 2) {   // the dose grid instead: its RED sectors are what DRAM sees written back 204 times over
+                for (const auto& sc : h->scorers)
+                    if (sc.kind != MQI_SCORER_DIJ && sc.d_dense) { base = sc.d_dense; bytes = nvox(h) * sizeof(double); break; }
+            }
+            bytes = std::min(bytes, h->l2_window_max);
             const size_t carve  = std::min(h->l2_persist_max, bytes);
             if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
-                attr.accessPolicyWindow.base_ptr  = h->d_mat;
+                attr.accessPolicyWindow.base_ptr  = const_cast<void*>(base);
                 attr.accessPolicyWindow.num_bytes = bytes;
                 attr.accessPolicyWindow.hitRatio  = (float) std::min(1.0, (double) carve / (double) bytes);
                 attr.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;

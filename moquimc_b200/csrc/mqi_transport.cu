@@ -1336,7 +1336,7 @@ dev_grid_entry_kernel(GridDev g, const float* __restrict__ pin, const float* __r
 __global__ void
 dev_hash_kernel(const uint32_t* k1, const uint32_t* k2, const unsigned long long* cap, size_t n, uint32_t* out) {
     for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
-        out[i] = hash_fun(k1[i], k2[i], cap[i]);
+        out[i] = hash_fun_magic(k1[i], k2[i], cap[i], remainder_magic(cap[i]));   // the form the transport kernel uses
 }
 
 __global__ void
