@@ -205,6 +205,8 @@ struct mqi_handle {
     double*                      d_stat_slice = nullptr;
     size_t                       stat_slice_n = 0;
     unsigned long long*          d_stat_range = nullptr;
+    double*                      d_stat3 = nullptr;   // scratch of the stopping criterion: sum of sigma/mu, count, max mean
+                                                       // (kept in the handle: cudaMalloc / cudaFree per evaluation cost milliseconds)
     mqi_run_stats           stats {};
 };
 
@@ -579,6 +581,7 @@ mqi_destroy(mqi_handle* h) {
     cudaFree(h->d_beamlets); cudaFree(h->d_cum); cudaFree(h->d_vertices); cudaFree(h->d_spot_ids);
     cudaFree(h->d_stat_slice);
     cudaFree(h->d_stat_range);
+    cudaFree(h->d_stat3);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1090,8 +1093,8 @@ mqi_stat_partial(mqi_handle* h, int scorer_sum, int scorer_sumsq, uint64_t n_his
     const double* sum = h->scorers[scorer_sum].d_dense;
     const double* sq  = h->scorers[scorer_sumsq].d_dense;
     if (!sum || !sq || n_histories < 2) return fail(MQI_ESTATE, "stat scorers are empty");
-    DevBuf<double> d;
-    CU(d.alloc(3));
+    if (!h->d_stat3) CU(cudaMalloc(&h->d_stat3, 3 * sizeof(double)));
+    struct { double* p; } d { h->d_stat3 };
     CU(cudaMemsetAsync(d.p, 0, 3 * sizeof(double), h->stream));
     if (max_mean < 0.0) {
         CU(launch_stat_max(sum, nvox(h), 1.0 / (double) n_histories, d.p + 2, h->stream));
@@ -1114,8 +1117,8 @@ mqi_stat_partial_buffers(mqi_handle* h, const void* d_sum, const void* d_sumsq, 
     if (n_histories < 2) return fail(MQI_ESTATE, "stat buffers need at least two histories");
     const double* sum = static_cast<const double*>(d_sum);
     const double* sq  = static_cast<const double*>(d_sumsq);
-    DevBuf<double> d;
-    CU(d.alloc(3));
+    if (!h->d_stat3) CU(cudaMalloc(&h->d_stat3, 3 * sizeof(double)));
+    struct { double* p; } d { h->d_stat3 };
     CU(cudaMemsetAsync(d.p, 0, 3 * sizeof(double), h->stream));
     if (max_mean < 0.0) {
         CU(launch_stat_max(sum, n_voxels, 1.0 / (double) n_histories, d.p + 2, h->stream));
@@ -1302,7 +1305,6 @@ stat_multi_impl(mqi_handle* const* handles, int n, int s_sum, int s_sq, uint64_t
         CU(cudaSetDevice(h->device));
         if (h->stat_slice_n < cap) {
             cudaFree(h->d_stat_slice);
-    cudaFree(h->d_stat_range);
             h->d_stat_slice = nullptr;
             h->stat_slice_n = 0;
             CU(cudaMalloc(&h->d_stat_slice, (2 * cap + 3) * sizeof(double)));

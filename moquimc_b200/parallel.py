@@ -31,6 +31,22 @@ def spot_shard(histories_per_spot, rank, world):
     return s0, s1 - s0, int(cum[s0]), int(cum[s1] - cum[s0])
 
 
+def spot_shard_blocks(histories_per_spot, rank, world, blocks_per_rank=4):
+    """Whole spots per rank in `blocks_per_rank` contiguous blocks dealt round-robin: [(first_history, n_histories), ...].
+    A plan lists its spots energy layer by energy layer and the cost of a spot grows with its range, so one contiguous
+    block per rank (spot_shard) leaves the rank with the highest layers working about twice as long as the one with the
+    lowest; the blocks of all ranks still tile the spot list exactly, and rows stay on one rank (no reduction)."""
+    h = np.asarray(histories_per_spot, dtype=np.uint64)
+    cum = np.concatenate(([0], np.cumsum(h, dtype=np.uint64)))
+    nb = world * blocks_per_rank if world > 1 else 1
+    out = []
+    for b in range(rank, nb, world):
+        s0, s1 = len(h) * b // nb, len(h) * (b + 1) // nb
+        if cum[s1] > cum[s0]:
+            out.append((int(cum[s0]), int(cum[s1] - cum[s0])))
+    return out
+
+
 def scenario_shard(n_scenarios, rank, world):
     """Robust-evaluation scenarios of this rank (round-robin, replicas only: no collective)."""
     return list(range(rank, n_scenarios, world))

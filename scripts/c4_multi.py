@@ -19,16 +19,24 @@ eng = []
 for d in range(n_gpus):
     e, s, total = K.c4_setup(d, cap, n_spots, per)
     eng.append((e, s))
-shards = [P.spot_shard([per] * n_spots, d, n_gpus) for d in range(n_gpus)]
-for (e, s), (s0, ns, h0, nh) in zip(eng, shards):      # warm-up
-    e.run(77, h0, min(nh, 100_000), per_spot=True)
+blocks = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+shards = [P.spot_shard_blocks([per] * n_spots, d, n_gpus, blocks) for d in range(n_gpus)]
+for (e, s), sh in zip(eng, shards):      # warm-up
+    e.run(77, sh[0][0], min(sh[0][1], 100_000), per_spot=True)
     e.clear_scorers()
 t0 = time.time()
-for (e, s), (s0, ns, h0, nh) in zip(eng, shards):
-    e.run_async(77, h0, nh, per_spot=True)
-stats = [e.run_stats() for e, s in eng]
+dev_ms = [0.0] * n_gpus
+full = [0] * n_gpus
+for k in range(max(len(sh) for sh in shards)):      # one block per device at a time, the devices run concurrently
+    live = [d for d in range(n_gpus) if k < len(shards[d])]
+    for d in live:
+        eng[d][0].run_async(77, shards[d][k][0], shards[d][k][1], per_spot=True)
+    for d in live:
+        st = eng[d][0].run_stats()
+        dev_ms[d] += st.kernel_ms
+        full[d] += int(st.dij_table_full)
 wall = time.time() - t0
-kms = max(st.kernel_ms for st in stats)
+kms = max(dev_ms)
 nnz = [e.get_sparse_count(s) for e, s in eng]
 # rows of the first 8 spots of device 0 against a single-device run of exactly those spots
 k1, k2, v = eng[0][0].get_sparse(eng[0][1])
@@ -41,5 +49,5 @@ b = {(int(x), int(y)): z for x, y, z in zip(b1, b2, bv)}
 same = a.keys() == b.keys() and bool(np.allclose([a[k] for k in sorted(a)], [b[k] for k in sorted(a)], rtol=1e-9))
 print(json.dumps({"config": "C4: 5000 spots x 10000 histories, spots sharded over %d GPU(s), %d slots per device" % (n_gpus, cap | 1),
                   "n_gpus": n_gpus, "kernel_ms_max": kms, "histories": n_spots * per, "histories_per_s": n_spots * per / (kms * 1e-3),
-                  "wall_s": wall, "nnz_per_device": nnz, "spots_per_device": [s[1] for s in shards],
-                  "table_full": [int(st.dij_table_full) for st in stats], "rows_equal_single_device": same}))
+                  "wall_s": wall, "nnz_per_device": nnz, "kernel_ms_per_device": dev_ms, "blocks_per_device": blocks,
+                  "table_full": full, "rows_equal_single_device": same}))

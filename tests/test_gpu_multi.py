@@ -45,10 +45,10 @@ def test_tps_env_on_all_devices_gives_the_single_device_dose(tmp_path):
     root = str(tmp_path)
     nd = n_devices()
     a, b = os.path.join(root, "o1"), os.path.join(root, "oN")
-    inp = S.make_case(root, n=N, spacing=SP, n_layers=6, ParticlesPerHistory=1000.0, OutputDir=a, Scorer="Dose LETd")
+    inp = S.make_case(root, n=N, spacing=SP, n_layers=6, ParticlesPerHistory=1000.0, OutputDir=a, Scorer="Dose,LETd")
     run_tps(inp)
     i2 = os.path.join(root, "multi.in")
-    S.write_input(i2, root, b, ParticlesPerHistory=1000.0, Scorer="Dose LETd", GPUID=",".join(str(i) for i in range(nd)))
+    S.write_input(i2, root, b, ParticlesPerHistory=1000.0, Scorer="Dose,LETd", GPUID=",".join(str(i) for i in range(nd)))
     out = run_tps(i2)
     assert "on %d GPU(s)" % nd in out
     for name in ("Dose", "LETd_numer", "LETd_denom"):

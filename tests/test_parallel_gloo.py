@@ -102,6 +102,14 @@ def test_shard_helpers():
     hps = [5, 0, 7, 3, 9]
     parts = [P.spot_shard(hps, r, 2) for r in range(2)]
     assert parts == [(0, 2, 0, 5), (2, 3, 5, 19)]
+    hps = [3, 1, 4, 1, 5, 9, 2, 6, 5, 3, 5, 8]
+    for w in (1, 2, 3, 8):
+        blocks = [P.spot_shard_blocks(hps, r, w, 2) for r in range(w)]
+        flat = sorted(b for bl in blocks for b in bl)
+        assert flat[0][0] == 0 and sum(n for _, n in flat) == sum(hps)           # the blocks tile the histories exactly
+        assert all(a + n == b for (a, n), (b, _) in zip(flat, flat[1:]))
+        cum = np.concatenate(([0], np.cumsum(hps)))
+        assert all(a in cum and a + n in cum for a, n in flat)                   # and cut between spots only
     sc = P.robust_scenarios()
     assert len(sc) == 21 and sc[0] == {"XShift": 0.0, "YShift": 0.0, "ZShift": 0.0, "DensityScaling": 1.0}
     assert sorted(sum((P.scenario_shard(21, r, 8) for r in range(8)), [])) == list(range(21))
