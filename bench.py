@@ -411,7 +411,7 @@ def strong_c3(rank, world, local, dev, stream, seed, criteria=1.0):
                         "statistical stopping at %g %% (StatThreshold 0.5), %d histories per pass" % (len(bl), criteria, total),
             "scaling": "strong", "n_gpus": world, "criteria_percent": criteria, "uncertainty_percent": current, "passes": passes,
             "histories": tracked, "time_to_criterion_s": total_s, "histories_per_s": tracked / total_s,
-            "transport_s": transport_s, "stat_s": stat_s, "final_reduce_s": reduce_s,
+            "transport_s": transport_s, "stat_s": stat_s, "stat_phases_s_rank0": loop.phase_seconds, "final_reduce_s": reduce_s,
             "collective_share": (stat_s + reduce_s) / total_s,
             "collective": "per pass: ncclReduceScatter of the scored range of sum d and sum d^2 (%d of %d values) + three scalar "
                           "all-reduces; once: ncclReduce of the dose grid" % (getattr(loop, "exchanged_values", 0), nvox) if world > 1

@@ -125,8 +125,17 @@ class StoppingLoop:
         self.group = group
         self.history = []
         self.stat_seconds = 0.0
+        self.phase_seconds = {"range": 0.0, "exchange": 0.0, "evaluate": 0.0}   # where stat_seconds goes
 
     CHUNK = 4096
+
+    @staticmethod
+    def _tick(t):
+        import time
+        import torch
+        if t.is_cuda:
+            torch.cuda.synchronize()
+        return time.perf_counter()
 
     def scored_range(self, total_sum, world):
         """[lo, lo + span) with span a multiple of `world`: the part of the grid some rank has scored into, found in
@@ -172,9 +181,11 @@ class StoppingLoop:
                 dist.all_reduce(n, op=dist.ReduceOp.SUM, group=self.group)
             tracked += int(n.item())
             lo, span = self.scored_range(total_sum, world)
+            t1 = self._tick(total_sum)
             per = span // world
             reduce_scatter_sum(s_sum[:per], total_sum[lo:lo + span], self.group)
             reduce_scatter_sum(s_sq[:per], total_sq[lo:lo + span], self.group)
+            t2 = self._tick(total_sum)
             mx = torch.tensor([self.evaluate(s_sum[:per], s_sq[:per], tracked, -1.0)[2]], dtype=torch.float64, device=total_sum.device)
             if multi:
                 dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
@@ -182,6 +193,10 @@ class StoppingLoop:
             part = torch.tensor([s, c], dtype=torch.float64, device=total_sum.device)
             if multi:
                 dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
+            t3 = self._tick(total_sum)
+            self.phase_seconds["range"] += t1 - t0
+            self.phase_seconds["exchange"] += t2 - t1
+            self.phase_seconds["evaluate"] += t3 - t2
             k += 1
             current = criterion_from_partials(float(part[0].item()), float(part[1].item()))
             self.history.append(current)
