@@ -368,21 +368,21 @@ def strong_c3(rank, world, local, dev, stream, seed, criteria=1.0):
     for kind, name, b in ((capi.SCORER_DOSE, "Dose", bufs[0]), (capi.SCORER_DOSE, "Dose_stat", bufs[1]), (capi.SCORER_DOSE_SQ, "DoseSquare_stat", bufs[2])):
         eng.bind_scorer_buffer(eng.add_scorer(kind, name), b.data_ptr())
     eng.set_beamlets(bl, hist)
-    first, count = P.history_shard(total, rank, world)
     kernel_ms = []
 
     def transport_pass(k):
-        st = eng.run(seed + k, first, count)
+        # interleaved sharding (chunks of 32 histories dealt round-robin over the ranks): the plan is sorted by energy
+        # layer, contiguous history ranges would leave the rank with the highest layers working longest
+        st = eng.run_sharded(seed + k, 0, total, world, rank)
         kernel_ms.append(st.kernel_ms)
-        return count
+        return st.histories
 
     def evaluate(s, q, n, mx):
         return eng.stat_partial_buffers(s.data_ptr(), q.data_ptr(), s.numel(), n, 0.5, mx)
     # warm-up, untimed: one short pass through the same loop (kernel module, torch's reduction kernels, the NCCL
     # channels of the reduce-scatter and of the final reduce), then the buffers are cleared
     def warm_pass(k):
-        eng.run(seed + 1000, first, min(count, 50_000))
-        return min(count, 50_000)
+        return eng.run_sharded(seed + 1000, 0, min(total, 100_000), world, rank).histories
     P.StoppingLoop(0.0, warm_pass, evaluate, max_passes=1).run(bufs[1], bufs[2])
     if world > 1:
         w = torch.zeros(world * 1024, dtype=torch.float64, device=dev)

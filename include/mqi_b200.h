@@ -174,6 +174,14 @@ MQI_API int mqi_run(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64
  * handle's stream; mqi_get_run_stats (or any download) waits for it.  Lets the caller overlap
  * transport with NCCL reductions / copies on other streams and time it with its own events. */
 MQI_API int mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t count, int per_spot);
+/* One shard of an interleaved partition of [first, first + count) over n_shards devices (new: the reference is
+ * single-GPU): the range is cut into chunks of 32 histories and chunk c is transported by shard c % n_shards, so every
+ * device gets the same mix of spots and energies -- contiguous sub-ranges of a plan sorted by energy layer leave the
+ * device with the highest layers working longest.  The shards of all devices together transport every history of the
+ * range exactly once, with the streams it would have drawn in a single launch; mqi_run_stats::histories counts this
+ * shard's.  Not for per-spot (Dij) runs sharded by spot: rows must stay on one device. */
+MQI_API int mqi_run_async_sharded(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t count, int per_spot,
+                          uint32_t n_shards, uint32_t shard);
 /* waits for the last mqi_run_async and returns its counters and device time */
 MQI_API int mqi_get_run_stats(mqi_handle* h, mqi_run_stats* out);
 /* options: "count_steps" (0/1: fill mqi_run_stats::steps; runs the general kernel, ~2 % slower),

@@ -79,6 +79,7 @@ def load():
         "mqi_set_vertices": [vp, vp, u64, vp],
         "mqi_run": [vp, u64, u64, u64, i32],
         "mqi_run_async": [vp, u64, u64, u64, i32],
+        "mqi_run_async_sharded": [vp, u64, u64, u64, i32, u32, u32],
         "mqi_set_stream": [vp, vp],
         "mqi_get_run_stats": [vp, C.POINTER(RunStats)],
         "mqi_set_option": [vp, C.c_char_p, C.c_int64],
@@ -304,6 +305,11 @@ class Engine:
         st = RunStats()
         self._check(self.L.mqi_get_run_stats(self.h, C.byref(st)))
         return st
+
+    def run_sharded(self, seed, first, count, n_shards, shard, per_spot=False):
+        """this device's interleaved share (chunks of 32 histories, chunk c to shard c % n_shards) of [first, first + count)"""
+        self._check(self.L.mqi_run_async_sharded(self.h, seed, first, count, 1 if per_spot else 0, n_shards, shard))
+        return self.run_stats()
 
     def run_async(self, seed, first, count, per_spot=False):
         self._check(self.L.mqi_run_async(self.h, seed, first, count, 1 if per_spot else 0))

@@ -373,6 +373,8 @@ fill_params(const mqi_handle* h, Params& p) {
         p.sc[i].cap_magic = remainder_magic(h->scorers[i].capacity);
         p.sc[i].roi      = h->scorers[i].d_roi;
     }
+    p.n_shards    = 1;
+    p.shard       = 0;
     p.quirks      = h->quirks;
     p.accum_mode  = h->accum;
     p.count_steps = h->count_steps;
@@ -867,8 +869,15 @@ collect_run(mqi_handle* h) {
 
 int
 mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t count, int per_spot) {
+    return mqi_run_async_sharded(h, seed, first_history, count, per_spot, 1, 0);
+}
+
+int
+mqi_run_async_sharded(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t count, int per_spot, uint32_t n_shards,
+                      uint32_t shard) {
     int rc = activate(h);
     if (rc) return rc;
+    if (n_shards == 0 || shard >= n_shards) return fail(MQI_EINVAL, "shard index out of range");
     if (!h->has_grid) return fail(MQI_ESTATE, "no grid set");
     if (h->scorers.empty()) return fail(MQI_ESTATE, "no scorer added");
     if (h->d_vertices) {
@@ -900,6 +909,8 @@ mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t cou
     }
     p.first    = first_history;
     p.count    = count;
+    p.n_shards = n_shards;
+    p.shard    = shard;
     p.per_spot = per_spot;
     if (h->d_vertices) {   // explicit vertices are addressed relative to the launch
         p.src.vertices = h->d_vertices + first_history;
@@ -913,7 +924,7 @@ mqi_run_async(mqi_handle* h, uint64_t seed, uint64_t first_history, uint64_t cou
     if (h->blocks_per_sm_override > 0) bps = std::min(bps, h->blocks_per_sm_override);
     // persistent grid: a whole number of CTAs per SM, never more lanes than histories
     const unsigned long long blk = (unsigned long long) transport_block(p.n_nodes > 1);
-    unsigned long long want = (count + blk - 1) / blk;
+    unsigned long long want = (count / n_shards + 32 + blk - 1) / blk;   // this shard's share of the range
     int                grid = (int) std::min<unsigned long long>((unsigned long long) h->sm_count * bps, want);
     {   // subsystem 3: the 16-bit material volume of the scored grid is read once per voxel step by every
         // lane; keep it resident in L2 (persisting access window on the launching stream) while the fp64

@@ -1167,7 +1167,8 @@ public:
         printf("total scorer %d current scorer %d\n", (int) scorers.size(), (int) scorers.size());
     }
 
-    // The history ranges of device r.  Per beam: one range, an equal share of the histories.  Per spot (Dij): whole
+    // The history ranges of device r.  Per beam: the whole range, of which the device transports its interleaved
+    // share.  Per spot (Dij): whole
     // SPOTS -- the rows of the matrix stay on one device, so the shards need no reduction -- dealt in kSpotBlocks
     // contiguous blocks per device, round-robin: a plan lists its spots energy layer by energy layer and the cost of a
     // spot grows with its range, so one contiguous block per device leaves the device with the highest layers working
@@ -1186,7 +1187,9 @@ public:
                 if (cum[s1] > cum[s0]) out.emplace_back(cum[s0], cum[s1]);
             }
         } else {
-            out.emplace_back(total_histories * r / g, total_histories * (r + 1) / g);
+            // per beam: every device takes its interleaved share of the WHOLE range (mqi_run_async_sharded: chunks of
+            // 32 histories dealt round-robin), so each gets the same mix of energy layers
+            out.emplace_back(0, total_histories);
         }
         return out;
     }
@@ -1213,7 +1216,8 @@ public:
                 if (at[r] >= todo[r].size()) continue;
                 auto&          rg = todo[r][at[r]];
                 const uint64_t n  = std::min<uint64_t>(batch, rg.second - rg.first);
-                check(mqi_run_async(handles[r], seed, rg.first, n, sim_type == PER_SPOT ? 1 : 0), "mqi_run_async");
+                if (sim_type == PER_SPOT) check(mqi_run_async(handles[r], seed, rg.first, n, 1), "mqi_run_async");
+                else check(mqi_run_async_sharded(handles[r], seed, rg.first, n, 0, (uint32_t) g, (uint32_t) r), "mqi_run_async_sharded");
                 rg.first += n;
                 if (rg.first >= rg.second) ++at[r];
                 launched[r] = 1;

@@ -734,6 +734,8 @@ refill_queue(const Params& P, uint32_t* q, int q_n) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(P.counters + C_NEXT, 32ull);
     base = __shfl_sync(0xffffffffu, base, 0);
+    // this launch's k-th fetch is chunk k * n_shards + shard of the range (n_shards = 1: chunk k)
+    base = (base * P.n_shards) + 32ull * P.shard;
     const unsigned long long i    = base + lane;
     const bool               have = i < P.count;
     bool     alive = false;
@@ -779,7 +781,7 @@ refill_queue(const Params& P, uint32_t* q, int q_n) {
         e[Q_NODE * kQueueCap] = (uint32_t) T.node;
     }
     __syncwarp();
-    const int exhausted = base + 32ull >= P.count ? 1 : 0;
+    const int exhausted = base + 32ull * P.n_shards >= P.count ? 1 : 0;   // the shard's next chunk lies beyond the range
     return (q_n + __popc(m)) | (exhausted << 16);
 }
 

@@ -98,8 +98,7 @@ def test_stat_multi_equals_the_criterion_on_the_summed_grids():
     for d in range(nd):
         e, ids = small_engine(d)
         e.set_beamlets(bl, [n])
-        a, b = n * d // nd, n * (d + 1) // nd
-        e.run(5, a, b - a)
+        e.run_sharded(5, 0, n, nd, d)       # interleaved shards, as tps_env runs a beam over a GPUID list
         engines.append(e)
     s, c, mx = capi.stat_multi(engines, ids[1], ids[2], n, 0.5)
     # reference: everything on one device
