@@ -359,7 +359,7 @@ def strong_c3(rank, world, local, dev, stream, seed, criteria=1.0):
     hist = [s["histories"] for s in spots]
     total = int(sum(hist))
     nvox = n3[0] * n3[1] * n3[2]
-    n_pad = world * P.slice_len(nvox, world)
+    n_pad = P.StoppingLoop.padded_len(nvox)
     eng = capi.Engine(local, physics=capi.PHYSICS_RELEASE)
     eng.set_stream(stream.cuda_stream)
     d_hu = torch.from_numpy(hu.reshape(-1)).to(dev)
@@ -383,7 +383,7 @@ def strong_c3(rank, world, local, dev, stream, seed, criteria=1.0):
     # channels of the reduce-scatter and of the final reduce), then the buffers are cleared
     def warm_pass(k):
         return eng.run_sharded(seed + 1000, 0, min(total, 100_000), world, rank).histories
-    P.StoppingLoop(0.0, warm_pass, evaluate, max_passes=1).run(bufs[1], bufs[2])
+    P.StoppingLoop(0.0, warm_pass, evaluate, threshold=0.5, max_passes=1).run(bufs[1], bufs[2])
     if world > 1:
         w = torch.zeros(world * 1024, dtype=torch.float64, device=dev)
         dist.reduce(w, dst=0)
@@ -393,7 +393,7 @@ def strong_c3(rank, world, local, dev, stream, seed, criteria=1.0):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    loop = P.StoppingLoop(criteria, transport_pass, evaluate, max_passes=400)
+    loop = P.StoppingLoop(criteria, transport_pass, evaluate, threshold=0.5, max_passes=400)
     tracked, current, passes = loop.run(bufs[1], bufs[2])
     t1 = time.perf_counter()
     if world > 1:
@@ -412,10 +412,13 @@ def strong_c3(rank, world, local, dev, stream, seed, criteria=1.0):
             "scaling": "strong", "n_gpus": world, "criteria_percent": criteria, "uncertainty_percent": current, "passes": passes,
             "histories": tracked, "time_to_criterion_s": total_s, "histories_per_s": tracked / total_s,
             "transport_s": transport_s, "stat_s": stat_s, "stat_phases_s_rank0": loop.phase_seconds, "final_reduce_s": reduce_s,
-            "collective_share": (stat_s + reduce_s) / total_s,
-            "collective": "per pass: ncclReduceScatter of the scored range of sum d and sum d^2 (%d of %d values) + three scalar "
-                          "all-reduces; once: ncclReduce of the dose grid" % (getattr(loop, "exchanged_values", 0), nvox) if world > 1
-                          else "none (1 GPU): the criterion is evaluated on the device",
+            "overhead_share": (total_s - transport_s) / total_s,   # everything but the slowest rank's kernels: selection, exchange,
+                                                                   # evaluation, the final reduce, launch and host latencies
+            "collective": ("per pass: max-all-reduce of one double and of %d chunk flags, ncclReduceScatter of the packed chunks of sum d "
+                           "and sum d^2 that can hold a voxel above the dose threshold (%d of %d values each), max- and sum-all-reduce "
+                           "of three doubles; once: ncclReduce of the dose grid" % (n_pad // P.StoppingLoop.CHUNK, loop.exchanged_values, nvox))
+                          if world > 1 else "none (1 GPU): the criterion is evaluated on the device, on the packed chunks (%d of %d values)"
+                          % (loop.exchanged_values, nvox),
             "timer": "host wall clock between device synchronisations and barriers, max over ranks", "dose_checksum": checksum}
 
 

@@ -237,10 +237,11 @@ MQI_API int mqi_scale_scorer(mqi_handle* h, int scorer, double factor);
 MQI_API int mqi_reduce_dense(mqi_handle* const* handles, int n, int scorer, int root);
 MQI_API int mqi_allreduce_dense(mqi_handle* const* handles, int n, int scorer);
 /* The stopping criterion of a run sharded over n devices (calculate_stat, mqi_tps_env.hpp:1339-1426, on the sums
- * of all devices) without gathering grids on one of them: the Dose / Dose^2 stat grids stay where they are and
- * keep accumulating; one ncclReduceScatter per grid gives every device the summed values of 1/n of the voxels,
- * each device evaluates its part, the host adds n x 3 doubles.  out as in mqi_stat_partial.  n == 1 is
- * mqi_stat_partial. */
+ * of all devices) without gathering grids on one of them: the Dose / Dose^2 stat grids stay where they are and keep
+ * accumulating.  Only the 4 096-voxel chunks in which some device holds a value that could exceed the criterion's
+ * dose threshold after summation are packed and exchanged, one ncclReduceScatter per grid gives every device the summed
+ * values of 1/n of them, each device evaluates its part, the host adds n x 3 doubles.  Result and selected voxels are
+ * those of an evaluation on whole summed grids.  out as in mqi_stat_partial.  n == 1 is mqi_stat_partial. */
 MQI_API int mqi_stat_multi(mqi_handle* const* handles, int n, int scorer_sum, int scorer_sumsq, uint64_t n_histories,
                    double threshold_fraction, double out[3]);
 

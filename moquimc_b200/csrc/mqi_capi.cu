@@ -204,7 +204,9 @@ struct mqi_handle {
     // this device's slice of the summed stat grids (mqi_stat_multi): sum | sum of squares, stat_slice_n doubles each
     double*                      d_stat_slice = nullptr;
     size_t                       stat_slice_n = 0;
-    unsigned long long*          d_stat_range = nullptr;
+    unsigned char*               d_stat_flags = nullptr;   // chunk flags and list of kept chunks (mqi_stat_multi)
+    unsigned int*                d_stat_list  = nullptr;
+    size_t                       stat_flags_n = 0;
     double*                      d_stat3 = nullptr;   // scratch of the stopping criterion: sum of sigma/mu, count, max mean
                                                        // (kept in the handle: cudaMalloc / cudaFree per evaluation cost milliseconds)
     mqi_run_stats           stats {};
@@ -582,7 +584,8 @@ mqi_destroy(mqi_handle* h) {
     cudaFree(h->d_tab_a0); cudaFree(h->d_tab_a1); cudaFree(h->d_tab_bs); cudaFree(h->d_tab_n0); cudaFree(h->d_tab_n1); cudaFree(h->d_correction); cudaFree(h->d_counters);
     cudaFree(h->d_beamlets); cudaFree(h->d_cum); cudaFree(h->d_vertices); cudaFree(h->d_spot_ids);
     cudaFree(h->d_stat_slice);
-    cudaFree(h->d_stat_range);
+    cudaFree(h->d_stat_flags);
+    cudaFree(h->d_stat_list);
     cudaFree(h->d_stat3);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1270,12 +1273,15 @@ reduce_impl(mqi_handle* const* handles, int n, int scorer, int root, bool all) {
     return MQI_OK;
 }
 
-// The stopping criterion over several devices without moving whole grids to one of them: every device keeps its
-// own running sums; one ncclReduceScatter per stat grid leaves each device with the summed values of 1/n of the
-// voxels (each link carries 1/n of the grid, all links at once), on which it evaluates its part of
-// calculate_stat; the host combines n x 3 doubles.  Only the range of the grid that some device has scored into is
-// exchanged (the stat grids are zero outside the beam).  The few voxels left over when n does not divide the grid go to
-// device 0 with one small ncclReduce.
+// The stopping criterion over several devices without moving grids to one of them.  Every device keeps its own running
+// sums.  calculate_stat averages sigma/mu over the voxels whose mean dose exceeds threshold x the largest mean dose, so
+// only voxels that CAN exceed it are exchanged: with M_lb = the largest local sum of any device (a lower bound of the
+// largest summed value), a voxel whose local sum is at most threshold * M_lb / n on every device sums to at most
+// threshold * M_lb and cannot qualify.  The grids are cut into chunks of 4 096 voxels; a chunk is kept if any device holds
+// a larger value in it; the kept chunks of both grids are packed, one ncclReduceScatter per grid leaves each device with
+// the summed values of 1/n of them (every link carries 1/n of the packed values, all links at once), each device
+// evaluates its slice, the host combines n x 3 doubles.  The selected voxels and the result are exactly those of an
+// evaluation on whole summed grids (tests/test_gpu_multi.py); at config C3 a few per cent of the grid travel.
 int
 stat_multi_impl(mqi_handle* const* handles, int n, int s_sum, int s_sq, uint64_t n_histories, double threshold_fraction,
                 double out[3]) {
@@ -1286,77 +1292,104 @@ stat_multi_impl(mqi_handle* const* handles, int n, int s_sum, int s_sq, uint64_t
     int       rc     = prepare_group(handles, n, ids, 2, &count);
     if (rc) return rc;
     if (n == 1) return mqi_stat_partial(handles[0], s_sum, s_sq, n_histories, threshold_fraction, -1.0, out);
-    // the stat grids are zero outside the beam: find the range of chunks any device has touched and exchange only that
-    const size_t chunk = 4096;
+    const size_t chunk = 4096, nchunks = (count + chunk - 1) / chunk;
+    // 1. the largest local sum of any device
+    std::vector<double> local_max(n, 0.0);
     for (int i = 0; i < n; ++i) {
         mqi_handle* h = handles[i];
         CU(cudaSetDevice(h->device));
-        if (!h->d_stat_range) CU(cudaMalloc(&h->d_stat_range, 2 * sizeof(unsigned long long)));
-        const unsigned long long init[2] = { ~0ull, 0ull };
-        CU(cudaMemcpyAsync(h->d_stat_range, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
-        CU(launch_nonzero_range(h->scorers[s_sum].d_dense, count, chunk, h->d_stat_range, h->stream));
+        if (!h->d_stat3) CU(cudaMalloc(&h->d_stat3, 3 * sizeof(double)));
+        CU(cudaMemsetAsync(h->d_stat3, 0, 3 * sizeof(double), h->stream));
+        CU(launch_stat_max(h->scorers[s_sum].d_dense, count, 1.0, h->d_stat3 + 2, h->stream));
+        CU(cudaMemcpyAsync(&local_max[i], h->d_stat3 + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }
-    size_t lo = count, hi = 0;
+    double m_lb = 0.0;
+    for (int i = 0; i < n; ++i) {
+        CU(cudaSetDevice(handles[i]->device));
+        CU(cudaStreamSynchronize(handles[i]->stream));
+        m_lb = std::max(m_lb, local_max[i]);
+    }
+    if (!(m_lb > 0.0)) return fail(MQI_ESTATE, "stat scorers are empty");
+    // 2. chunks in which some device holds a value above threshold * M_lb / n
+    const double bound = threshold_fraction * m_lb / (double) n;
+    std::vector<std::vector<unsigned char>> flags(n, std::vector<unsigned char>(nchunks));
     for (int i = 0; i < n; ++i) {
         mqi_handle* h = handles[i];
         CU(cudaSetDevice(h->device));
-        unsigned long long r[2];
-        CU(cudaMemcpyAsync(r, h->d_stat_range, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        if (r[1] > r[0]) {
-            lo = std::min<size_t>(lo, (size_t) r[0] * chunk);
-            hi = std::max<size_t>(hi, std::min<size_t>(count, (size_t) r[1] * chunk));
+        if (h->stat_flags_n < nchunks) {
+            cudaFree(h->d_stat_flags);
+            cudaFree(h->d_stat_list);
+            h->d_stat_flags = nullptr;
+            h->d_stat_list  = nullptr;
+            h->stat_flags_n = 0;
+            CU(cudaMalloc(&h->d_stat_flags, nchunks));
+            CU(cudaMalloc(&h->d_stat_list, nchunks * sizeof(unsigned int)));
+            h->stat_flags_n = nchunks;
         }
+        CU(launch_chunk_above(h->scorers[s_sum].d_dense, count, chunk, bound, h->d_stat_flags, h->stream));
+        CU(cudaMemcpyAsync(flags[i].data(), h->d_stat_flags, nchunks, cudaMemcpyDeviceToHost, h->stream));
     }
-    if (hi <= lo) return fail(MQI_ESTATE, "stat scorers are empty");
-    const size_t span = hi - lo;
-    const size_t per = span / (size_t) n, tail = span - per * (size_t) n, cap = per + tail;
+    std::vector<unsigned int> list;
+    for (int i = 0; i < n; ++i) {
+        CU(cudaSetDevice(handles[i]->device));
+        CU(cudaStreamSynchronize(handles[i]->stream));
+    }
+    for (size_t c = 0; c < nchunks; ++c) {
+        unsigned char any = 0;
+        for (int i = 0; i < n; ++i) any |= flags[i][c];
+        if (any) list.push_back((unsigned int) c);
+    }
+    // 3. pack the kept chunks of both grids (padded with zeros to a multiple of n) and reduce-scatter them
+    const size_t packed = ((list.size() * chunk + (size_t) n - 1) / (size_t) n) * (size_t) n, per = packed / (size_t) n;
+    if (per == 0) return fail(MQI_ESTATE, "stat scorers are empty");
     for (int i = 0; i < n; ++i) {
         mqi_handle* h = handles[i];
         CU(cudaSetDevice(h->device));
-        if (h->stat_slice_n < cap) {
+        if (h->stat_slice_n < packed) {   // [packed sum | packed sq | slice sum | slice sq]
             cudaFree(h->d_stat_slice);
             h->d_stat_slice = nullptr;
             h->stat_slice_n = 0;
-            CU(cudaMalloc(&h->d_stat_slice, (2 * cap + 3) * sizeof(double)));
+            const size_t cap = packed + packed / 4 + chunk * (size_t) n;   // head room: the kept set grows slowly from pass to pass
+            CU(cudaMalloc(&h->d_stat_slice, (2 * cap + 2 * (cap / (size_t) n + 1)) * sizeof(double)));
             h->stat_slice_n = cap;
+        }
+        double* pa = h->d_stat_slice;
+        double* pb = pa + h->stat_slice_n;
+        CU(cudaMemcpyAsync(h->d_stat_list, list.data(), list.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, h->stream));
+        CU(launch_pack_chunks(h->scorers[s_sum].d_dense, h->scorers[s_sq].d_dense, count, chunk, h->d_stat_list, list.size(), pa, pb, h->stream));
+        if (packed > list.size() * chunk) {
+            CU(cudaMemsetAsync(pa + list.size() * chunk, 0, (packed - list.size() * chunk) * sizeof(double), h->stream));
+            CU(cudaMemsetAsync(pb + list.size() * chunk, 0, (packed - list.size() * chunk) * sizeof(double), h->stream));
         }
     }
     NC(g_nccl.GroupStart());
     for (int i = 0; i < n; ++i) {
         mqi_handle* h = handles[i];
         CU(cudaSetDevice(h->device));
-        const double* sum = h->scorers[s_sum].d_dense + lo;
-        const double* sq  = h->scorers[s_sq].d_dense + lo;
-        double*       a   = h->d_stat_slice;
-        double*       b   = h->d_stat_slice + h->stat_slice_n;
-        if (per) {
-            NC(g_nccl.ReduceScatter(sum, a, per, kNcclFloat64, kNcclSum, g_comms[i], h->stream));
-            NC(g_nccl.ReduceScatter(sq, b, per, kNcclFloat64, kNcclSum, g_comms[i], h->stream));
-        }
-        if (tail) {
-            NC(g_nccl.Reduce(sum + per * n, a + per, tail, kNcclFloat64, kNcclSum, 0, g_comms[i], h->stream));
-            NC(g_nccl.Reduce(sq + per * n, b + per, tail, kNcclFloat64, kNcclSum, 0, g_comms[i], h->stream));
-        }
+        double* pa = h->d_stat_slice;
+        double* pb = pa + h->stat_slice_n;
+        double* sa = pb + h->stat_slice_n;
+        double* sb = sa + (h->stat_slice_n / (size_t) n + 1);
+        NC(g_nccl.ReduceScatter(pa, sa, per, kNcclFloat64, kNcclSum, g_comms[i], h->stream));
+        NC(g_nccl.ReduceScatter(pb, sb, per, kNcclFloat64, kNcclSum, g_comms[i], h->stream));
     }
     NC(g_nccl.GroupEnd());
-    // pass 1: the largest mean dose; pass 2: sum of sigma / mu and the number of voxels above the threshold
+    // 4. pass 1: the largest mean dose; pass 2: sum of sigma / mu and the number of voxels above the threshold
     std::vector<double> host(3 * (size_t) n, 0.0);
     double              max_mean = 0.0;
     for (int pass = 0; pass < 2; ++pass) {
         for (int i = 0; i < n; ++i) {
             mqi_handle* h = handles[i];
             CU(cudaSetDevice(h->device));
-            const size_t cnt = per + (i == 0 ? tail : 0);
-            double*      a   = h->d_stat_slice;
-            double*      b   = a + h->stat_slice_n;
-            double*      d3  = b + h->stat_slice_n;
+            double* sa = h->d_stat_slice + 2 * h->stat_slice_n;
+            double* sb = sa + (h->stat_slice_n / (size_t) n + 1);
+            double* d3 = h->d_stat3;
             if (pass == 0) {
                 CU(cudaMemsetAsync(d3, 0, 3 * sizeof(double), h->stream));
-                if (cnt) CU(launch_stat_max(a, cnt, 1.0 / (double) n_histories, d3 + 2, h->stream));
+                CU(launch_stat_max(sa, per, 1.0 / (double) n_histories, d3 + 2, h->stream));
                 CU(cudaMemcpyAsync(&host[3 * i + 2], d3 + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             } else {
-                if (cnt) CU(launch_stat_partial(a, b, cnt, (double) n_histories, threshold_fraction * max_mean, d3, h->stream));
+                CU(launch_stat_partial(sa, sb, per, (double) n_histories, threshold_fraction * max_mean, d3, h->stream));
                 CU(cudaMemcpyAsync(&host[3 * i], d3, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             }
         }

@@ -100,8 +100,10 @@ cudaError_t launch_dij_chunk_write(const void* table, size_t capacity, size_t ch
 cudaError_t launch_scale(double* p, size_t n, double f, cudaStream_t st);
 // stopping criterion: per-voxel mean / sigma from sum and sum of squares, partial reductions
 cudaError_t launch_stat_max(const double* sum, size_t n, double inv_n, double* d_out_max, cudaStream_t st);
-// first / one-past-last chunk of `chunk` elements holding a non-zero value -> d_out2[0] (min), d_out2[1] (max)
-cudaError_t launch_nonzero_range(const double* a, size_t n, size_t chunk, unsigned long long* d_out2, cudaStream_t st);
+// stopping criterion over several devices: flag[c] = any value of chunk c above bound; gather of listed chunks
+cudaError_t launch_chunk_above(const double* a, size_t n, size_t chunk, double bound, unsigned char* d_flag, cudaStream_t st);
+cudaError_t launch_pack_chunks(const double* a, const double* b, size_t n, size_t chunk, const unsigned int* d_list, size_t n_list,
+                               double* pa, double* pb, cudaStream_t st);
 cudaError_t launch_stat_partial(const double* sum, const double* sumsq, size_t n, double n_hist, double cut,
                                 double* d_out2, cudaStream_t st);
 }   // namespace mqib

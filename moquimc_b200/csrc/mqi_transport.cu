@@ -1479,19 +1479,30 @@ stat_partial_kernel(const double* __restrict__ sum, const double* __restrict__ s
     }
 }
 
-// first and one-past-last chunk (of `chunk` elements) of a grid that holds a non-zero value: out[0] = min, out[1] = max
-// (initialised by the caller to ~0 and 0).  The stat grids are zero outside the beam, so a multi-GPU evaluation of the
-// stopping criterion only has to exchange this range.
+// chunk flags of the stopping criterion over several devices: flag[c] = 1 if any value of chunk c exceeds `bound`
+// (one block per chunk, grid-stride over the chunks)
 __global__ void
-nonzero_range_kernel(const double* __restrict__ a, size_t n, size_t chunk, unsigned long long* out) {
+chunk_above_kernel(const double* __restrict__ a, size_t n, size_t chunk, double bound, unsigned char* __restrict__ flag) {
     const size_t nchunks = (n + chunk - 1) / chunk;
     for (size_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const size_t b0 = c * chunk, b1 = min(n, b0 + chunk);
         bool         any = false;
-        for (size_t i = b0 + threadIdx.x; i < b1 && !any; i += blockDim.x) any = a[i] != 0.0;
-        if (__syncthreads_or(any) && threadIdx.x == 0) {
-            atomicMin(out, (unsigned long long) c);
-            atomicMax(out + 1, (unsigned long long) c + 1ull);
+        for (size_t i = b0 + threadIdx.x; i < b1 && !any; i += blockDim.x) any = a[i] > bound;
+        const int r = __syncthreads_or(any);
+        if (threadIdx.x == 0) flag[c] = r ? 1 : 0;
+    }
+}
+
+// gather the listed chunks of two grids into packed buffers (zeros behind the end of the grid)
+__global__ void
+pack_chunks_kernel(const double* __restrict__ a, const double* __restrict__ b, size_t n, size_t chunk,
+                   const unsigned int* __restrict__ list, size_t n_list, double* __restrict__ pa, double* __restrict__ pb) {
+    for (size_t k = blockIdx.x; k < n_list; k += gridDim.x) {
+        const size_t src = (size_t) list[k] * chunk, dst = k * chunk;
+        for (size_t i = threadIdx.x; i < chunk; i += blockDim.x) {
+            const bool in = src + i < n;
+            pa[dst + i] = in ? a[src + i] : 0.0;
+            pb[dst + i] = in ? b[src + i] : 0.0;
         }
     }
 }
@@ -1647,9 +1658,16 @@ launch_stat_partial(const double* sum, const double* sumsq, size_t n, double n_h
     return cudaGetLastError();
 }
 cudaError_t
-launch_nonzero_range(const double* a, size_t n, size_t chunk, unsigned long long* d_out2, cudaStream_t st) {
+launch_chunk_above(const double* a, size_t n, size_t chunk, double bound, unsigned char* d_flag, cudaStream_t st) {
     const size_t nchunks = (n + chunk - 1) / chunk;
-    nonzero_range_kernel<<<(int) std::min<size_t>(nchunks, 148 * 8), 256, 0, st>>>(a, n, chunk, d_out2);
+    chunk_above_kernel<<<(int) std::min<size_t>(nchunks, 148 * 8), 256, 0, st>>>(a, n, chunk, bound, d_flag);
+    return cudaGetLastError();
+}
+cudaError_t
+launch_pack_chunks(const double* a, const double* b, size_t n, size_t chunk, const unsigned int* d_list, size_t n_list, double* pa,
+                   double* pb, cudaStream_t st) {
+    if (n_list == 0) return cudaSuccess;
+    pack_chunks_kernel<<<(int) std::min<size_t>(n_list, 148 * 8), 256, 0, st>>>(a, b, n, chunk, d_list, n_list, pa, pb);
     return cudaGetLastError();
 }
 cudaError_t

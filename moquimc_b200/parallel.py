@@ -8,9 +8,10 @@ without a data-path collective:
     summed with ONE reduce per beam;
   * Dij: contiguous blocks of SPOTS per rank -- rows of the CSR are disjoint, no reduction;
   * robust scenarios: independent jobs, round-robin;
-  * statistical stopping: every rank keeps the running sum / sum-of-squares grids of its own histories; per pass the
-    two grids are reduce-scattered, every rank evaluates calculate_stat (mqi_tps_env.hpp:1339-1426) on its slice of
-    the summed grids, three doubles are all-reduced.  The dose itself is reduced once, after the last pass.
+  * statistical stopping: every rank keeps the running sum / sum-of-squares grids of its own histories; per pass only the
+    chunks of the grids that can hold a voxel above the criterion's dose threshold are packed and reduce-scattered,
+    every rank evaluates calculate_stat (mqi_tps_env.hpp:1339-1426) on its slice, three doubles are all-reduced
+    (StoppingLoop).  The dose itself is reduced once, after the last pass.
 
 Nothing here computes physics; the transport itself is the CUDA library (capi.Engine).
 """
@@ -106,28 +107,44 @@ class StoppingLoop:
     """run_by_beam_stat (mqi_tps_env.hpp:1242-1336) across ranks, without moving whole grids per pass.
 
     Every rank keeps its OWN running sums (sum d, sum d^2 of the histories it transported: the scorers simply keep
-    accumulating).  After a pass the two grids are reduce-scattered, each rank evaluates calculate_stat
-    (mqi_tps_env.hpp:1339-1426) on its slice of the summed grids, and three numbers are all-reduced: the largest mean
-    dose (max), then the sum of sigma/mu and the number of voxels above the threshold (sum).
+    accumulating).  calculate_stat (mqi_tps_env.hpp:1339-1426) averages sigma/mu over the voxels whose mean dose exceeds
+    threshold x the largest mean dose, so after a pass only the voxels that CAN exceed it are exchanged:
 
-    transport_pass(k) must ADD this rank's share of pass k into total_sum / total_sq and return the number of
-    histories it transported.  evaluate(sum_slice, sq_slice, n_histories, max_mean) returns (sum of sigma/mu over the
-    selected voxels, number of selected voxels, largest mean dose of the slice); with max_mean < 0 only the third
-    value is used.  On a GPU box evaluate is capi.Engine.stat_partial_buffers, the fused CUDA kernel.
-    total_sum / total_sq hold world * slice_len(nvox, world) elements (zero padding behind the grid).  Only the
-    range of the grids that some rank has scored into is exchanged (scored_range)."""
+      * M_lb = max over ranks of the rank's largest local sum -- a lower bound of the largest summed value;
+      * a voxel whose local sum is at most threshold * M_lb / world on EVERY rank sums to at most threshold * M_lb and
+        cannot qualify; the grids are cut into chunks of CHUNK voxels and a chunk is kept if any rank holds a larger
+        value in it (one max-all-reduce of the chunk flags, 12 800 flags for a 512 x 512 x 200 grid);
+      * the kept chunks of sum d and sum d^2 are packed, reduce-scattered (every link carries 1 / world of the packed
+        values, all links at once) and every rank evaluates its slice: the largest mean dose (max-all-reduce of one
+        double), then sum of sigma/mu and the voxel count (sum-all-reduce of two doubles).
 
-    def __init__(self, criteria_percent, transport_pass, evaluate, max_passes=1000, group=None):
+    The selected voxels and the criterion are exactly those of an evaluation on whole summed grids; at config C3 the
+    packed exchange is a few per cent of the grid.  The dose itself is reduced once, after the last pass.
+
+    transport_pass(k) must ADD this rank's share of pass k into total_sum / total_sq and return the number of histories
+    it transported.  evaluate(sum_slice, sq_slice, n_histories, max_mean) returns (sum of sigma/mu over the selected
+    voxels, number of selected voxels, largest mean dose of the slice); with max_mean < 0 only the third value is
+    used.  On a GPU box evaluate is capi.Engine.stat_partial_buffers, the fused CUDA kernel.  total_sum / total_sq hold
+    padded_len(nvox) elements (zero padding behind the grid)."""
+
+    CHUNK = 4096
+
+    def __init__(self, criteria_percent, transport_pass, evaluate, threshold=0.5, max_passes=1000, group=None):
         self.criteria = criteria_percent
         self.transport_pass = transport_pass
         self.evaluate = evaluate
+        self.threshold = threshold
         self.max_passes = max_passes
         self.group = group
         self.history = []
         self.stat_seconds = 0.0
-        self.phase_seconds = {"range": 0.0, "exchange": 0.0, "evaluate": 0.0}   # where stat_seconds goes
+        self.phase_seconds = {"wait_and_select": 0.0, "exchange": 0.0, "evaluate": 0.0}   # where stat_seconds goes
+        self.exchanged_values = 0
 
-    CHUNK = 4096
+    @classmethod
+    def padded_len(cls, n):
+        """length of the stat buffers of a grid of n voxels: a whole number of chunks"""
+        return (n + cls.CHUNK - 1) // cls.CHUNK * cls.CHUNK
 
     @staticmethod
     def _tick(t):
@@ -137,29 +154,19 @@ class StoppingLoop:
             torch.cuda.synchronize()
         return time.perf_counter()
 
-    def scored_range(self, total_sum, world):
-        """[lo, lo + span) with span a multiple of `world`: the part of the grid some rank has scored into, found in
-        chunks of CHUNK values (the stat grids are zero outside the beam, so only this range is exchanged)."""
+    def kept_chunks(self, total_sum, world):
+        """indices of the chunks that can hold a voxel above the threshold (the same list on every rank)"""
         import torch
         import torch.distributed as dist
-        n = total_sum.numel()
-        m = n // self.CHUNK
-        lo, hi = n, 0
-        if m:
-            nz = torch.nonzero(total_sum[:m * self.CHUNK].view(m, self.CHUNK).amax(dim=1) > 0)
-            if nz.numel():
-                lo, hi = int(nz[0].item()) * self.CHUNK, (int(nz[-1].item()) + 1) * self.CHUNK
-        if m * self.CHUNK < n and bool((total_sum[m * self.CHUNK:].amax() > 0).item()):
-            lo, hi = min(lo, m * self.CHUNK), n
+        view = total_sum.view(-1, self.CHUNK)
+        cmax = view.amax(dim=1)
+        m_lb = cmax.max().reshape(1).clone()
         if world > 1:
-            r = torch.tensor([-lo, hi], dtype=torch.int64, device=total_sum.device)
-            dist.all_reduce(r, op=dist.ReduceOp.MAX, group=self.group)
-            lo, hi = -int(r[0].item()), int(r[1].item())
-        if hi <= lo:
-            lo, hi = 0, n
-        span = ((hi - lo + world - 1) // world) * world
-        lo = max(0, min(lo, n - span))
-        return lo, min(span, n - lo)
+            dist.all_reduce(m_lb, op=dist.ReduceOp.MAX, group=self.group)
+        keep = (cmax > (self.threshold / world) * m_lb).to(torch.int32)
+        if world > 1:
+            dist.all_reduce(keep, op=dist.ReduceOp.MAX, group=self.group)
+        return torch.nonzero(keep).reshape(-1), view
 
     def run(self, total_sum, total_sq):
         import time
@@ -167,41 +174,38 @@ class StoppingLoop:
         import torch.distributed as dist
         multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
         world = dist.get_world_size(self.group) if multi else 1
-        n_slice = total_sum.numel() // world
-        assert n_slice * world == total_sum.numel() == total_sq.numel()
-        s_sum = torch.zeros(n_slice, dtype=total_sum.dtype, device=total_sum.device)
-        s_sq = torch.zeros_like(s_sum)
+        assert total_sum.numel() == total_sq.numel() and total_sum.numel() % self.CHUNK == 0 and self.CHUNK % world == 0
         tracked, current, k = 0, 100.0, 0
         while current > self.criteria and k < self.max_passes:
             n = torch.tensor([self.transport_pass(k)], dtype=torch.int64, device=total_sum.device)
-            if total_sum.is_cuda:
-                torch.cuda.synchronize()
-            t0 = time.perf_counter()
+            t0 = self._tick(total_sum)
             if multi:
-                dist.all_reduce(n, op=dist.ReduceOp.SUM, group=self.group)
+                dist.all_reduce(n, op=dist.ReduceOp.SUM, group=self.group)     # also where a rank waits for the slowest
             tracked += int(n.item())
-            lo, span = self.scored_range(total_sum, world)
+            idx, view = self.kept_chunks(total_sum, world)
             t1 = self._tick(total_sum)
-            per = span // world
-            reduce_scatter_sum(s_sum[:per], total_sum[lo:lo + span], self.group)
-            reduce_scatter_sum(s_sq[:per], total_sq[lo:lo + span], self.group)
+            p_sum = view.index_select(0, idx).reshape(-1)
+            p_sq = total_sq.view(-1, self.CHUNK).index_select(0, idx).reshape(-1)
+            per = p_sum.numel() // world
+            s_sum = torch.empty(per, dtype=total_sum.dtype, device=total_sum.device)
+            s_sq = torch.empty_like(s_sum)
+            reduce_scatter_sum(s_sum, p_sum, self.group)
+            reduce_scatter_sum(s_sq, p_sq, self.group)
             t2 = self._tick(total_sum)
-            mx = torch.tensor([self.evaluate(s_sum[:per], s_sq[:per], tracked, -1.0)[2]], dtype=torch.float64, device=total_sum.device)
+            mx = torch.tensor([self.evaluate(s_sum, s_sq, tracked, -1.0)[2] if per else 0.0], dtype=torch.float64, device=total_sum.device)
             if multi:
                 dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
-            s, c, _ = self.evaluate(s_sum[:per], s_sq[:per], tracked, float(mx.item()))
+            s, c, _ = self.evaluate(s_sum, s_sq, tracked, float(mx.item())) if per else (0.0, 0, 0.0)
             part = torch.tensor([s, c], dtype=torch.float64, device=total_sum.device)
             if multi:
                 dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
             t3 = self._tick(total_sum)
-            self.phase_seconds["range"] += t1 - t0
+            self.phase_seconds["wait_and_select"] += t1 - t0
             self.phase_seconds["exchange"] += t2 - t1
             self.phase_seconds["evaluate"] += t3 - t2
             k += 1
             current = criterion_from_partials(float(part[0].item()), float(part[1].item()))
             self.history.append(current)
-            self.exchanged_values = span
-            if total_sum.is_cuda:
-                torch.cuda.synchronize()
-            self.stat_seconds += time.perf_counter() - t0
+            self.exchanged_values = int(p_sum.numel())
+            self.stat_seconds += t3 - t0
         return tracked, current, k

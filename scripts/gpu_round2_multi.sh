@@ -18,7 +18,7 @@ for n in $( [ "$N" = 8 ] && echo "8 4 2" || echo "$N" ); do
 import json
 try:
     d = json.loads(open("gpurun_out/r2m_bench_${n}gpu.json").read().strip().splitlines()[-1])
-    print("  value %.4e e2e %.4e strong: %s" % (d["value"], d["e2e"]["value"], {k: d["strong"].get(k) for k in ("time_to_criterion_s", "passes", "histories", "transport_s", "stat_s", "final_reduce_s", "collective_share", "uncertainty_percent", "note")}))
+    print("  value %.4e e2e %.4e strong: %s" % (d["value"], d["e2e"]["value"], {k: d["strong"].get(k) for k in ("time_to_criterion_s", "passes", "histories", "transport_s", "stat_s", "final_reduce_s", "overhead_share", "stat_phases_s_rank0", "uncertainty_percent", "collective", "note")}))
 except Exception as ex:
     print("  parse failed", ex); print(open("gpurun_out/r2m_bench_${n}gpu.err").read()[-1500:])
 PY

@@ -67,7 +67,7 @@ def worker(rank, world, port, out_dir):
         np.savez(os.path.join(out_dir, "dij_%d.npz" % rank), k1=k1, k2=k2, v=v)
         # ---- statistical stopping: fresh streams per pass, rank-local running sums, reduce-scatter of the stat pair,
         # identical decision on all ranks
-        n_pad = world * P.slice_len(nvox, world)
+        n_pad = P.StoppingLoop.padded_len(nvox)
         ts, tq = torch.zeros(n_pad, dtype=torch.float64), torch.zeros(n_pad, dtype=torch.float64)
 
         def transport_pass(k):
@@ -76,8 +76,9 @@ def worker(rank, world, port, out_dir):
             ts[:nvox] += torch.from_numpy(np.ascontiguousarray(a.reshape(-1)))
             tq[:nvox] += torch.from_numpy(np.ascontiguousarray(b.reshape(-1)))
             return count
-        loop = P.StoppingLoop(60.0, transport_pass, numpy_criterion, max_passes=6)
+        loop = P.StoppingLoop(60.0, transport_pass, numpy_criterion, threshold=0.5, max_passes=6)
         tracked, current, passes = loop.run(ts, tq)
+        assert 0 < loop.exchanged_values < n_pad        # only the chunks that can pass the dose threshold travel
         np.save(os.path.join(out_dir, "stat_%d.npy" % rank), np.array([tracked, current, passes] + loop.history))
         P.reduce_dense(ts, dst=0)          # the dose itself travels once, after the last pass
         if rank == 0:
