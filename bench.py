@@ -384,9 +384,11 @@ def strong_c3(rank, world, local, dev, stream, seed, criteria=1.0):
     def warm_pass(k):
         return eng.run_sharded(seed + 1000, 0, min(total, 100_000), world, rank).histories
     P.StoppingLoop(0.0, warm_pass, evaluate, threshold=0.5, max_passes=1).run(bufs[1], bufs[2])
-    if world > 1:
-        w = torch.zeros(world * 1024, dtype=torch.float64, device=dev)
-        dist.reduce(w, dst=0)
+    if world > 1:   # NCCL sets up the channels of a collective on its first large call: not part of a pass
+        w = torch.zeros(4 * 1024 * 1024, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            P.reduce_scatter_sum(torch.empty(w.numel() // world, dtype=torch.float64, device=dev), w)
+        dist.reduce(bufs[0], dst=0)
     for b in bufs:
         b.zero_()
     torch.cuda.synchronize()
