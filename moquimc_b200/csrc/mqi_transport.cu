@@ -539,9 +539,18 @@ score_step(const Params& P, const Smem& sm, const MatEntry& M, unsigned cnb, uin
     if (SET == SET_DOSE_STAT) {
         const double v = dose + dose_te;
         if (!(v > 0.0)) return;   // then the square is not positive either
+        const double v2 = dose * dose + dose_te * dose_te;
+        if (!P.sc[0].roi && !P.sc[1].roi && !P.sc[2].roi) {   // three DIRECT rois (the common case): one test
+            if ((int) cnb > 0) {
+                atomicAdd(P.sc[0].dense + cnb, v);
+                atomicAdd(P.sc[1].dense + cnb, v);
+                atomicAdd(P.sc[2].dense + cnb, v2);
+            }
+            return;
+        }
         if (roi_accepts(P.sc[0].roi, cnb)) atomicAdd(P.sc[0].dense + cnb, v);
         if (roi_accepts(P.sc[1].roi, cnb)) atomicAdd(P.sc[1].dense + cnb, v);
-        if (roi_accepts(P.sc[2].roi, cnb)) atomicAdd(P.sc[2].dense + cnb, dose * dose + dose_te * dose_te);
+        if (roi_accepts(P.sc[2].roi, cnb)) atomicAdd(P.sc[2].dense + cnb, v2);
         return;
     }
     const int    n       = P.n_scorers;
