@@ -419,8 +419,7 @@ def strong_c3(rank, world, local, dev, stream, seed, criteria=1.0):
             "collective": ("per pass: max-all-reduce of one double and of %d chunk flags, ncclReduceScatter of the packed chunks of sum d "
                            "and sum d^2 that can hold a voxel above the dose threshold (%d of %d values each), max- and sum-all-reduce "
                            "of three doubles; once: ncclReduce of the dose grid" % (n_pad // P.StoppingLoop.CHUNK, loop.exchanged_values, nvox))
-                          if world > 1 else "none (1 GPU): the criterion is evaluated on the device, on the packed chunks (%d of %d values)"
-                          % (loop.exchanged_values, nvox),
+                          if world > 1 else "none (1 GPU): the criterion is evaluated on the device where the grids are",
             "timer": "host wall clock between device synchronisations and barriers, max over ranks", "dose_checksum": checksum}
 
 

@@ -182,16 +182,21 @@ class StoppingLoop:
             if multi:
                 dist.all_reduce(n, op=dist.ReduceOp.SUM, group=self.group)     # also where a rank waits for the slowest
             tracked += int(n.item())
-            idx, view = self.kept_chunks(total_sum, world)
-            t1 = self._tick(total_sum)
-            p_sum = view.index_select(0, idx).reshape(-1)
-            p_sq = total_sq.view(-1, self.CHUNK).index_select(0, idx).reshape(-1)
-            per = p_sum.numel() // world
-            s_sum = torch.empty(per, dtype=total_sum.dtype, device=total_sum.device)
-            s_sq = torch.empty_like(s_sum)
-            reduce_scatter_sum(s_sum, p_sum, self.group)
-            reduce_scatter_sum(s_sq, p_sq, self.group)
-            t2 = self._tick(total_sum)
+            if world == 1:      # nothing to exchange: the criterion is evaluated on the grids where they are
+                t1 = t2 = t0
+                s_sum, s_sq, per = total_sum, total_sq, total_sum.numel()
+                p_sum = total_sum
+            else:
+                idx, view = self.kept_chunks(total_sum, world)
+                t1 = self._tick(total_sum)
+                p_sum = view.index_select(0, idx).reshape(-1)
+                p_sq = total_sq.view(-1, self.CHUNK).index_select(0, idx).reshape(-1)
+                per = p_sum.numel() // world
+                s_sum = torch.empty(per, dtype=total_sum.dtype, device=total_sum.device)
+                s_sq = torch.empty_like(s_sum)
+                reduce_scatter_sum(s_sum, p_sum, self.group)
+                reduce_scatter_sum(s_sq, p_sq, self.group)
+                t2 = self._tick(total_sum)
             mx = torch.tensor([self.evaluate(s_sum, s_sq, tracked, -1.0)[2] if per else 0.0], dtype=torch.float64, device=total_sum.device)
             if multi:
                 dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
@@ -206,6 +211,6 @@ class StoppingLoop:
             k += 1
             current = criterion_from_partials(float(part[0].item()), float(part[1].item()))
             self.history.append(current)
-            self.exchanged_values = int(p_sum.numel())
+            self.exchanged_values = int(p_sum.numel()) if world > 1 else 0
             self.stat_seconds += t3 - t0
         return tracked, current, k
