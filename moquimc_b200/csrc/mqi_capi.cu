@@ -926,7 +926,7 @@ mqi_run_async_sharded(mqi_handle* h, uint64_t seed, uint64_t first_history, uint
     if (bps < 1) return fail(MQI_ECUDA, "transport kernel does not fit on an SM");
     if (h->blocks_per_sm_override > 0) bps = std::min(bps, h->blocks_per_sm_override);
     // persistent grid: a whole number of CTAs per SM, never more lanes than histories
-    const unsigned long long blk = (unsigned long long) transport_block(p.n_nodes > 1);
+    const unsigned long long blk = (unsigned long long) transport_block(p);
     unsigned long long want = (count / n_shards + 32 + blk - 1) / blk;   // this shard's share of the range
     int                grid = (int) std::min<unsigned long long>((unsigned long long) h->sm_count * bps, want);
     {   // subsystem 3: the 16-bit material volume of the scored grid is read once per voxel step by every

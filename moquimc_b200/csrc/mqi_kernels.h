@@ -23,6 +23,10 @@
 #ifndef MQI_K_BLOCK
 #define MQI_K_BLOCK 768
 #endif
+#ifndef MQI_K_BLOCK_DIJ
+#define MQI_K_BLOCK_DIJ MQI_K_BLOCK   /* threads per CTA of the single-Dij-scorer kernel (SET_DIJ with write-combining); C4 at the reference's
+                                         table size: 640: 8.11e7, 768: 8.68e7 histories/s (profiles/r2_experiments.md) */
+#endif
 #ifndef MQI_K_BLOCK_MULTI
 #define MQI_K_BLOCK_MULTI 640   /* threads per CTA of the multi-node kernels (worlds with beamline children): 96 registers per thread
                                    instead of 80 take the per-lane node descriptor without spilling (8 B against 84 B); measured on
@@ -65,7 +69,8 @@ struct MatEntry;
 struct BeamletDev;
 struct VertexDev;
 
-int         transport_block(bool multi);
+int         transport_block(bool multi, bool dij_set);
+int         transport_block(const Params& p);
 size_t      transport_smem_bytes(int n_edge_floats, int n_nodes);
 bool        transport_is_simple(const Params& p);
 cudaError_t transport_occupancy(const Params& p, int variant, size_t smem, int* blocks_per_sm);

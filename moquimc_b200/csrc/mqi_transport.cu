@@ -835,7 +835,7 @@ csda_row_fix(const float4* a1, int n, int n0, float r) {
 // MULTI: the world has beamline children (range shifter, aperture) in front of the scored grid; every
 // lane carries the index of the child it is in and reads that child's descriptor from shared memory.
 template<int VARIANT, int SET, bool MULTI, bool DIJWC = false>
-__global__ void __launch_bounds__(MULTI ? MQI_K_BLOCK_MULTI : MQI_K_BLOCK, MQI_K_MIN_BLOCKS)
+__global__ void __launch_bounds__(MULTI ? MQI_K_BLOCK_MULTI : (SET == SET_DIJ && DIJWC ? MQI_K_BLOCK_DIJ : MQI_K_BLOCK), MQI_K_MIN_BLOCKS)
 transport_kernel(const __grid_constant__ Params P) {
     constexpr bool SIMPLE  = SET == SET_DOSE;
     constexpr bool COUNTED = SET == SET_GENERIC;   // count_steps runs the general kernel
@@ -1528,14 +1528,19 @@ static inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
 
 size_t
 transport_smem_bytes(int n_edge_floats, int n_nodes) {
-    const size_t block = (size_t) transport_block(n_nodes > 1);
+    // sized for the largest CTA of the world's kernels (the single-Dij-scorer kernel may run another CTA size)
+    const size_t block = (size_t) std::max(transport_block(n_nodes > 1, false), transport_block(n_nodes > 1, true));
     return smem_queue_offset(n_edge_floats, n_nodes) + (block / 32) * kQueueWords * sizeof(uint32_t);
 }
+
+int transport_scorer_set(const Params& p);
 
 // threads per CTA of the kernels of a world with / without beamline children (the multi-node kernels carry a
 // per-lane node descriptor: fewer threads per CTA leave them more registers)
 int
-transport_block(bool multi) { return multi ? MQI_K_BLOCK_MULTI : MQI_K_BLOCK; }
+transport_block(bool multi, bool dij_set) { return multi ? MQI_K_BLOCK_MULTI : (dij_set ? MQI_K_BLOCK_DIJ : MQI_K_BLOCK); }
+int
+transport_block(const Params& p) { return transport_block(p.n_nodes > 1, p.dij_wc_scorer >= 0 && transport_scorer_set(p) == SET_DIJ); }
 
 typedef void (*transport_fn)(const Params);
 template<int SET, bool MULTI, bool DIJWC>
@@ -1581,12 +1586,12 @@ transport_occupancy(const Params& p, int variant, size_t smem, int* blocks_per_s
     transport_fn f = pick_transport(variant, transport_scorer_set(p), p.n_nodes > 1, p.dij_wc_scorer >= 0);
     cudaError_t  e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, f, transport_block(p.n_nodes > 1), smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, f, transport_block(p), smem);
 }
 
 cudaError_t
 launch_transport(const Params& p, int variant, int grid, size_t smem, cudaStream_t st) {
-    pick_transport(variant, transport_scorer_set(p), p.n_nodes > 1, p.dij_wc_scorer >= 0)<<<grid, transport_block(p.n_nodes > 1), smem, st>>>(p);
+    pick_transport(variant, transport_scorer_set(p), p.n_nodes > 1, p.dij_wc_scorer >= 0)<<<grid, transport_block(p), smem, st>>>(p);
     return cudaGetLastError();
 }
 
