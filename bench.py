@@ -385,7 +385,7 @@ def strong_c3(rank, world, local, dev, stream, seed, criteria=1.0):
         return eng.run_sharded(seed + 1000, 0, min(total, 100_000), world, rank).histories
     P.StoppingLoop(0.0, warm_pass, evaluate, threshold=0.5, max_passes=1).run(bufs[1], bufs[2])
     if world > 1:   # NCCL sets up the channels of a collective on its first large call: not part of a pass
-        w = torch.zeros(4 * 1024 * 1024, dtype=torch.float64, device=dev)
+        w = torch.zeros(12 * 1024 * 1024, dtype=torch.float64, device=dev)   # the size of the packed exchange of a pass
         for _ in range(2):
             P.reduce_scatter_sum(torch.empty(w.numel() // world, dtype=torch.float64, device=dev), w)
         dist.reduce(bufs[0], dst=0)
@@ -395,7 +395,7 @@ def strong_c3(rank, world, local, dev, stream, seed, criteria=1.0):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    loop = P.StoppingLoop(criteria, transport_pass, evaluate, threshold=0.5, max_passes=400)
+    loop = P.StoppingLoop(criteria, transport_pass, evaluate, threshold=0.5, max_passes=400, histories_per_pass=total)
     tracked, current, passes = loop.run(bufs[1], bufs[2])
     t1 = time.perf_counter()
     if world > 1:
@@ -416,11 +416,12 @@ def strong_c3(rank, world, local, dev, stream, seed, criteria=1.0):
             "transport_s": transport_s, "stat_s": stat_s, "stat_phases_s_rank0": loop.phase_seconds, "final_reduce_s": reduce_s,
             "overhead_share": (total_s - transport_s) / total_s,   # everything but the slowest rank's kernels: selection, exchange,
                                                                    # evaluation, the final reduce, launch and host latencies
-            "collective": ("per pass: max-all-reduce of one double and of %d chunk flags, ncclReduceScatter of the packed chunks of sum d "
+            "collective": ("per pass %d collectives: max-all-reduce of %d chunk flags, ONE ncclReduceScatter of the packed chunks of sum d "
                            "and sum d^2 that can hold a voxel above the dose threshold (%d of %d values each), max- and sum-all-reduce "
-                           "of three doubles; once: ncclReduce of the dose grid" % (n_pad // P.StoppingLoop.CHUNK, loop.exchanged_values, nvox))
+                           "of three doubles; once: ncclReduce of the dose grid" % (loop.collectives_per_pass, n_pad // P.StoppingLoop.CHUNK,
+                                                                                   loop.exchanged_values, nvox))
                           if world > 1 else "none (1 GPU): the criterion is evaluated on the device where the grids are",
-            "timer": "host wall clock between device synchronisations and barriers, max over ranks", "dose_checksum": checksum}
+            "timer": "host wall clock between device synchronisations and barriers, max over ranks; the phases by CUDA events on rank 0", "dose_checksum": checksum}
 
 
 def bench_b200(args):

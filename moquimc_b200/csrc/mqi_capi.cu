@@ -182,6 +182,8 @@ struct mqi_handle {
     // beamline children in transport order (multi-node launches), and their device mirror
     std::vector<HostNode> beamline;
     GridDev*  d_nodes = nullptr;
+    uint32_t* d_adv_raw = nullptr;      // hand-over buffers of the multi-node kernels (transport_handover_bytes), grown on demand
+    size_t    adv_raw_bytes = 0;
     float*    d_edges_all = nullptr;
     int       n_edge_floats_all = 0;
     bool      nodes_dirty = true;
@@ -583,6 +585,7 @@ mqi_destroy(mqi_handle* h) {
     }
     cudaFree(h->d_tab_a0); cudaFree(h->d_tab_a1); cudaFree(h->d_tab_bs); cudaFree(h->d_tab_n0); cudaFree(h->d_tab_n1); cudaFree(h->d_correction); cudaFree(h->d_counters);
     cudaFree(h->d_beamlets); cudaFree(h->d_cum); cudaFree(h->d_vertices); cudaFree(h->d_spot_ids);
+    cudaFree(h->d_adv_raw);
     cudaFree(h->d_stat_slice);
     cudaFree(h->d_stat_flags);
     cudaFree(h->d_stat_list);
@@ -962,6 +965,17 @@ mqi_run_async_sharded(mqi_handle* h, uint64_t seed, uint64_t first_history, uint
             if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
             h->l2_window_set = set_window;
         }
+    }
+    {
+        const size_t hb = transport_handover_bytes(grid, p.n_nodes);
+        if (hb > h->adv_raw_bytes) {
+            CU(cudaStreamSynchronize(h->stream));   // an earlier launch may still use the smaller buffer
+            cudaFree(h->d_adv_raw);
+            h->d_adv_raw = nullptr; h->adv_raw_bytes = 0;
+            CU(cudaMalloc(&h->d_adv_raw, hb));
+            h->adv_raw_bytes = hb;
+        }
+        p.adv_raw = h->d_adv_raw;
     }
     CU(cudaMemsetAsync(h->d_counters, 0, C_COUNT * sizeof(unsigned long long), h->stream));
     CU(cudaEventRecord(h->ev0, h->stream));

@@ -45,6 +45,21 @@
                                 with 640 threads per CTA, profiles/r2_experiments.md) */
 #endif
 
+#ifndef MQI_K_ADV_QUEUE
+#define MQI_K_ADV_QUEUE 1    /* multi-node worlds: 1 = tracks that leave a beamline child go through a per-warp hand-over buffer and are
+                                located in the next child 32 at a time (process_handovers); 0 = batched hand-overs in the owning lane */
+#endif
+#ifndef MQI_K_ADV_PUSH_INLINE
+#define MQI_K_ADV_PUSH_INLINE __noinline__
+#endif
+#ifndef MQI_K_ADV_MIN
+#define MQI_K_ADV_MIN 32     /* buffered hand-overs that make the warp process them instead of fetching primaries when its queue is empty */
+#endif
+#ifndef MQI_K_ADV_RAW_CAP
+#define MQI_K_ADV_RAW_CAP 96 /* entries of a warp's hand-over buffer (48 B each, global memory); a lane that finds it full falls back to
+                                restart_lane */
+#endif
+
 #ifndef MQI_K_RSP_EXACT
 #define MQI_K_RSP_EXACT 0    /* 1: the transport kernel evaluates spr_default in the reference's precision (rsp_eval_exact) */
 #endif
@@ -72,6 +87,7 @@ struct VertexDev;
 int         transport_block(bool multi, bool dij_set);
 int         transport_block(const Params& p);
 size_t      transport_smem_bytes(int n_edge_floats, int n_nodes);
+size_t      transport_handover_bytes(int grid, int n_nodes);   // per-launch scratch of a multi-node world (0: none)
 bool        transport_is_simple(const Params& p);
 cudaError_t transport_occupancy(const Params& p, int variant, size_t smem, int* blocks_per_sm);
 cudaError_t launch_transport(const Params& p, int variant, int grid, size_t smem, cudaStream_t st);

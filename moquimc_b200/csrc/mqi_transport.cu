@@ -28,7 +28,7 @@ struct Smem {
     const float2* bs;   // {cs_pp + cs_pO_el + cs_pO_inel, slope}                  Ei = 0.5
     const float*  edges;   // node k: xe | ye | ze at edges + nodes[k].edge_off (single node: offset 0)
     const GridDev* nodes;  // multi-node launches only
-    uint32_t*     queue;   // kQueueWords words per warp
+    uint32_t*     queue;   // queue_words(multi) words per warp
 };
 
 // queue of pre-sampled primaries, one per warp, structure of arrays: field f of entry e at
@@ -36,8 +36,17 @@ struct Smem {
 // drained by the lanes whose track ended.  Shared memory is taken from the L1 carve-out, so the queue
 // is kept as small as one refill.
 constexpr int kQueueCap    = 32;
-enum QueueField { Q_PX = 0, Q_PY, Q_PZ, Q_DX, Q_DY, Q_DZ, Q_KE, Q_IX, Q_IY, Q_IZ, Q_H0, Q_H1, Q_SPOT, Q_NODE, Q_FIELDS };
-constexpr int kQueueWords  = Q_FIELDS * kQueueCap;
+// Q_BLK (multi-node launches only): the Philox block the track continues with -- a queue entry is then either a fresh
+// primary or a track handed over from one beamline child to the next (process_handovers)
+enum QueueField { Q_PX = 0, Q_PY, Q_PZ, Q_DX, Q_DY, Q_DZ, Q_KE, Q_IX, Q_IY, Q_IZ, Q_H0, Q_H1, Q_SPOT, Q_NODE, Q_FIELDS, Q_BLK = Q_FIELDS };
+__host__ __device__ constexpr int queue_words(bool multi) { return (multi ? Q_FIELDS + 1 : Q_FIELDS) * kQueueCap; }
+
+// Hand-over buffer (multi-node launches, MQI_K_ADV_QUEUE): tracks that left a beamline child alive, in that child's frame,
+// waiting to be mapped to the world and located in the next child by the whole warp at once.  One buffer per warp in global
+// memory (written and read through L2: 2 pushes per history), structure of arrays like the queue.
+constexpr int kRawCap = MQI_K_ADV_RAW_CAP;
+enum RawField { R_PX = 0, R_PY, R_PZ, R_DX, R_DY, R_DZ, R_KE, R_H0, R_H1, R_SPOT, R_NODE, R_BLK, R_FIELDS };
+constexpr int kRawWords = R_FIELDS * kRawCap;
 constexpr size_t kTableBytes = kTableN * (2 * sizeof(float4) + sizeof(float2));
 
 __host__ __device__ __forceinline__ size_t
@@ -700,24 +709,29 @@ enter_nodes(const Params& P, const Smem& sm, TrackIO& T) {
 // A lane whose track ended continues with (a) the same track in the next child of the world, if it
 // left its node alive (multi-node launches: local -> world, mqi_transport.hpp:234-239, then the c_ind
 // loop goes on), or (b) the secondary on top of its stack, which starts at child 0 again (:160-162).
+// a track that left child G alive: child frame -> world frame, mqi_transport.hpp:234-239
+__device__ __forceinline__ void
+node_to_world(const GridDev& G, TrackIO& T) {
+    if (!G.identity) {
+        const float* R  = G.rot_fwd;
+        const float  qx = T.px, qy = T.py, qz = T.pz;
+        T.px = R[0] * qx + R[1] * qy + R[2] * qz + G.trans[0];
+        T.py = R[3] * qx + R[4] * qy + R[5] * qz + G.trans[1];
+        T.pz = R[6] * qx + R[7] * qy + R[8] * qz + G.trans[2];
+        const float ex = T.dx, ey = T.dy, ez = T.dz;
+        T.dx = R[0] * ex + R[1] * ey + R[2] * ez;
+        T.dy = R[3] * ex + R[4] * ey + R[5] * ez;
+        T.dz = R[6] * ex + R[7] * ey + R[8] * ez;
+    }
+}
+
 template<bool MULTI>
 __device__ __noinline__ bool
 restart_lane(const Params& P, const Secondary* __restrict__ stack, TrackIO& __restrict__ T, int advance) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem sm = smem_view(smem_raw, P.n_edge_floats, P.n_nodes);
     if (MULTI && advance) {
-        const GridDev& G = sm.nodes[T.node];
-        if (!G.identity) {
-            const float* R  = G.rot_fwd;
-            const float  qx = T.px, qy = T.py, qz = T.pz;
-            T.px = R[0] * qx + R[1] * qy + R[2] * qz + G.trans[0];
-            T.py = R[3] * qx + R[4] * qy + R[5] * qz + G.trans[1];
-            T.pz = R[6] * qx + R[7] * qy + R[8] * qz + G.trans[2];
-            const float ex = T.dx, ey = T.dy, ez = T.dz;
-            T.dx = R[0] * ex + R[1] * ey + R[2] * ez;
-            T.dy = R[3] * ex + R[4] * ey + R[5] * ez;
-            T.dz = R[6] * ex + R[7] * ey + R[8] * ez;
-        }
+        node_to_world(sm.nodes[T.node], T);
         T.node += 1;   // the caller only advances when a next child exists
     } else {
         const Secondary s = stack[--T.sp];   // by value: the nine loads are issued back to back, then the stores
@@ -727,6 +741,64 @@ restart_lane(const Params& P, const Secondary* __restrict__ stack, TrackIO& __re
         T.node   = 0;
     }
     return enter_nodes<MULTI>(P, sm, T);
+}
+
+// one track into a warp's hand-over buffer (out of line: twelve scattered stores that the step loop should not hold
+// registers for)
+__device__ MQI_K_ADV_PUSH_INLINE void
+push_handover(uint32_t* w, float px, float py, float pz, float dx, float dy, float dz, float ke, uint32_t h0, uint32_t h1, uint32_t spot,
+              uint32_t node, uint32_t blk) {
+    __stcg(w + R_PX * kRawCap, __float_as_uint(px)); __stcg(w + R_PY * kRawCap, __float_as_uint(py));
+    __stcg(w + R_PZ * kRawCap, __float_as_uint(pz)); __stcg(w + R_DX * kRawCap, __float_as_uint(dx));
+    __stcg(w + R_DY * kRawCap, __float_as_uint(dy)); __stcg(w + R_DZ * kRawCap, __float_as_uint(dz));
+    __stcg(w + R_KE * kRawCap, __float_as_uint(ke));
+    __stcg(w + R_H0 * kRawCap, h0); __stcg(w + R_H1 * kRawCap, h1);
+    __stcg(w + R_SPOT * kRawCap, spot); __stcg(w + R_NODE * kRawCap, node);
+    __stcg(w + R_BLK * kRawCap, blk);
+}
+
+// The whole warp takes the top (up to 32) tracks of its hand-over buffer: every lane maps one from the child it left to
+// the world frame (mqi_transport.hpp:234-239), offers it to the following children (enter_nodes, the c_ind loop) and
+// appends it to the warp's EMPTY queue if it enters one.  What restart_lane's advance branch does for one lane at a
+// time, at full SIMT width.  Returns the number of queue entries written.
+__device__ __noinline__ int
+process_handovers(const Params& P, uint32_t* q, const uint32_t* raw, int n_raw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem sm   = smem_view(smem_raw, P.n_edge_floats, P.n_nodes);
+    const int  lane = threadIdx.x & 31;
+    const int  e    = n_raw - 1 - lane;
+    bool       alive = false;
+    TrackIO    T;
+    uint32_t   h0 = 0, h1 = 0, spot = 0, blk = 0;
+    if (e >= 0) {
+        const uint32_t* r = raw + e;
+        T.px = __uint_as_float(__ldcg(r + R_PX * kRawCap)); T.py = __uint_as_float(__ldcg(r + R_PY * kRawCap));
+        T.pz = __uint_as_float(__ldcg(r + R_PZ * kRawCap)); T.dx = __uint_as_float(__ldcg(r + R_DX * kRawCap));
+        T.dy = __uint_as_float(__ldcg(r + R_DY * kRawCap)); T.dz = __uint_as_float(__ldcg(r + R_DZ * kRawCap));
+        T.ke = __uint_as_float(__ldcg(r + R_KE * kRawCap));
+        h0 = __ldcg(r + R_H0 * kRawCap); h1 = __ldcg(r + R_H1 * kRawCap);
+        spot = __ldcg(r + R_SPOT * kRawCap); blk = __ldcg(r + R_BLK * kRawCap);
+        T.node   = (int) __ldcg(r + R_NODE * kRawCap);
+        T.recoil = 0;
+        node_to_world(sm.nodes[T.node], T);
+        T.node += 1;   // a track is only handed over when a next child exists
+        alive = enter_nodes<true>(P, sm, T);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, alive);
+    if (alive) {
+        uint32_t* w = q + __popc(m & ((1u << lane) - 1u));
+        w[Q_PX * kQueueCap] = __float_as_uint(T.px); w[Q_PY * kQueueCap] = __float_as_uint(T.py);
+        w[Q_PZ * kQueueCap] = __float_as_uint(T.pz); w[Q_DX * kQueueCap] = __float_as_uint(T.dx);
+        w[Q_DY * kQueueCap] = __float_as_uint(T.dy); w[Q_DZ * kQueueCap] = __float_as_uint(T.dz);
+        w[Q_KE * kQueueCap] = __float_as_uint(T.ke);
+        w[Q_IX * kQueueCap] = (uint32_t) T.ix; w[Q_IY * kQueueCap] = (uint32_t) T.iy; w[Q_IZ * kQueueCap] = (uint32_t) T.iz;
+        w[Q_H0 * kQueueCap] = h0; w[Q_H1 * kQueueCap] = h1;
+        w[Q_SPOT * kQueueCap] = spot;
+        w[Q_NODE * kQueueCap] = (uint32_t) T.node;
+        w[Q_BLK * kQueueCap]  = blk;
+    }
+    __syncwarp();
+    return __popc(m);
 }
 
 // The whole warp fetches the next 32 history ids with one atomic, samples (or loads) their primary
@@ -788,6 +860,7 @@ refill_queue(const Params& P, uint32_t* q, int q_n) {
         e[Q_H0 * kQueueCap] = h0; e[Q_H1 * kQueueCap] = h1;
         e[Q_SPOT * kQueueCap] = P.per_spot ? spot : kEmptyKey32;
         e[Q_NODE * kQueueCap] = (uint32_t) T.node;
+        if (MULTI) e[Q_BLK * kQueueCap] = P.src.vertices ? 0u : 2u;   // blocks 0-1 belong to the source sampling
     }
     __syncwarp();
     const int exhausted = base + 32ull * P.n_shards >= P.count ? 1 : 0;   // the shard's next chunk lies beyond the range
@@ -885,8 +958,12 @@ transport_kernel(const __grid_constant__ Params P) {
     // the warp's queue of pre-sampled primaries: entries in the queue | history counter exhausted << 16
     // (warp-uniform; one register)
     int q_state = 0;
+#if MQI_K_ADV_QUEUE
+    int n_raw = 0;      // MULTI: tracks in the warp's hand-over buffer (warp-uniform)
+#else
     int adv_wait = 0;   // MULTI: turns the oldest lane waiting for a node hand-over has waited (warp-uniform)
     constexpr int kAdvBatch = MQI_K_ADV_BATCH, kAdvTurns = MQI_K_ADV_TURNS;
+#endif
 
     // Warp-level reconvergence.  Restarting a lane is executed by the few lanes whose track just ended;
     // without an explicit join the compiler only reconverges them at the END of the iteration, i.e. the
@@ -906,6 +983,30 @@ transport_kernel(const __grid_constant__ Params P) {
         // (the whole warp waiting for ~ 300 instructions of a single lane, twice per history) this was 27 % of the
         // issued warp instructions at 1.5 active lanes (profiles/r2_experiments.md).
         bool hand_over = true;
+#if MQI_K_ADV_QUEUE
+        // Hand-over queue: a track that left a beamline child alive does not have to go on in the lane that brought it
+        // there.  The lane writes it -- position and direction in the child's frame, energy, history id, Philox block --
+        // to the warp's hand-over buffer and takes the next located track from the warp's queue (a primary or an earlier
+        // hand-over); when the queue runs empty the whole warp maps 32 buffered tracks to the world frame and locates
+        // them in their next child at once (process_handovers).  The stream protocol is untouched: a history's blocks
+        // are consumed in the same order by whichever lane owns the track.  A lane that still holds secondaries of the
+        // history (sp > 0; they follow the primary in the history's block sequence) keeps the track: restart_lane below.
+        uint32_t* const raw = MULTI ? P.adv_raw + ((size_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kRawWords : nullptr;
+        if (MULTI) {
+            const bool     push = (fl & FL_ADVANCE) != 0u && sp == 0;
+            const unsigned pm   = __ballot_sync(0xffffffffu, push);
+            if (pm) {
+                const int r = n_raw + __popc(pm & ((1u << (threadIdx.x & 31)) - 1u));
+                if (push && r < kRawCap) {
+                    if (DIJWC) flush_dij(P, wc, spot_ind);
+                    push_handover(raw + r, px, py, pz, dx, dy, dz, ke, h0, h1, spot_ind, (uint32_t) node, blk);
+                    fl = 0u;   // the lane is free and takes the next queue entry below
+                }
+                n_raw = min(n_raw + __popc(pm), kRawCap);   // lanes the buffer has no room for hand their track over themselves
+                __syncwarp();
+            }
+        }
+#else
         if (MULTI) {
             const unsigned adv = __ballot_sync(0xffffffffu, (fl & FL_ADVANCE) != 0u);
             if (adv) {
@@ -914,6 +1015,7 @@ transport_kernel(const __grid_constant__ Params P) {
                 if (hand_over) adv_wait = 0;
             }
         }
+#endif
         bool need = false;   // the lane needs a new primary
         if (!(fl & (FL_ALIVE | FL_DONE)) && !(MULTI && (fl & FL_ADVANCE) && !hand_over)) {
             if (DIJWC) flush_dij(P, wc, spot_ind);   // the track ended: insert its pending write-combined Dij hit
@@ -939,12 +1041,23 @@ transport_kernel(const __grid_constant__ Params P) {
         if (need_mask) {
             const int n_need = __popc(need_mask);
             const int lane   = threadIdx.x & 31;
-            uint32_t* q      = sm.queue + (threadIdx.x >> 5) * kQueueWords;
+            uint32_t* q      = sm.queue + (threadIdx.x >> 5) * queue_words(MULTI);
             // warp-uniform: the queue is empty and the source is not exhausted -> every lane helps to refill.
             // Lanes a nearly empty queue cannot serve this turn idle for one pass and are served next turn.
+#if MQI_K_ADV_QUEUE
+            if (MULTI && (q_state & 0xffff) == 0 && n_raw > 0 && (n_raw >= MQI_K_ADV_MIN || (q_state >> 16) != 0)) {
+                // buffered hand-overs first (a full warp's worth, or whatever is left once the source is exhausted)
+                q_state = process_handovers(P, q, raw, n_raw) | (q_state & 0x10000);
+                n_raw   = max(n_raw - 32, 0);
+            } else
+#endif
             if (q_state == 0) q_state = refill_queue<MULTI>(P, q, 0);
             const int  q_n       = q_state & 0xffff;
+#if MQI_K_ADV_QUEUE
+            const bool src_empty = (q_state >> 16) != 0 && !(MULTI && n_raw > 0);   // buffered hand-overs are work to come
+#else
             const bool src_empty = (q_state >> 16) != 0;
+#endif
             if (need) {
                 const int e = q_n - 1 - __popc(need_mask & ((1u << lane) - 1u));
                 if (e >= 0) {
@@ -957,7 +1070,8 @@ transport_kernel(const __grid_constant__ Params P) {
                     h0 = qe[Q_H0 * kQueueCap]; h1 = qe[Q_H1 * kQueueCap];
                     spot_ind = qe[Q_SPOT * kQueueCap];
                     if (MULTI) node = (int) qe[Q_NODE * kQueueCap];
-                    blk    = P.src.vertices ? 0u : 2u;   // blocks 0-1 belong to the source sampling
+                    if (MULTI) blk = qe[Q_BLK * kQueueCap];      // a primary's first block, or where a handed-over track goes on
+                    else blk = P.src.vertices ? 0u : 2u;         // blocks 0-1 belong to the source sampling
                     fl = FL_ALIVE;
                 } else if (src_empty) {
                     fl = FL_DONE;
@@ -1530,7 +1644,17 @@ size_t
 transport_smem_bytes(int n_edge_floats, int n_nodes) {
     // sized for the largest CTA of the world's kernels (the single-Dij-scorer kernel may run another CTA size)
     const size_t block = (size_t) std::max(transport_block(n_nodes > 1, false), transport_block(n_nodes > 1, true));
-    return smem_queue_offset(n_edge_floats, n_nodes) + (block / 32) * kQueueWords * sizeof(uint32_t);
+    return smem_queue_offset(n_edge_floats, n_nodes) + (block / 32) * queue_words(n_nodes > 1) * sizeof(uint32_t);
+}
+
+// hand-over buffers of a multi-node launch: kRawWords words per warp of the grid
+size_t
+transport_handover_bytes(int grid, int n_nodes) {
+#if MQI_K_ADV_QUEUE
+    if (n_nodes > 1) return (size_t) grid * (MQI_K_BLOCK_MULTI / 32) * kRawWords * sizeof(uint32_t);
+#endif
+    (void) grid; (void) n_nodes;
+    return 0;
 }
 
 int transport_scorer_set(const Params& p);

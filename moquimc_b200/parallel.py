@@ -110,13 +110,15 @@ class StoppingLoop:
     accumulating).  calculate_stat (mqi_tps_env.hpp:1339-1426) averages sigma/mu over the voxels whose mean dose exceeds
     threshold x the largest mean dose, so after a pass only the voxels that CAN exceed it are exchanged:
 
-      * M_lb = max over ranks of the rank's largest local sum -- a lower bound of the largest summed value;
-      * a voxel whose local sum is at most threshold * M_lb / world on EVERY rank sums to at most threshold * M_lb and
-        cannot qualify; the grids are cut into chunks of CHUNK voxels and a chunk is kept if any rank holds a larger
-        value in it (one max-all-reduce of the chunk flags, 12 800 flags for a 512 x 512 x 200 grid);
-      * the kept chunks of sum d and sum d^2 are packed, reduce-scattered (every link carries 1 / world of the packed
-        values, all links at once) and every rank evaluates its slice: the largest mean dose (max-all-reduce of one
-        double), then sum of sigma/mu and the voxel count (sum-all-reduce of two doubles).
+      * a voxel that qualifies sums to more than threshold * M (M = the largest summed value), so at least one rank holds
+        more than threshold * M / world of it; every rank's own largest value m_r is a lower bound of M, so a voxel whose
+        local value is at most threshold * m_r / world on EVERY rank r cannot qualify.  The grids are cut into chunks of
+        CHUNK voxels and a chunk is kept if any rank holds a larger value in it (one max-all-reduce of the chunk flags,
+        12 800 flags for a 512 x 512 x 200 grid; no exchange is needed for the bound itself);
+      * the kept chunks of sum d and sum d^2 are packed into one buffer and reduce-scattered (ONE collective: every link
+        carries 1 / world of the packed values, all links at once) and every rank evaluates its slice: the largest mean
+        dose (max-all-reduce of one double), then sum of sigma/mu and the voxel count (sum-all-reduce of two doubles).
+        Four collectives per pass; the phase times are taken with CUDA events, not host synchronisations.
 
     The selected voxels and the criterion are exactly those of an evaluation on whole summed grids; at config C3 the
     packed exchange is a few per cent of the grid.  The dose itself is reduced once, after the last pass.
@@ -129,17 +131,22 @@ class StoppingLoop:
 
     CHUNK = 4096
 
-    def __init__(self, criteria_percent, transport_pass, evaluate, threshold=0.5, max_passes=1000, group=None):
+    def __init__(self, criteria_percent, transport_pass, evaluate, threshold=0.5, max_passes=1000, group=None,
+                 histories_per_pass=None):
+        """histories_per_pass: histories ALL ranks transport per pass, if the caller knows it (a fixed plan): saves the
+        sum-all-reduce of the per-rank counts."""
         self.criteria = criteria_percent
         self.transport_pass = transport_pass
         self.evaluate = evaluate
         self.threshold = threshold
         self.max_passes = max_passes
         self.group = group
+        self.histories_per_pass = histories_per_pass
         self.history = []
         self.stat_seconds = 0.0
         self.phase_seconds = {"wait_and_select": 0.0, "exchange": 0.0, "evaluate": 0.0}   # where stat_seconds goes
         self.exchanged_values = 0
+        self.collectives_per_pass = 0
 
     @classmethod
     def padded_len(cls, n):
@@ -147,56 +154,73 @@ class StoppingLoop:
         return (n + cls.CHUNK - 1) // cls.CHUNK * cls.CHUNK
 
     @staticmethod
-    def _tick(t):
+    def _mark(t):
+        """a time stamp that does not stop the host: a CUDA event on the current stream (GPU), the clock (CPU)"""
         import time
         import torch
         if t.is_cuda:
-            torch.cuda.synchronize()
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
         return time.perf_counter()
 
+    @staticmethod
+    def _between(a, b):
+        return a.elapsed_time(b) * 1e-3 if hasattr(a, "elapsed_time") else b - a
+
     def kept_chunks(self, total_sum, world):
-        """indices of the chunks that can hold a voxel above the threshold (the same list on every rank)"""
+        """indices of the chunks that can hold a voxel above the threshold (the same list on every rank).  A voxel that
+        qualifies sums to more than threshold x the largest summed value M, so at least one rank holds more than
+        threshold x M / world of it; every rank tests its chunks against its OWN largest value m_r <= M (no exchange
+        needed for the bound) and the flags are OR-ed: a superset of the chunks that matter, the evaluation is exact."""
         import torch
         import torch.distributed as dist
         view = total_sum.view(-1, self.CHUNK)
         cmax = view.amax(dim=1)
-        m_lb = cmax.max().reshape(1).clone()
-        if world > 1:
-            dist.all_reduce(m_lb, op=dist.ReduceOp.MAX, group=self.group)
-        keep = (cmax > (self.threshold / world) * m_lb).to(torch.int32)
+        keep = (cmax > (self.threshold / world) * cmax.max()).to(torch.int32)
         if world > 1:
             dist.all_reduce(keep, op=dist.ReduceOp.MAX, group=self.group)
         return torch.nonzero(keep).reshape(-1), view
 
     def run(self, total_sum, total_sq):
-        import time
         import torch
         import torch.distributed as dist
         multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
         world = dist.get_world_size(self.group) if multi else 1
         assert total_sum.numel() == total_sq.numel() and total_sum.numel() % self.CHUNK == 0 and self.CHUNK % world == 0
         tracked, current, k = 0, 100.0, 0
+        marks = []
         while current > self.criteria and k < self.max_passes:
-            n = torch.tensor([self.transport_pass(k)], dtype=torch.int64, device=total_sum.device)
-            t0 = self._tick(total_sum)
-            if multi:
-                dist.all_reduce(n, op=dist.ReduceOp.SUM, group=self.group)     # also where a rank waits for the slowest
-            tracked += int(n.item())
+            n_local = self.transport_pass(k)
+            t0 = self._mark(total_sum)
+            ncoll = 0
+            if self.histories_per_pass is not None:
+                tracked += int(self.histories_per_pass)
+            elif multi:
+                n = torch.tensor([n_local], dtype=torch.int64, device=total_sum.device)
+                dist.all_reduce(n, op=dist.ReduceOp.SUM, group=self.group)
+                tracked += int(n.item())
+                ncoll += 1
+            else:
+                tracked += int(n_local)
             if world == 1:      # nothing to exchange: the criterion is evaluated on the grids where they are
                 t1 = t2 = t0
                 s_sum, s_sq, per = total_sum, total_sq, total_sum.numel()
-                p_sum = total_sum
+                n_packed = 0
             else:
                 idx, view = self.kept_chunks(total_sum, world)
-                t1 = self._tick(total_sum)
-                p_sum = view.index_select(0, idx).reshape(-1)
-                p_sq = total_sq.view(-1, self.CHUNK).index_select(0, idx).reshape(-1)
-                per = p_sum.numel() // world
-                s_sum = torch.empty(per, dtype=total_sum.dtype, device=total_sum.device)
-                s_sq = torch.empty_like(s_sum)
-                reduce_scatter_sum(s_sum, p_sum, self.group)
-                reduce_scatter_sum(s_sq, p_sq, self.group)
-                t2 = self._tick(total_sum)
+                t1 = self._mark(total_sum)
+                # the kept chunks of both grids in ONE buffer, rank r's share of sum d next to its share of sum d^2:
+                # one reduce-scatter leaves every rank with the summed values of 1 / world of the packed voxels
+                n_packed = int(idx.numel()) * self.CHUNK
+                per = n_packed // world
+                packed = torch.stack((view.index_select(0, idx).view(world, per),
+                                      total_sq.view(-1, self.CHUNK).index_select(0, idx).view(world, per)), dim=1).reshape(-1)
+                mine = torch.empty(2 * per, dtype=total_sum.dtype, device=total_sum.device)
+                reduce_scatter_sum(mine, packed, self.group)
+                s_sum, s_sq = mine[:per], mine[per:]
+                t2 = self._mark(total_sum)
+                ncoll += 2
             mx = torch.tensor([self.evaluate(s_sum, s_sq, tracked, -1.0)[2] if per else 0.0], dtype=torch.float64, device=total_sum.device)
             if multi:
                 dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
@@ -204,13 +228,20 @@ class StoppingLoop:
             part = torch.tensor([s, c], dtype=torch.float64, device=total_sum.device)
             if multi:
                 dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
-            t3 = self._tick(total_sum)
-            self.phase_seconds["wait_and_select"] += t1 - t0
-            self.phase_seconds["exchange"] += t2 - t1
-            self.phase_seconds["evaluate"] += t3 - t2
+                ncoll += 2
+            part = part.tolist()
+            t3 = self._mark(total_sum)
+            marks.append((t0, t1, t2, t3))
             k += 1
-            current = criterion_from_partials(float(part[0].item()), float(part[1].item()))
+            current = criterion_from_partials(float(part[0]), float(part[1]))
             self.history.append(current)
-            self.exchanged_values = int(p_sum.numel()) if world > 1 else 0
-            self.stat_seconds += t3 - t0
+            self.exchanged_values = n_packed
+            self.collectives_per_pass = ncoll
+        if marks and hasattr(marks[-1][3], "synchronize"):
+            marks[-1][3].synchronize()
+        for t0, t1, t2, t3 in marks:
+            self.phase_seconds["wait_and_select"] += self._between(t0, t1)
+            self.phase_seconds["exchange"] += self._between(t1, t2)
+            self.phase_seconds["evaluate"] += self._between(t2, t3)
+            self.stat_seconds += self._between(t0, t3)
         return tracked, current, k

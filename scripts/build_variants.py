@@ -12,11 +12,13 @@ VARIANTS = {
     "adv1": (768, 1, 0, "-DMQI_K_ADV_BATCH=1", "-DMQI_K_ADV_TURNS=0"), "adv10": (768, 1, 0, "-DMQI_K_ADV_BATCH=6", "-DMQI_K_ADV_TURNS=10", "-DMQI_K_BLOCK_MULTI=640"),
     "pw1": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=1"), "pw2": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=2"),
     "pw4": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=4"), "adv10b": (768, 1, 0, "-DMQI_K_ADV_BATCH=6", "-DMQI_K_ADV_TURNS=10"),
-    "pf1": (768, 1, 0, "-DMQI_K_DIJ_PREFETCH=1"), "pf2": (768, 1, 0, "-DMQI_K_DIJ_PREFETCH=2"),
-    "df": (768, 1, 0, "-DMQI_K_DIJ_DEFER=1"), "dfp": (768, 1, 0, "-DMQI_K_DIJ_DEFER=1", "-DMQI_K_DIJ_PREFETCH=1"),
-    "df640": (768, 1, 0, "-DMQI_K_DIJ_DEFER=1", "-DMQI_K_BLOCK_DIJ=640"), "dfp640": (768, 1, 0, "-DMQI_K_DIJ_DEFER=1", "-DMQI_K_DIJ_PREFETCH=1", "-DMQI_K_BLOCK_DIJ=640"),
-    "dfp2_640": (768, 1, 0, "-DMQI_K_DIJ_DEFER=1", "-DMQI_K_DIJ_PREFETCH=2", "-DMQI_K_BLOCK_DIJ=640"),
-    "cur640": (768, 1, 0, "-DMQI_K_BLOCK_DIJ=640"), "pf1_640": (768, 1, 0, "-DMQI_K_DIJ_PREFETCH=1", "-DMQI_K_BLOCK_DIJ=640"),
+        "cur640": (768, 1, 0, "-DMQI_K_BLOCK_DIJ=640"),
+    "old": (768, 1, 0, "-DMQI_K_ADV_QUEUE=0", "-DMQI_K_DIJ_COOP=0"), "new": (768, 1, 0),
+    "coop_b2": (768, 1, 0, "-DMQI_K_DIJ_BATCHES=2"), "coop640": (768, 1, 0, "-DMQI_K_BLOCK_DIJ=640"),
+    "coop640_b2": (768, 1, 0, "-DMQI_K_BLOCK_DIJ=640", "-DMQI_K_DIJ_BATCHES=2"), "coop_t4b2": (768, 1, 0, "-DMQI_K_DIJ_TEAM=4", "-DMQI_K_DIJ_BATCHES=2"),
+    "coop_t4b3": (768, 1, 0, "-DMQI_K_DIJ_TEAM=4", "-DMQI_K_DIJ_BATCHES=3"), "coop_t16": (768, 1, 0, "-DMQI_K_DIJ_TEAM=16", "-DMQI_K_DIJ_BATCHES=3"),
+    "advmin16": (768, 1, 0, "-DMQI_K_ADV_MIN=16"), "advmin24": (768, 1, 0, "-DMQI_K_ADV_MIN=24"), "adv768": (768, 1, 0, "-DMQI_K_BLOCK_MULTI=768"),
+    "cur896": (768, 1, 0, "-DMQI_K_BLOCK_DIJ=896"), "cur1024": (768, 1, 0, "-DMQI_K_BLOCK_DIJ=1024"),
     "cur": (768, 1, 0), "ph10": (768, 1, 0, "-DMQI_K_PHILOX_ROUNDS=10"),
     "b256": (256, 4, 0), "b512": (512, 2, 0), "b128": (128, 8, 0), "b256_3": (256, 3, 0),
     "early_lut": (256, 4, 0, "-DMQI_K_LATE_LUT=0"), "base": (256, 4, 0),
