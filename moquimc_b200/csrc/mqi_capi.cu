@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -533,6 +534,7 @@ create_impl(mqi_handle* h, int device_id) {
     CU(cudaGetDeviceProperties(&prop, device_id));
     h->sm_count = prop.multiProcessorCount;
     h->l2_persist_max = (size_t) prop.persistingL2CacheMaxSize;
+    if (const char* e = std::getenv("MQI_L2_PERSIST")) h->l2_persist = std::atoi(e);   // tuning aid: default of the option "l2_persist"
     h->l2_window_max  = (size_t) prop.accessPolicyMaxWindowSize;
     CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
