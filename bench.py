@@ -389,24 +389,34 @@ def strong_c3(rank, world, local, dev, stream, seed, criteria=1.0):
         for _ in range(2):
             P.reduce_scatter_sum(torch.empty(w.numel() // world, dtype=torch.float64, device=dev), w)
         dist.reduce(bufs[0], dst=0)
-    for b in bufs:
-        b.zero_()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    loop = P.StoppingLoop(criteria, transport_pass, evaluate, threshold=0.5, max_passes=400, histories_per_pass=total)
-    tracked, current, passes = loop.run(bufs[1], bufs[2])
-    t1 = time.perf_counter()
-    if world > 1:
-        dist.reduce(bufs[0], dst=0, op=dist.ReduceOp.SUM)    # the dose travels once
-    torch.cuda.synchronize()
-    t2 = time.perf_counter()
-    tt = torch.tensor([t2 - t0, sum(kernel_ms) * 1e-3, loop.stat_seconds, t2 - t1], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_s, transport_s, stat_s, reduce_s = (float(x) for x in tt.tolist())
+    def timed_loop():
+        for b in bufs:
+            b.zero_()
+        del kernel_ms[:]
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        lp = P.StoppingLoop(criteria, transport_pass, evaluate, threshold=0.5, max_passes=400, histories_per_pass=total)
+        res = lp.run(bufs[1], bufs[2])
+        t1 = time.perf_counter()
+        if world > 1:
+            dist.reduce(bufs[0], dst=0, op=dist.ReduceOp.SUM)    # the dose travels once
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        tt = torch.tensor([t2 - t0, sum(kernel_ms) * 1e-3, lp.stat_seconds, t2 - t1], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return lp, res, [float(x) for x in tt.tolist()]
+
+    loop, (tracked, current, passes), (total_s, transport_s, stat_s, reduce_s) = timed_loop()
     checksum = float(bufs[0][:nvox].sum().item()) if rank == 0 else 0.0
+    reversed_fetch = None
+    if world > 1:   # the same loop with every launch handing out its histories last to first (option fetch_order): the plan is
+        eng.set_option("fetch_order", 1)   # listed by ascending energy, so the tail of each small launch is made of short histories
+        _, (tr2, cur2, p2), (tot2, trs2, _, _) = timed_loop()
+        eng.set_option("fetch_order", 0)
+        reversed_fetch = {"time_to_criterion_s": tot2, "transport_s": trs2, "passes": p2, "uncertainty_percent": cur2, "histories": tr2}
     eng.set_stream(None)
     eng.close()
     return {"workload": "C3: synthetic head-and-neck CT 512x512x200, %d-spot PBS plan, Dose + the two stat scorers, release physics, "
@@ -421,7 +431,8 @@ def strong_c3(rank, world, local, dev, stream, seed, criteria=1.0):
                            "of three doubles; once: ncclReduce of the dose grid" % (loop.collectives_per_pass, n_pad // P.StoppingLoop.CHUNK,
                                                                                    loop.exchanged_values, nvox))
                           if world > 1 else "none (1 GPU): the criterion is evaluated on the device where the grids are",
-            "timer": "host wall clock between device synchronisations and barriers, max over ranks; the phases by CUDA events on rank 0", "dose_checksum": checksum}
+            "timer": "host wall clock between device synchronisations and barriers, max over ranks; the phases by CUDA events on rank 0", "dose_checksum": checksum,
+            "reversed_fetch_order": reversed_fetch}
 
 
 def bench_b200(args):

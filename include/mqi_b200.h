@@ -193,7 +193,10 @@ MQI_API int mqi_get_run_stats(mqi_handle* h, mqi_run_stats* out);
  * 5 000-spot configuration),
  * "rsp_exact" (0/1: mqi_dev_rsp evaluates spr_default in the reference's own precision -- fp64 energy term, correctly
  * rounded pow -- and is then bit-exact against the reference; the transport kernel keeps the fp32 evaluation, within
- * 4 ulp, because the exact one costs 32 % of the C1 throughput (+46 % kernel time): DESIGN.md section 6) */
+ * 4 ulp, because the exact one costs 32 % of the C1 throughput (+46 % kernel time): DESIGN.md section 6),
+ * "fetch_order" (0 default / 1: a launch hands out its chunks of 32 histories first to last (0) or last to first (1), so that a
+ * plan listed by ascending energy starts its longest histories first and the tail of the persistent kernel is made of the
+ * short ones; the same histories with the same streams either way.  Measured slower on whole plans) */
 MQI_API int mqi_set_option(mqi_handle* h, const char* key, int64_t value);
 /* Launch on a caller-owned cudaStream_t (e.g. the framework's current stream, so that its events
  * bracket the kernels) instead of the handle's own stream; NULL restores the handle's stream.  The

@@ -815,8 +815,20 @@ refill_queue(const Params& P, uint32_t* q, int q_n) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(P.counters + C_NEXT, 32ull);
     base = __shfl_sync(0xffffffffu, base, 0);
-    // this launch's k-th fetch is chunk k * n_shards + shard of the range (n_shards = 1: chunk k)
-    base = (base * P.n_shards) + 32ull * P.shard;
+    // this launch's k-th fetch is chunk k * n_shards + shard of the range (n_shards = 1: chunk k) -- or, with P.reverse, the
+    // shard's chunks from the last to the first: a plan that lists its energy layers in ascending order then starts its
+    // longest histories first and its shortest last, which is what the tail of a persistent launch wants
+    bool exhausted;
+    if (P.reverse) {
+        const unsigned long long n_chunks = (P.count + 31ull) >> 5;
+        const unsigned long long mine     = n_chunks > P.shard ? (n_chunks - P.shard + P.n_shards - 1ull) / P.n_shards : 0ull;   // chunks of this shard
+        const unsigned long long k        = base >> 5;
+        exhausted = k + 1ull >= mine;
+        base      = k < mine ? ((mine - 1ull - k) * P.n_shards + P.shard) << 5 : P.count;
+    } else {
+        base      = (base * P.n_shards) + 32ull * P.shard;
+        exhausted = base + 32ull * P.n_shards >= P.count;   // the shard's next chunk lies beyond the range
+    }
     const unsigned long long i    = base + lane;
     const bool               have = i < P.count;
     bool     alive = false;
@@ -863,8 +875,7 @@ refill_queue(const Params& P, uint32_t* q, int q_n) {
         if (MULTI) e[Q_BLK * kQueueCap] = P.src.vertices ? 0u : 2u;   // blocks 0-1 belong to the source sampling
     }
     __syncwarp();
-    const int exhausted = base + 32ull * P.n_shards >= P.count ? 1 : 0;   // the shard's next chunk lies beyond the range
-    return (q_n + __popc(m)) | (exhausted << 16);
+    return (q_n + __popc(m)) | ((exhausted ? 1 : 0) << 16);
 }
 
 // further tries of the delta-electron energy rejection loop (about one event in ten needs them):

@@ -188,18 +188,27 @@ def test_dij_write_combining_changes_nothing_but_the_number_of_inserts():
     np.testing.assert_allclose(acc, dense_a, rtol=1e-9, atol=dense_a.max() * 1e-13)
 
 
-def test_interleaved_shards_tile_the_history_range():
+@pytest.mark.parametrize("fetch_order", [0, 1])
+def test_interleaved_shards_tile_the_history_range(fetch_order):
     """mqi_run_async_sharded: chunks of 32 histories dealt round-robin over n shards.  The shards together transport
     every history of the range exactly once with the streams of a single launch -- here all shards run one after the other on
-    one device -- and each shard sees the same mix of spots (the point of interleaving: a plan sorted by energy layer)."""
+    one device -- and each shard sees the same mix of spots (the point of interleaving: a plan sorted by energy layer).
+    Both fetch orders (option fetch_order: a launch's chunks first to last, or last to first so that the longest histories
+    of an ascending plan start first) transport the same histories: the reference dose is taken in forward order."""
     n_spots, per = 5, 1237          # a range that is not a multiple of 32 * shards
     n = n_spots * per
     bl = [capi.make_beamlet(70.0 + 20.0 * s, [(s - 2) * 6.0, 0, 0.5, 0, 0, -1], [3, 3, 0, 0, 0, 0], uniform=True) for s in range(n_spots)]
     e, (s_dose, s_dij) = engine(kinds=(capi.SCORER_DOSE, capi.SCORER_DIJ), capacity=2_000_003)
     e.set_beamlets(bl, [per] * n_spots)
+    e.set_option("fetch_order", 0)
     st = e.run(seed=9, first=100, count=n - 200, per_spot=True)
     full, full_keys = e.get_dense(s_dose).copy(), set(zip(*e.get_sparse(s_dij)[:2]))
     assert st.histories == n - 200
+    e.set_option("fetch_order", fetch_order)
+    e.clear_scorers()
+    st = e.run(seed=9, first=100, count=n - 200, per_spot=True)
+    assert st.histories == n - 200
+    np.testing.assert_allclose(e.get_dense(s_dose), full, rtol=1e-9, atol=full.max() * 1e-13)
     for shards in (2, 3, 8):
         e.clear_scorers()
         counts, rows = [], []
