@@ -115,10 +115,10 @@ class StoppingLoop:
         local value is at most threshold * m_r / world on EVERY rank r cannot qualify.  The grids are cut into chunks of
         CHUNK voxels and a chunk is kept if any rank holds a larger value in it (one max-all-reduce of the chunk flags,
         12 800 flags for a 512 x 512 x 200 grid; no exchange is needed for the bound itself);
-      * the kept chunks of sum d and sum d^2 are packed into one buffer and reduce-scattered (ONE collective: every link
+      * the kept chunks of sum d and sum d^2 are packed and reduce-scattered (one collective per grid: every link
         carries 1 / world of the packed values, all links at once) and every rank evaluates its slice: the largest mean
         dose (max-all-reduce of one double), then sum of sigma/mu and the voxel count (sum-all-reduce of two doubles).
-        Four collectives per pass; the phase times are taken with CUDA events, not host synchronisations.
+        Five collectives per pass; the phase times are taken with CUDA events, not host synchronisations.
 
     The selected voxels and the criterion are exactly those of an evaluation on whole summed grids; at config C3 the
     packed exchange is a few per cent of the grid.  The dose itself is reduced once, after the last pass.
@@ -210,17 +210,16 @@ class StoppingLoop:
             else:
                 idx, view = self.kept_chunks(total_sum, world)
                 t1 = self._mark(total_sum)
-                # the kept chunks of both grids in ONE buffer, rank r's share of sum d next to its share of sum d^2:
-                # one reduce-scatter leaves every rank with the summed values of 1 / world of the packed voxels
+                # the kept chunks of each grid packed; one reduce-scatter per grid leaves every rank with the summed values of
+                # 1 / world of the packed voxels
                 n_packed = int(idx.numel()) * self.CHUNK
                 per = n_packed // world
-                packed = torch.stack((view.index_select(0, idx).view(world, per),
-                                      total_sq.view(-1, self.CHUNK).index_select(0, idx).view(world, per)), dim=1).reshape(-1)
-                mine = torch.empty(2 * per, dtype=total_sum.dtype, device=total_sum.device)
-                reduce_scatter_sum(mine, packed, self.group)
-                s_sum, s_sq = mine[:per], mine[per:]
+                s_sum = torch.empty(per, dtype=total_sum.dtype, device=total_sum.device)
+                s_sq = torch.empty_like(s_sum)
+                reduce_scatter_sum(s_sum, view.index_select(0, idx).reshape(-1), self.group)
+                reduce_scatter_sum(s_sq, total_sq.view(-1, self.CHUNK).index_select(0, idx).reshape(-1), self.group)
                 t2 = self._mark(total_sum)
-                ncoll += 2
+                ncoll += 3
             mx = torch.tensor([self.evaluate(s_sum, s_sq, tracked, -1.0)[2] if per else 0.0], dtype=torch.float64, device=total_sum.device)
             if multi:
                 dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
