@@ -65,8 +65,13 @@
 #endif
 
 #ifndef MQI_K_PROBE_WIDTH
-#define MQI_K_PROBE_WIDTH 2  /* consecutive slots of the Dij table whose keys one probe step loads together (dij_probe_from); C4 at the
-                                reference's table size: 1: 6.3e7, 2: 8.4e7, 4: 7.3e7 histories/s (profiles/r2_experiments.md) */
+#define MQI_K_PROBE_WIDTH 1  /* slots of the Dij table whose keys the FIRST step of a probe sequence loads together (dij_probe_from) */
+#endif
+#ifndef MQI_K_PROBE_WIDTH2
+#define MQI_K_PROBE_WIDTH2 4 /* ... and every later step.  C4 at the reference's table size / at 1.6e9 slots, histories/s: every step
+                                1 slot 6.3e7, 2 slots 8.56e7 / 1.02e8, 4 slots 7.3e7; first step 1 slot and later steps 2: 8.61e7,
+                                3: 8.32e7, 4: 8.80e7 / 1.05e8 (kept), 5: 8.55e7, 6: 8.53e7 / 1.00e8, 8: 7.98e7; first 2 and later 4: 8.40e7,
+                                6: 8.26e7, 8: 7.86e7 (profiles/r2_experiments.md) */
 #endif
 
 #ifndef MQI_K_LATE_LUT

@@ -373,43 +373,59 @@ dense_add(double* __restrict__ acc, unsigned cnb, double v, int accum_mode) {
 // open-addressing (voxel, spot) -> dose table with a single 64-bit CAS per claim.  Same hash
 // function, home slot and linear probing as insert_hashtable (mqi_transport.hpp:68-111), so the set
 // of occupied keys is identical; the reference's two independent 32-bit CAS (race B5) are replaced.
-// Probing reads kProbeWidth (four) consecutive slots at once (independent loads, two or three 32-byte sectors) and then takes the
-// first one in probe order that is free or holds the key: the same slot linear probing ends in -- a slot seen
-// occupied by another key stays so (keys are never removed), a slot seen free is claimed through the CAS, which
-// reports whoever won it -- with one dependent memory round trip for 85 % of the inserts at load factor 0.73
-// instead of 2.4.  `probes` slots of the sequence have already been rejected by the caller.
+// A probe step reads the keys of several consecutive slots at once (independent loads) and takes the first one in probe
+// order that is free or holds the key: the same slot linear probing ends in -- a slot seen occupied by another key stays so
+// (keys are never removed), a slot seen free is claimed through the CAS, which reports whoever won it.  The first step of a
+// sequence looks at kProbeWidth slots (one: more than half of the inserts end at their home slot even at load factor 0.73) ...
 constexpr int kProbeWidth = MQI_K_PROBE_WIDTH;
+// ... and the later steps of a probe sequence kProbeWidth2 slots: the lanes of a warp that insert in a turn wait for the longest
+// probe sequence among them, and at load factor 0.73 that tail is long (mean 2.4 slots, but the longest of ten is ~ 12): the
+// unlucky pairs that are still looking after the first step take wider steps, the common case pays one load.
+constexpr int kProbeWidth2 = MQI_K_PROBE_WIDTH2;
+
+// one step of the probe sequence: the keys of W consecutive slots from `slot` (wrapping), loaded together; true if the pair
+// went into one of them
+template<int W>
+__device__ __forceinline__ bool
+dij_probe_step(DijSlot* table, unsigned long long capacity, unsigned long long& slot, unsigned long long key, double v) {
+    DijSlot*           e[W];
+    unsigned long long kk[W];
+    if (slot + W <= capacity) {   // no wrap-around inside this group (all but the last home slots)
+#pragma unroll
+        for (int i = 0; i < W; ++i) e[i] = table + slot + i;
+        slot = slot + W == capacity ? 0 : slot + W;
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            e[i] = table + slot;
+            slot = slot + 1 == capacity ? 0 : slot + 1;
+        }
+    }
+    // L2 is the point of coherence of the table (the CAS and the adds are performed there): a cache-global
+    // load sees every claimed key; a system-scope volatile load costs more and buys nothing
+#pragma unroll
+    for (int i = 0; i < W; ++i) kk[i] = __ldcg(&e[i]->key);
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        unsigned long long prev = kk[i];
+        if (prev == kEmptyKey64) prev = atomicCAS(&e[i]->key, kEmptyKey64, key);
+        if (prev == kEmptyKey64 || prev == key) {
+            red_add_f64(&e[i]->value, v);
+            return true;
+        }
+    }
+    return false;
+}
+
 __device__ __forceinline__ void
 dij_probe_from(DijSlot* table, unsigned long long capacity, unsigned long long slot, unsigned long long probes,
                unsigned long long key, double v, unsigned long long* counters) {
-    for (; probes < capacity; probes += kProbeWidth) {
-        DijSlot*           e[kProbeWidth];
-        unsigned long long kk[kProbeWidth];
-        if (slot + kProbeWidth <= capacity) {   // no wrap-around inside this group (all but the last home slots)
-#pragma unroll
-            for (int i = 0; i < kProbeWidth; ++i) e[i] = table + slot + i;
-            slot = slot + kProbeWidth == capacity ? 0 : slot + kProbeWidth;
-        } else {
-#pragma unroll
-            for (int i = 0; i < kProbeWidth; ++i) {
-                e[i] = table + slot;
-                slot = slot + 1 == capacity ? 0 : slot + 1;
-            }
-        }
-        // L2 is the point of coherence of the table (the CAS and the adds are performed there): a cache-global
-        // load sees every claimed key; a system-scope volatile load costs more and buys nothing
-#pragma unroll
-        for (int i = 0; i < kProbeWidth; ++i) kk[i] = __ldcg(&e[i]->key);
-#pragma unroll
-        for (int i = 0; i < kProbeWidth; ++i) {
-            unsigned long long prev = kk[i];
-            if (prev == kEmptyKey64) prev = atomicCAS(&e[i]->key, kEmptyKey64, key);
-            if (prev == kEmptyKey64 || prev == key) {
-                red_add_f64(&e[i]->value, v);
-                return;
-            }
-        }
+    if (probes < capacity) {
+        if (dij_probe_step<kProbeWidth>(table, capacity, slot, key, v)) return;
+        probes += kProbeWidth;
     }
+    for (; probes < capacity; probes += kProbeWidth2)
+        if (dij_probe_step<kProbeWidth2>(table, capacity, slot, key, v)) return;
     atomicAdd(counters + C_DIJ_FULL, 1ull);   // the reference would spin forever here
 }
 

@@ -18,6 +18,12 @@ VARIANTS = {
     "coop640_b2": (768, 1, 0, "-DMQI_K_BLOCK_DIJ=640", "-DMQI_K_DIJ_BATCHES=2"), "coop_t4b2": (768, 1, 0, "-DMQI_K_DIJ_TEAM=4", "-DMQI_K_DIJ_BATCHES=2"),
     "coop_t4b3": (768, 1, 0, "-DMQI_K_DIJ_TEAM=4", "-DMQI_K_DIJ_BATCHES=3"), "coop_t16": (768, 1, 0, "-DMQI_K_DIJ_TEAM=16", "-DMQI_K_DIJ_BATCHES=3"),
     "advmin16": (768, 1, 0, "-DMQI_K_ADV_MIN=16"), "advmin24": (768, 1, 0, "-DMQI_K_ADV_MIN=24"), "adv768": (768, 1, 0, "-DMQI_K_BLOCK_MULTI=768"),
+    "pw2_4": (768, 1, 0, "-DMQI_K_PROBE_WIDTH2=4"), "pw2_6": (768, 1, 0, "-DMQI_K_PROBE_WIDTH2=6"), "pw2_8": (768, 1, 0, "-DMQI_K_PROBE_WIDTH2=8"),
+    "pw1_4": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=1", "-DMQI_K_PROBE_WIDTH2=4"), "pw3_6": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=3", "-DMQI_K_PROBE_WIDTH2=6"),
+    "pw1_2": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=1", "-DMQI_K_PROBE_WIDTH2=2"), "pw1_3": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=1", "-DMQI_K_PROBE_WIDTH2=3"),
+    "pw1_5": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=1", "-DMQI_K_PROBE_WIDTH2=5"), "pw1_6": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=1", "-DMQI_K_PROBE_WIDTH2=6"),
+    "pw1_8": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=1", "-DMQI_K_PROBE_WIDTH2=8"),
+    "pw2_3": (768, 1, 0, "-DMQI_K_PROBE_WIDTH2=3"),
     "cur896": (768, 1, 0, "-DMQI_K_BLOCK_DIJ=896"), "cur1024": (768, 1, 0, "-DMQI_K_BLOCK_DIJ=1024"),
     "cur": (768, 1, 0), "ph10": (768, 1, 0, "-DMQI_K_PHILOX_ROUNDS=10"),
     "b256": (256, 4, 0), "b512": (512, 2, 0), "b128": (128, 8, 0), "b256_3": (256, 3, 0),
