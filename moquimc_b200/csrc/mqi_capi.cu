@@ -830,12 +830,17 @@ mqi_set_beamlets(mqi_handle* h, const mqi_beamlet* beamlets, uint32_t n_spots, c
         acc += histories_per_spot[i];
         cum[i] = acc;
     }
-    cudaFree(h->d_beamlets); cudaFree(h->d_cum);
-    h->d_beamlets = nullptr; h->d_cum = nullptr;
-    cudaFree(h->d_vertices); cudaFree(h->d_spot_ids);
-    h->d_vertices = nullptr; h->d_spot_ids = nullptr; h->n_vertices = 0;
-    CU(cudaMalloc(&h->d_beamlets, n_spots * sizeof(BeamletDev)));
-    CU(cudaMalloc(&h->d_cum, n_spots * sizeof(unsigned long long)));
+    // the buffers of the previous source go back to the handle's pool and come out of it again when the size is the same
+    // (a new batch of the same plan): cudaFree would wait for every kernel on the device, another handle's included
+    pool_free(h, h->d_beamlets, h->n_spots * sizeof(BeamletDev));
+    pool_free(h, h->d_cum, h->n_spots * sizeof(unsigned long long));
+    h->d_beamlets = nullptr; h->d_cum = nullptr; h->n_spots = 0;
+    if (h->d_vertices) {
+        cudaFree(h->d_vertices); cudaFree(h->d_spot_ids);
+        h->d_vertices = nullptr; h->d_spot_ids = nullptr; h->n_vertices = 0;
+    }
+    CU(pool_alloc(h, &h->d_beamlets, n_spots * sizeof(BeamletDev)));
+    CU(pool_alloc(h, &h->d_cum, n_spots * sizeof(unsigned long long)));
     CU(cudaMemcpyAsync(h->d_beamlets, beamlets, n_spots * sizeof(BeamletDev), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_cum, cum.data(), n_spots * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));

@@ -1388,7 +1388,10 @@ transport_kernel(const __grid_constant__ Params P) {
 // =============================================================================================
 // auxiliary kernels
 // =============================================================================================
-__global__ void
+// 128 threads of at most 32 registers: 4 096 registers per CTA, what a 768-thread transport CTA (80 registers) leaves free on an
+// SM -- so the conversion of the NEXT batch's HU volume (another handle, another stream) runs beside a resident transport
+// kernel instead of waiting for it, and the host call that uploads the volume returns while the kernel before is still busy.
+__global__ void __launch_bounds__(128, 16)
 hu_to_material_kernel(const int16_t* __restrict__ hu, uint16_t* __restrict__ mat, size_t n) {
     // 8 voxels (16 B) per thread per iteration, grid-stride
     const size_t n8 = n / 8;
@@ -1748,7 +1751,7 @@ launch_transport(const Params& p, int variant, int grid, size_t smem, cudaStream
 
 cudaError_t
 launch_hu_to_material(const int16_t* d_hu, uint16_t* d_mat, size_t n, cudaStream_t st) {
-    hu_to_material_kernel<<<grid_for(n / 8 + 1), 256, 0, st>>>(d_hu, d_mat, n);
+    hu_to_material_kernel<<<grid_for(n / 8 + 1, 128), 128, 0, st>>>(d_hu, d_mat, n);
     return cudaGetLastError();
 }
 cudaError_t
