@@ -74,6 +74,12 @@
                                 6: 8.26e7, 8: 7.86e7 (profiles/r2_experiments.md) */
 #endif
 
+#ifndef MQI_K_EXACT_DIV
+#define MQI_K_EXACT_DIV 1    /* 1: the three voxel-exit divisions of a step are correctly rounded (bit-exact geometry against the reference's
+                                CPU build); 0: rcp.approx * n as in the reference's own --use_fast_math CUDA build (measured: see
+                                profiles/r2_experiments.md) */
+#endif
+
 #ifndef MQI_K_LATE_LUT
 #define MQI_K_LATE_LUT 1   /* delay the material LUT load behind the step's random numbers (see mqi_transport.cu) */
 #endif

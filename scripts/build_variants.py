@@ -25,6 +25,7 @@ VARIANTS = {
     "pw1_8": (768, 1, 0, "-DMQI_K_PROBE_WIDTH=1", "-DMQI_K_PROBE_WIDTH2=8"),
     "pw2_3": (768, 1, 0, "-DMQI_K_PROBE_WIDTH2=3"),
     "m576": (768, 1, 0, "-DMQI_K_BLOCK_MULTI=576"), "m704": (768, 1, 0, "-DMQI_K_BLOCK_MULTI=704"),
+    "apxdiv": (768, 1, 0, "-DMQI_K_EXACT_DIV=0"),
     "cur896": (768, 1, 0, "-DMQI_K_BLOCK_DIJ=896"), "cur1024": (768, 1, 0, "-DMQI_K_BLOCK_DIJ=1024"),
     "cur": (768, 1, 0), "ph10": (768, 1, 0, "-DMQI_K_PHILOX_ROUNDS=10"),
     "b256": (256, 4, 0), "b512": (512, 2, 0), "b128": (128, 8, 0), "b256_3": (256, 3, 0),
