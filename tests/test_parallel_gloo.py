@@ -164,3 +164,59 @@ def test_stopping_loop_is_consistent_across_ranks(two_rank_outputs):
         sq += d2.reshape(-1)
     s, c, mx = numpy_criterion(torch.from_numpy(tot), torch.from_numpy(sq), int(tracked), float((tot / tracked).max()))
     np.testing.assert_allclose(current, 100.0 * s / c, rtol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------
+# the chunk selection with rank-local bounds (StoppingLoop.kept_chunks) on synthetic grids, four ranks
+# ------------------------------------------------------------------------------------------------
+def _selection_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        nvox = 40 * P.StoppingLoop.CHUNK + 123           # not a whole number of chunks: the buffers are padded
+        n_pad = P.StoppingLoop.padded_len(nvox)
+        # every rank has its own peak (height 1, in its own chunk) and a share of 0.3 of a common spot X in yet another chunk:
+        # X sums to 1.2, the largest value of the summed grid, but no rank holds threshold x ITS OWN largest value there
+        # (0.3 < 0.5 x 1); only the bound threshold / world x m_r (0.125) keeps its chunk
+        rng = np.random.default_rng(7 + rank)
+        x = np.arange(nvox, dtype=np.float64)
+        C = P.StoppingLoop.CHUNK
+        bump = lambda c, h: h * np.exp(-0.5 * ((x - c * C) / (0.05 * C)) ** 2)   # noqa: E731
+        local = rng.random(nvox)
+        d = (bump((5.5, 12.5, 20.5, 28.5)[rank], 1.0) + bump(35.5, 0.3)) * (0.95 + 0.1 * local)
+        ts, tq = torch.zeros(n_pad, dtype=torch.float64), torch.zeros(n_pad, dtype=torch.float64)
+        n_hist = 1000
+
+        def transport_pass(k):
+            ts[:nvox] += torch.from_numpy(d * n_hist)
+            tq[:nvox] += torch.from_numpy((3.0 * d * (1.0 + 0.2 * local)) * n_hist)   # E[x^2] > mean^2 everywhere: positive variances
+            return n_hist // world
+
+        loop = P.StoppingLoop(0.0, transport_pass, numpy_criterion, threshold=0.5, max_passes=2, histories_per_pass=n_hist)
+        tracked, current, passes = loop.run(ts, tq)
+        assert (passes, tracked, loop.collectives_per_pass) == (2, 2 * n_hist, 5), (passes, tracked, loop.collectives_per_pass, loop.history)
+        assert 0 < loop.exchanged_values < n_pad
+        full_s, full_q = ts.clone(), tq.clone()
+        dist.all_reduce(full_s)
+        dist.all_reduce(full_q)
+        if rank == 0:
+            np.save(os.path.join(out_dir, "sel.npy"), np.array([current, loop.exchanged_values, n_pad]))
+            np.save(os.path.join(out_dir, "sel_sum.npy"), full_s.numpy())
+            np.save(os.path.join(out_dir, "sel_sq.npy"), full_q.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_chunk_selection_with_local_bounds_is_exact_on_four_ranks(tmp_path):
+    """StoppingLoop keeps a chunk if ANY rank holds more than threshold / world x that rank's OWN largest value in it (no
+    exchange for the bound).  The synthetic grids are the case that loses voxels if the division by world is forgotten (the
+    hottest voxel of the sum is nobody's hot spot: checked by mutating the rule); the criterion must equal the evaluation on
+    the whole summed grids."""
+    out = str(tmp_path)
+    mp.spawn(_selection_worker, args=(4, 29500 + ((os.getpid() + 977) % 2000), out), nprocs=4, join=True)
+    current, exchanged, n_pad = np.load(os.path.join(out, "sel.npy"))
+    s, q = np.load(os.path.join(out, "sel_sum.npy")), np.load(os.path.join(out, "sel_sq.npy"))
+    n = 2000
+    ss, c, mx = numpy_criterion(torch.from_numpy(s), torch.from_numpy(q), n, float((s / n).max()))
+    assert c > 0 and exchanged < n_pad
+    np.testing.assert_allclose(current, 100.0 * ss / c, rtol=1e-10)
